@@ -1,0 +1,163 @@
+/* gim_b200.h -- C ABI of the B200-native GIM hot path (libgim_b200.so).
+ *
+ * The reference (roymor1/OptimalStrategiesAgainstGenerativeAttacks) has NO native/FFI layer: its hot
+ * path is eager PyTorch library calls.  Each entry point below replaces the torch/cuDNN/cuBLAS call(s)
+ * that the cited reference lines issue; the Python host code in
+ * optimalstrategiesagainstgenerativeattacks_b200/ binds them with ctypes and keeps
+ * the reference's nn.Module / trainer / checkpoint surface.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; every pointer is DEVICE memory owned by the caller;
+ *  - kernels never allocate, free or synchronise; they are enqueued on `stream` (CUDA-graph capturable);
+ *  - return 0 on success, a negative GIM_E_* code on failure (never throws); gim_last_error() gives text;
+ *  - activations are NHWC ("pixels x channels"), dtype GIM_F32 or GIM_BF16; statistics, weights' masters,
+ *    weight gradients, feature vectors [rows, dim] are always fp32;
+ *  - conv weights are "packed": [taps = k*k][Cout][Cin] (tap t = r*k + s), the K-major B operand of the
+ *    implicit GEMM; convs are stride 1, zero "same" padding (k odd) -- the only kind the reference uses
+ *    (model_blocks.py:492-495, 750-751, 792-793, 838-840).
+ * All file:line citations are relative to the reference root.
+ */
+#ifndef GIM_B200_H
+#define GIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gim_stream_t;             /* cudaStream_t */
+
+enum { GIM_F32 = 0, GIM_BF16 = 1 };
+enum { GIM_OK = 0, GIM_E_ARG = -1, GIM_E_CUDA = -2, GIM_E_UNSUPPORTED = -3 };
+enum { GIM_ALGO_AUTO = 0, GIM_ALGO_SIMT = 1, GIM_ALGO_TCGEN05 = 2 };
+
+int         gim_version(void);
+const char* gim_last_error(void);
+/* 1 if the tcgen05/TMA implicit-GEMM path can take this conv shape/dtype, else 0 */
+int         gim_conv2d_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype);
+/* counts kernel launches issued through this library since the last reset (bench.py `gpu_launches`) */
+long long   gim_launch_count(int reset);
+
+/* ---- convolution: nn.Conv2d forward / input-grad / weight-grad (model_blocks.py:497-514, 753-773, 795-865) ---- */
+/* y[n,h,w,co] = bias[co] + sum_{r,s,ci} x[n,h+r-p,w+s-p,ci] * w[r*k+s][co][ci];  x,y,w: dtype; bias fp32 or NULL */
+int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y,
+                   int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t stream);
+/* gw[t][co][ci] (fp32) = sum_{n,h,w} gy[n,h,w,co] * x[n,h+r-p,w+s-p,ci]  (overwrites gw) */
+int gim_conv2d_wgrad(const void* x, const void* gy, float* gw,
+                     int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t stream);
+/* w_fp32[t][co][ci] -> out[t][co][ci] (dtype)  /  flipped+transposed out[T-1-t][ci][co] (the dgrad operand) */
+int gim_weight_cast(const float* w, void* out, int taps, int cout, int cin, int dtype, gim_stream_t stream);
+int gim_weight_flip(const float* w, void* out, int taps, int cout, int cin, int dtype, gim_stream_t stream);
+/* out[c] (fp32) = sum_rows x[row][c]   (bias gradient; rows = n*h*w) */
+int gim_colsum(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t stream);
+
+/* ---- spectral norm: torch.nn.utils.spectral_norm hook, 1 power iteration (model_blocks.py:492-495 etc.) ---- */
+/* weight_orig [cout][cin][k][k] fp32; u[cout], v[cin*k*k] updated in place when power_iter!=0;
+ * writes w_sn (fp32 packed [taps][cout][cin]) = W/sigma, sigma (1 float), and copies u_used/v_used for backward.
+ * scratch: >= (cout + cin*k*k + 8) floats. */
+int gim_sn_forward(const float* weight_orig, float* u, float* v, int power_iter, float eps,
+                   float* w_sn, float* sigma, float* u_used, float* v_used, float* scratch,
+                   int cout, int cin, int ksize, gim_stream_t stream);
+/* g_weight_orig = (G - (sum G*W/sigma) u v^T) / sigma, G = unpacked g_w_sn */
+int gim_sn_backward(const float* g_w_sn, const float* weight_orig, const float* u_used, const float* v_used,
+                    const float* sigma, float* g_weight_orig, float* scratch,
+                    int cout, int cin, int ksize, gim_stream_t stream);
+
+/* ---- pointwise / resampling (model_blocks.py:489-490, 740, 744; gim_img_models.py:215) ---- */
+int gim_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, gim_stream_t stream);
+int gim_lrelu_bwd(const void* gy, const void* x, void* gx, long long n, float slope, int dtype, gim_stream_t stream);
+int gim_tanh_fwd(const void* x, void* y, long long n, int dtype, gim_stream_t stream);
+int gim_tanh_bwd(const void* gy, const void* y, void* gx, long long n, int dtype, gim_stream_t stream);
+/* out = alpha*x + beta*y (y may be NULL) */
+int gim_axpby(const void* x, const void* y, void* out, long long n, float alpha, float beta, int dtype, gim_stream_t stream);
+/* out = (*scalar)*x ; scalar is a device fp32 (SelfAttention gamma, model_blocks.py:548) */
+int gim_scale_dev(const void* x, const float* scalar, void* out, long long n, int dtype, gim_stream_t stream);
+/* out[0] (fp32, overwritten) = sum x*y */
+int gim_dot(const void* x, const void* y, float* out, long long n, int dtype, gim_stream_t stream);
+/* y[n,ho,wo,c] = scale * sum_{2x2} (a (+ b)) , ho=h/2, wo=wd/2 (floor)  -- AvgPool2d(2) (+ fused residual add) */
+int gim_pool2_sum(const void* a, const void* b, void* y, int n, int h, int wd, int c, float scale, int dtype, gim_stream_t stream);
+/* gx[n,h,w,c] = scale * gy[n,h/2,w/2,c] (0 where h/2>=ho or w/2>=wo) -- nearest Upsample x2 / AvgPool backward */
+int gim_unpool2_bcast(const void* gy, void* gx, int n, int h, int wd, int c, float scale, int dtype, gim_stream_t stream);
+/* layout + dtype conversion at the module boundary: NCHW fp32 <-> NHWC dtype */
+int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
+int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
+/* dst[row][dst_off + j] = src[row][src_off + j], j<c  (channel concat / split, gim_img_models.py:385) */
+int gim_copy_cols(const void* src, int src_ld, int src_off, void* dst, int dst_ld, int dst_off,
+                  long long rows, int c, int dtype, gim_stream_t stream);
+int gim_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, gim_stream_t stream);
+
+/* ---- InstanceNorm2d / ada_in (model_blocks.py:611-630, 747-748; gim_img_models.py:126) ---- */
+/* per (n,c): mean and M2 = sum (x-mean)^2 over the hw pixels */
+int gim_norm_stats(const void* x, float* mean, float* m2, int n, int hw, int c, int dtype, gim_stream_t stream);
+/* y = act(a[n,c]*x + b[n,c]),  act = LeakyReLU(slope) if slope != 1 */
+int gim_affine_act_fwd(const void* x, const float* a, const float* b, void* y, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
+/* s1[n,c] = sum gyh, s2[n,c] = sum gyh*(x-mean), gyh = gy * act'(y)   (y = forward output, NULL if no act) */
+int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, float* s1, float* s2,
+                        int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
+/* gx = A[n,c]*gyh + B[n,c]*(x-mean[n,c]) + C[n,c] */
+int gim_norm_bwd_apply(const void* gy, const void* x, const void* y, const float* mean, const float* A, const float* B, const float* C,
+                       void* gx, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
+/* coefficient kernels on [n,c] fp32 arrays.  mode 0 = InstanceNorm(weight[c],bias[c],eps: biased var),
+ * mode 1 = ada_in(std_style[n,c], mean_style[n,c], eps added to the unbiased std) */
+int gim_norm_coeffs(int mode, const float* mean, const float* m2, const float* p_scale, const float* p_shift,
+                    float* a, float* b, int n, int hw, int c, float eps, gim_stream_t stream);
+int gim_norm_bwd_coeffs(int mode, const float* m2, const float* s1, const float* s2, const float* p_scale,
+                        float* A, float* B, float* C, float* g_scale, float* g_shift,
+                        int n, int hw, int c, float eps, gim_stream_t stream);
+
+/* ---- small dense algebra (nn.Linear, torch.bmm, nn.Softmax: model_blocks.py:77-94, 541-545, 786-789) ---- */
+/* C[b] = alpha * A[b] x B[b] + beta * C[b]; element (m,k) of A[b] at A + b*sAb + m*sAm + k*sAk, etc. C is [m][n] with ldc */
+int gim_gemm_strided(const void* A, int dtA, long long sAb, long long sAm, long long sAk,
+                     const void* B, int dtB, long long sBb, long long sBk, long long sBn,
+                     void* C, int dtC, long long sCb, long long ldc,
+                     int m, int n, int k, int batch, float alpha, float beta, gim_stream_t stream);
+/* y[row][j] = x[row][j] + bias[j] ; act LeakyReLU(slope) if slope!=1 */
+int gim_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int c, float slope, gim_stream_t stream);
+int gim_softmax_rows_fwd(const float* x, float* y, long long rows, int cols, gim_stream_t stream);
+int gim_softmax_rows_bwd(const float* gy, const float* y, float* gx, long long rows, int cols, gim_stream_t stream);
+/* gradient of softmax_rows_bwd(gy,y) w.r.t. y given upstream ggx (R1 double backward) */
+int gim_softmax_rows_bwd_bwd(const float* ggx, const float* gy, const float* y, float* g_y, long long rows, int cols, gim_stream_t stream);
+
+/* ---- permutation-invariant set statistics over the sample axis (gim_basic_models.py:20-51, 152-172; model_blocks.py:41-48) ---- */
+/* x [b][s][d] fp32.  out_sum[b*ld + j] = scale * sum_s x ; out_std = sqrt(var_unbiased + eps) (zeros if s==1); either may be NULL */
+int gim_set_stats_fwd(const float* x, float* out_sum, float* out_std, int ld_out, int b, int s, int d, float scale, float eps, gim_stream_t stream);
+/* gx[b][s][d] = scale*g_sum[b][j] + g_std[b][j]*(x-mean)/((s-1)*std)   (g_* rows have stride ld_g; either may be NULL) */
+int gim_set_stats_bwd(const float* g_sum, const float* g_std, int ld_g, const float* x, float* gx, int b, int s, int d, float scale, float eps, gim_stream_t stream);
+/* second order of the std term: given ggx -> gg_std[b][d], g_x[b][s][d] */
+int gim_set_std_bwd_bwd(const float* ggx, const float* g_std, int ld_g, const float* x, float* gg_std, float* g_x, int b, int s, int d, float eps, gim_stream_t stream);
+/* y[b][s][d] = x - mean_s(x) (+ add[b][d] if add != NULL)   (gim_img_models.py:378-380, gim_gaussian_models.py:84-88) */
+int gim_set_center_add(const float* x, const float* add, float* y, int b, int s, int d, int center, gim_stream_t stream);
+
+/* ---- encoder tail: AdaptiveMaxPool2d((1,1)) (gim_img_models.py:53-54) ---- */
+int gim_gmax_fwd(const void* x, float* y, int32_t* idx, int n, int hw, int c, int dtype, gim_stream_t stream);
+int gim_gather_idx(const void* x, const int32_t* idx, float* y, int n, int hw, int c, int dtype, gim_stream_t stream);
+int gim_scatter_idx(const float* g, const int32_t* idx, void* gx, int n, int hw, int c, int dtype, gim_stream_t stream);
+
+/* ---- losses (gim_img_trainer.py:90-94; training/utils.py:115-124) ---- */
+int gim_bce_logits_fwd(const float* x, float target, float* loss, long long n, gim_stream_t stream);
+int gim_bce_logits_bwd(const float* g, const float* x, float target, float* gx, long long n, gim_stream_t stream);
+/* out[b] = sum_j x[b][j]^2 (fp32 out) ;  y[b][j] = alpha * s[b] * x[b][j] */
+int gim_rows_sqsum(const void* x, float* out, int b, long long l, int dtype, gim_stream_t stream);
+int gim_rows_scale(const void* x, const float* s, void* y, int b, long long l, float alpha, int dtype, gim_stream_t stream);
+
+/* ---- fused multi-tensor Adam (torch.optim.Adam at gim_img_trainer.py:50-58, gim_gaussian_trainer.py:48-49) ---- */
+typedef struct {
+    float*       p;      /* parameter */
+    const float* g;      /* gradient */
+    float*       m;      /* exp_avg */
+    float*       v;      /* exp_avg_sq */
+    long long    numel;
+    int          group;  /* index into lrs[] */
+    int          pad;
+} gim_adam_tensor;
+/* `table` and `lrs` are device arrays; `step` is a device int64 counter incremented by the kernel (bias
+ * corrections use step+1); grad_scale multiplies g first (1/world_size after an allreduce(sum)). */
+int gim_adam_multi(const gim_adam_tensor* table, int n_tensors, long long max_numel, const float* lrs,
+                   long long* step, float beta1, float beta2, float eps, float grad_scale, gim_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIM_B200_H */

@@ -1,0 +1,335 @@
+// CUDA-core (FFMA, fp32 accumulate) implicit-GEMM convolution: the fp32 parity path (rel 1e-4 gate) and the path for the
+// skinny layers (Cin <= 6 or Cout <= 3) that are HBM-bound and do not map onto 128xN tensor-core tiles.
+// The tensor-core path (conv_tc.cu, tcgen05 + TMEM + TMA) takes the dense bf16 layers.
+#include "common.cuh"
+
+namespace gim {
+
+constexpr int BK = 16;
+
+// y[pix][co] = bias[co] + sum_kf A(pix,kf) * w[tap(kf)][co][ci(kf)],  kf = tap*cin + ci flattened so tiny-Cin layers waste nothing.
+template <typename T, int BM, int BN>
+__global__ void __launch_bounds__(256) conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                                            T* __restrict__ y, int n, int h, int wd, int cin, int cout, int ks) {
+    static_assert((BM / 4) * (BN / 4) == 256, "tile must map onto 256 threads of 4x4 outputs");
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    __shared__ int pix_h[BM], pix_w[BM];
+    __shared__ long long pix_base[BM];
+
+    const int tid = threadIdx.x;
+    const int pad = (ks - 1) / 2;
+    const long long npix = (long long)n * h * wd;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int ktot = ks * ks * cin;
+
+    for (int m = tid; m < BM; m += 256) {
+        long long g = m0 + m;
+        if (g < npix) {
+            int ww = (int)(g % wd);
+            long long t = g / wd;
+            int hh = (int)(t % h);
+            long long img = t / h;
+            pix_h[m] = hh;
+            pix_w[m] = ww;
+            pix_base[m] = img * (long long)h * wd;
+        } else {
+            pix_h[m] = -100000;
+            pix_w[m] = 0;
+            pix_base[m] = 0;
+        }
+    }
+    __syncthreads();
+
+    const int ty = tid / (BN / 4), tx = tid % (BN / 4);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < ktot; k0 += BK) {
+        for (int e = tid; e < BM * BK; e += 256) {
+            int m = e / BK, kk = e % BK;
+            int kf = k0 + kk;
+            float v = 0.f;
+            if (kf < ktot) {
+                int tap = kf / cin, ci = kf - tap * cin;
+                int r = tap / ks, s = tap - r * ks;
+                int hh = pix_h[m] + r - pad, ww = pix_w[m] + s - pad;
+                if (hh >= 0 && hh < h && ww >= 0 && ww < wd) v = to_f<T>(x[(pix_base[m] + (long long)hh * wd + ww) * cin + ci]);
+            }
+            As[kk][m] = v;
+        }
+        for (int e = tid; e < BN * BK; e += 256) {
+            int c = e / BK, kk = e % BK;
+            int kf = k0 + kk, co = n0 + c;
+            float v = 0.f;
+            if (kf < ktot && co < cout) {
+                int tap = kf / cin, ci = kf - tap * cin;
+                v = to_f<T>(w[((long long)tap * cout + co) * cin + ci]);
+            }
+            Bs[kk][c] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        long long g = m0 + ty * 4 + i;
+        if (g >= npix) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = n0 + tx * 4 + j;
+            if (co < cout) y[g * cout + co] = from_f<T>(acc[i][j] + (bias ? bias[co] : 0.f));
+        }
+    }
+}
+
+// gw[tap][co][ci] += sum_{pix in split} gy[pix][co] * x[pix + tap][ci];  N index nf = tap*cin + ci flattened.
+template <typename T, int BM, int BN>
+__global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ gw, int n, int h,
+                                                              int wd, int cin, int cout, int ks, long long pix_per_split) {
+    static_assert((BM / 4) * (BN / 4) == 256, "tile must map onto 256 threads of 4x4 outputs");
+    __shared__ float As[BK][BM + 4];   // gy^T : [pixel][co]
+    __shared__ float Bs[BK][BN + 4];   // shifted x : [pixel][nf]
+    __shared__ int nf_dr[BN], nf_ds[BN], nf_ci[BN];
+
+    const int tid = threadIdx.x;
+    const int pad = (ks - 1) / 2;
+    const long long npix = (long long)n * h * wd;
+    const int co0 = blockIdx.x * BM;
+    const int nf0 = blockIdx.y * BN;
+    const int ntot = ks * ks * cin;
+    long long p_begin = (long long)blockIdx.z * pix_per_split;
+    long long p_end = p_begin + pix_per_split;
+    if (p_end > npix) p_end = npix;
+
+    for (int j = tid; j < BN; j += 256) {
+        int nf = nf0 + j;
+        if (nf < ntot) {
+            int tap = nf / cin;
+            nf_ci[j] = nf - tap * cin;
+            nf_dr[j] = tap / ks - pad;
+            nf_ds[j] = tap % ks - pad;
+        } else {
+            nf_ci[j] = -1;
+            nf_dr[j] = 0;
+            nf_ds[j] = 0;
+        }
+    }
+    __syncthreads();
+
+    const int ty = tid / (BN / 4), tx = tid % (BN / 4);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (long long p0 = p_begin; p0 < p_end; p0 += BK) {
+        for (int e = tid; e < BM * BK; e += 256) {
+            int kk = e / BM, m = e % BM;          // consecutive threads -> consecutive channels of one pixel (coalesced)
+            long long g = p0 + kk;
+            int co = co0 + m;
+            As[kk][m] = (g < p_end && co < cout) ? to_f<T>(gy[g * cout + co]) : 0.f;
+        }
+        for (int e = tid; e < BN * BK; e += 256) {
+            int kk = e / BN, j = e % BN;
+            long long g = p0 + kk;
+            float v = 0.f;
+            if (g < p_end && nf_ci[j] >= 0) {
+                int ww = (int)(g % wd);
+                long long t = g / wd;
+                int hh = (int)(t % h);
+                long long img = t / h;
+                hh += nf_dr[j];
+                ww += nf_ds[j];
+                if (hh >= 0 && hh < h && ww >= 0 && ww < wd) v = to_f<T>(x[((img * h + hh) * (long long)wd + ww) * cin + nf_ci[j]]);
+            }
+            Bs[kk][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int co = co0 + ty * 4 + i;
+        if (co >= cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int nf = nf0 + tx * 4 + j;
+            if (nf < ntot) {
+                int tap = nf / cin, ci = nf - tap * cin;
+                atomicAdd(&gw[((long long)tap * cout + co) * cin + ci], acc[i][j]);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) weight_cast_kernel(const float* __restrict__ w, T* __restrict__ out, long long total) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) out[i] = from_f<T>(w[i]);
+}
+
+// out[T-1-t][ci][co] = w[t][co][ci]
+template <typename T>
+__global__ void __launch_bounds__(256) weight_flip_kernel(const float* __restrict__ w, T* __restrict__ out, int taps, int cout, int cin) {
+    long long total = (long long)taps * cout * cin;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int co = (int)(i % cout);
+        long long r = i / cout;
+        int ci = (int)(r % cin);
+        int tf = (int)(r / cin);
+        out[i] = from_f<T>(w[((long long)(taps - 1 - tf) * cout + co) * cin + ci]);
+    }
+}
+
+// out[c] += sum over this CTA's rows; grid.x row chunks, grid.y channel chunks of 32; block (32, 8)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int c, long long rows_per_cta) {
+    __shared__ float sh[8][33];
+    int ch = blockIdx.y * 32 + threadIdx.x;
+    long long r0 = (long long)blockIdx.x * rows_per_cta;
+    long long r1 = r0 + rows_per_cta;
+    if (r1 > rows) r1 = rows;
+    float s = 0.f;
+    if (ch < c) for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += to_f<T>(x[r * c + ch]);
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && ch < c) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+        atomicAdd(&out[ch], t);
+    }
+}
+
+template <typename T>
+static int conv_fwd_simt(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
+    long long npix = (long long)n * h * wd;
+    if (cout <= 16) {
+        dim3 grid((unsigned)((npix + 255) / 256), (cout + 15) / 16);
+        conv_fwd_simt_kernel<T, 256, 16><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, (T*)y, n, h, wd, cin, cout, ks);
+    } else {
+        dim3 grid((unsigned)((npix + 63) / 64), (cout + 63) / 64);
+        conv_fwd_simt_kernel<T, 64, 64><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, (T*)y, n, h, wd, cin, cout, ks);
+    }
+    return check_launch("conv_fwd_simt");
+}
+
+template <typename T>
+static int conv_wgrad_simt(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
+    long long npix = (long long)n * h * wd;
+    int ntot = ks * ks * cin;
+    bool skinny = ntot <= 16;
+    int bm = skinny ? 256 : 64, bn = skinny ? 16 : 64;
+    int tiles = ((cout + bm - 1) / bm) * ((ntot + bn - 1) / bn);
+    long long want = ((long long)num_sms() * 4 + tiles - 1) / tiles;
+    long long max_split = (npix + 4 * BK - 1) / (4 * BK);
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    long long per = (npix + want - 1) / want;
+    per = (per + BK - 1) / BK * BK;
+    int splits = (int)((npix + per - 1) / per);
+    dim3 grid((cout + bm - 1) / bm, (ntot + bn - 1) / bn, splits);
+    if (skinny) conv_wgrad_simt_kernel<T, 256, 16><<<grid, 256, 0, st>>>((const T*)x, (const T*)gy, gw, n, h, wd, cin, cout, ks, per);
+    else conv_wgrad_simt_kernel<T, 64, 64><<<grid, 256, 0, st>>>((const T*)x, (const T*)gy, gw, n, h, wd, cin, cout, ks, per);
+    return check_launch("conv_wgrad_simt");
+}
+
+// implemented in conv_tc.cu
+int conv_fwd_tc(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st);
+int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st);
+bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
+bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
+
+}  // namespace gim
+
+using namespace gim;
+
+extern "C" {
+
+int gim_conv2d_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype) {
+    return conv_tc_supported(n, h, w, cin, cout, ksize, dtype) ? 1 : 0;
+}
+
+int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo,
+                   gim_stream_t s) {
+    GIM_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv2d_fwd: empty shape");
+    GIM_REQUIRE(ksize >= 1 && (ksize & 1), "conv2d_fwd: kernel size must be odd ('same' padding)");
+    GIM_REQUIRE((long long)n * h * wd / 64 + 1 < 2147483647LL, "conv2d_fwd: too many pixels");
+    cudaStream_t st = (cudaStream_t)s;
+    bool tc_ok = conv_tc_supported(n, h, wd, cin, cout, ksize, dtype);
+    if (algo == GIM_ALGO_TCGEN05 && !tc_ok) return fail(GIM_E_UNSUPPORTED, "conv2d_fwd: shape/dtype not supported by the tcgen05 path");
+    if ((algo == GIM_ALGO_TCGEN05) || (algo == GIM_ALGO_AUTO && tc_ok)) return conv_fwd_tc(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
+    GIM_DISPATCH_DTYPE(dtype, return conv_fwd_simt<T>(x, w, bias, y, n, h, wd, cin, cout, ksize, st));
+}
+
+int gim_conv2d_wgrad(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t s) {
+    GIM_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv2d_wgrad: empty shape");
+    GIM_REQUIRE(ksize >= 1 && (ksize & 1), "conv2d_wgrad: kernel size must be odd");
+    cudaStream_t st = (cudaStream_t)s;
+    bool tc_ok = wgrad_tc_supported(n, h, wd, cin, cout, ksize, dtype);
+    if (algo == GIM_ALGO_TCGEN05 && !tc_ok) return fail(GIM_E_UNSUPPORTED, "conv2d_wgrad: shape/dtype not supported by the tcgen05 path");
+    if (cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)ksize * ksize * cout * cin, st) != cudaSuccess) return fail(GIM_E_CUDA, "wgrad memset");
+    if ((algo == GIM_ALGO_TCGEN05) || (algo == GIM_ALGO_AUTO && tc_ok)) return conv_wgrad_tc(x, gy, gw, n, h, wd, cin, cout, ksize, st);
+    GIM_DISPATCH_DTYPE(dtype, return conv_wgrad_simt<T>(x, gy, gw, n, h, wd, cin, cout, ksize, st));
+}
+
+int gim_weight_cast(const float* w, void* out, int taps, int cout, int cin, int dtype, gim_stream_t s) {
+    long long total = (long long)taps * cout * cin;
+    if (total <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (weight_cast_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(w, (T*)out, total)));
+    return check_launch("weight_cast");
+}
+int gim_weight_flip(const float* w, void* out, int taps, int cout, int cin, int dtype, gim_stream_t s) {
+    long long total = (long long)taps * cout * cin;
+    if (total <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (weight_flip_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(w, (T*)out, taps, cout, cin)));
+    return check_launch("weight_flip");
+}
+int gim_colsum(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t s) {
+    if (c <= 0) return GIM_OK;
+    if (cudaMemsetAsync(out, 0, sizeof(float) * (size_t)c, (cudaStream_t)s) != cudaSuccess) return fail(GIM_E_CUDA, "colsum memset");
+    if (rows <= 0) return GIM_OK;
+    int cchunks = (c + 31) / 32;
+    long long want = ((long long)num_sms() * 4 + cchunks - 1) / cchunks;
+    long long maxc = (rows + 63) / 64;
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    long long per = (rows + want - 1) / want;
+    dim3 grid((unsigned)((rows + per - 1) / per), cchunks), block(32, 8);
+    GIM_DISPATCH_DTYPE(dtype, (colsum_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)x, out, rows, c, per)));
+    return check_launch("colsum");
+}
+
+}  // extern "C"

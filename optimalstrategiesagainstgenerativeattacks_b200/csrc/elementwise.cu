@@ -1,0 +1,271 @@
+// Pointwise, resampling and layout kernels (HBM-bound: 16-byte vector accesses, grid-stride, grids sized from the SM count).
+#include "common.cuh"
+
+namespace gim {
+
+thread_local char g_err[512] = "";
+long long g_launches = 0;
+
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void ld16(const T* p, float (&f)[16 / sizeof(T)]) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 16 / (int)sizeof(T); ++i) f[i] = to_f<T>(e[i]);
+}
+template <typename T>
+__device__ __forceinline__ void st16(T* p, const float (&f)[16 / sizeof(T)]) {
+    uint4 raw;
+    T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 16 / (int)sizeof(T); ++i) e[i] = from_f<T>(f[i]);
+    *reinterpret_cast<uint4*>(p) = raw;
+}
+
+// generic 1/2/3-input elementwise map with 16B vectors when all pointers are 16B aligned
+template <typename T, int NIN, typename F>
+__global__ void __launch_bounds__(256) map_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
+                                                  T* __restrict__ out, long long n, bool vec, F f) {
+    constexpr int V = Vec16<T>::N;
+    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    long long nv = vec ? n / V : 0;
+    for (long long i = tid; i < nv; i += stride) {
+        float fa[V], fb[V], fc[V], fo[V];
+        ld16<T>(a + i * V, fa);
+        if (NIN > 1) ld16<T>(b + i * V, fb);
+        if (NIN > 2) ld16<T>(c + i * V, fc);
+#pragma unroll
+        for (int j = 0; j < V; ++j) fo[j] = f(fa[j], NIN > 1 ? fb[j] : 0.f, NIN > 2 ? fc[j] : 0.f);
+        st16<T>(out + i * V, fo);
+    }
+    for (long long i = nv * V + tid; i < n; i += stride) {
+        float x = to_f<T>(a[i]);
+        float y = NIN > 1 ? to_f<T>(b[i]) : 0.f;
+        float z = NIN > 2 ? to_f<T>(c[i]) : 0.f;
+        out[i] = from_f<T>(f(x, y, z));
+    }
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <typename T, int NIN, typename F>
+static int launch_map(const void* a, const void* b, const void* c, void* out, long long n, cudaStream_t st, F f, const char* name) {
+    if (n <= 0) return GIM_OK;
+    bool vec = aligned16(a) && aligned16(out) && (NIN < 2 || aligned16(b)) && (NIN < 3 || aligned16(c));
+    int grid = ew_grid(n, 256, 2 * Vec16<T>::N);
+    map_kernel<T, NIN, F><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, (const T*)c, (T*)out, n, vec, f);
+    return check_launch(name);
+}
+
+struct LreluF { float s; __device__ float operator()(float x, float, float) const { return x > 0.f ? x : x * s; } };
+struct LreluB { float s; __device__ float operator()(float g, float x, float) const { return x > 0.f ? g : g * s; } };
+struct TanhF { __device__ float operator()(float x, float, float) const { return tanhf(x); } };
+struct TanhB { __device__ float operator()(float g, float y, float) const { return g * (1.f - y * y); } };
+struct Axpby { float a, b; __device__ float operator()(float x, float y, float) const { return a * x + b * y; } };
+struct Ax { float a; __device__ float operator()(float x, float, float) const { return a * x; } };
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_dev_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ out, long long n) {
+    float sc = *s;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = from_f<T>(sc * to_f<T>(x[i]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dot_kernel(const T* __restrict__ x, const T* __restrict__ y, float* __restrict__ out, long long n) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += to_f<T>(x[i]) * to_f<T>(y[i]);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// y[n,ho,wo,c] = scale * sum_{dy,dx in 2x2} (a + b)[n,2ho+dy,2wo+dx,c]
+template <typename T>
+__global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
+                                                    int n, int h, int w, int c, float scale) {
+    int ho = h / 2, wo = w / 2;
+    long long total = (long long)n * ho * wo * c;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % c);
+        long long p = i / c;
+        int x = (int)(p % wo); p /= wo;
+        int yy = (int)(p % ho);
+        long long img = p / ho;
+        long long base = ((img * h + 2 * yy) * w + 2 * x) * (long long)c + ch;
+        long long rs = (long long)w * c;
+        float s = to_f<T>(a[base]) + to_f<T>(a[base + c]) + to_f<T>(a[base + rs]) + to_f<T>(a[base + rs + c]);
+        if (b) s += to_f<T>(b[base]) + to_f<T>(b[base + c]) + to_f<T>(b[base + rs]) + to_f<T>(b[base + rs + c]);
+        y[i] = from_f<T>(scale * s);
+    }
+}
+
+// gx[n,h,w,c] = scale * gy[n,h/2,w/2,c] or 0 outside
+template <typename T>
+__global__ void __launch_bounds__(256) unpool2_kernel(const T* __restrict__ gy, T* __restrict__ gx, int n, int h, int w, int c, float scale) {
+    int ho = h / 2, wo = w / 2;
+    long long total = (long long)n * h * w * c;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % c);
+        long long p = i / c;
+        int x = (int)(p % w); p /= w;
+        int yy = (int)(p % h);
+        long long img = p / h;
+        float v = 0.f;
+        if ((yy >> 1) < ho && (x >> 1) < wo) v = scale * to_f<T>(gy[((img * ho + (yy >> 1)) * wo + (x >> 1)) * (long long)c + ch]);
+        gx[i] = from_f<T>(v);
+    }
+}
+
+// NCHW fp32 -> NHWC T via a 32x32 shared-memory transpose of the [C][HW] plane of each image
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int c, int hw) {
+    __shared__ float tile[32][33];
+    long long img = blockIdx.z;
+    int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* xi = x + img * (long long)c * hw;
+    T* yi = y + img * (long long)c * hw;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int cc = c0 + j, p = p0 + threadIdx.x;
+        tile[j][threadIdx.x] = (cc < c && p < hw) ? xi[(long long)cc * hw + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int p = p0 + j, cc = c0 + threadIdx.x;
+        if (p < hw && cc < c) yi[(long long)p * c + cc] = from_f<T>(tile[threadIdx.x][j]);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int c, int hw) {
+    __shared__ float tile[32][33];
+    long long img = blockIdx.z;
+    int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const T* xi = x + img * (long long)c * hw;
+    float* yi = y + img * (long long)c * hw;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int p = p0 + j, cc = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (p < hw && cc < c) ? to_f<T>(xi[(long long)p * c + cc]) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int cc = c0 + j, p = p0 + threadIdx.x;
+        if (cc < c && p < hw) yi[(long long)cc * hw + p] = tile[threadIdx.x][j];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy_cols_kernel(const T* __restrict__ src, int src_ld, int src_off, T* __restrict__ dst, int dst_ld,
+                                                        int dst_off, long long rows, int c) {
+    long long total = rows * c;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long r = i / c;
+        int j = (int)(i % c);
+        dst[r * dst_ld + dst_off + j] = src[r * src_ld + src_off + j];
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = from_f<TO>(to_f<TI>(x[i]));
+}
+
+}  // namespace gim
+
+using namespace gim;
+
+extern "C" {
+
+int gim_version(void) { return 100; }
+const char* gim_last_error(void) { return g_err; }
+long long gim_launch_count(int reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int gim_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, gim_stream_t s) {
+    GIM_DISPATCH_DTYPE(dtype, return (launch_map<T, 1>(x, nullptr, nullptr, y, n, (cudaStream_t)s, LreluF{slope}, "lrelu_fwd")));
+}
+int gim_lrelu_bwd(const void* gy, const void* x, void* gx, long long n, float slope, int dtype, gim_stream_t s) {
+    GIM_DISPATCH_DTYPE(dtype, return (launch_map<T, 2>(gy, x, nullptr, gx, n, (cudaStream_t)s, LreluB{slope}, "lrelu_bwd")));
+}
+int gim_tanh_fwd(const void* x, void* y, long long n, int dtype, gim_stream_t s) {
+    GIM_DISPATCH_DTYPE(dtype, return (launch_map<T, 1>(x, nullptr, nullptr, y, n, (cudaStream_t)s, TanhF{}, "tanh_fwd")));
+}
+int gim_tanh_bwd(const void* gy, const void* y, void* gx, long long n, int dtype, gim_stream_t s) {
+    GIM_DISPATCH_DTYPE(dtype, return (launch_map<T, 2>(gy, y, nullptr, gx, n, (cudaStream_t)s, TanhB{}, "tanh_bwd")));
+}
+int gim_axpby(const void* x, const void* y, void* out, long long n, float alpha, float beta, int dtype, gim_stream_t s) {
+    if (y) {
+        GIM_DISPATCH_DTYPE(dtype, return (launch_map<T, 2>(x, y, nullptr, out, n, (cudaStream_t)s, Axpby{alpha, beta}, "axpby")));
+    }
+    GIM_DISPATCH_DTYPE(dtype, return (launch_map<T, 1>(x, nullptr, nullptr, out, n, (cudaStream_t)s, Ax{alpha}, "ax")));
+}
+int gim_scale_dev(const void* x, const float* scalar, void* out, long long n, int dtype, gim_stream_t s) {
+    if (n <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (scale_dev_kernel<T><<<ew_grid(n, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, scalar, (T*)out, n)));
+    return check_launch("scale_dev");
+}
+int gim_dot(const void* x, const void* y, float* out, long long n, int dtype, gim_stream_t s) {
+    if (cudaMemsetAsync(out, 0, sizeof(float), (cudaStream_t)s) != cudaSuccess) return fail(GIM_E_CUDA, "dot memset");
+    if (n <= 0) return GIM_OK;
+    int grid = ew_grid(n, 256, 16);
+    if (grid > 2 * num_sms()) grid = 2 * num_sms();
+    GIM_DISPATCH_DTYPE(dtype, (dot_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)y, out, n)));
+    return check_launch("dot");
+}
+int gim_pool2_sum(const void* a, const void* b, void* y, int n, int h, int wd, int c, float scale, int dtype, gim_stream_t s) {
+    long long total = (long long)n * (h / 2) * (wd / 2) * c;
+    if (total <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (pool2_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (T*)y, n, h, wd, c, scale)));
+    return check_launch("pool2_sum");
+}
+int gim_unpool2_bcast(const void* gy, void* gx, int n, int h, int wd, int c, float scale, int dtype, gim_stream_t s) {
+    long long total = (long long)n * h * wd * c;
+    if (total <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (unpool2_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)gy, (T*)gx, n, h, wd, c, scale)));
+    return check_launch("unpool2_bcast");
+}
+int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t s) {
+    int hw = h * wd;
+    if (n <= 0 || c <= 0 || hw <= 0) return GIM_OK;
+    GIM_REQUIRE(n <= 65535 && (c + 31) / 32 <= 65535, "nchw_to_nhwc: batch/channels too large for one launch");
+    dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+    GIM_DISPATCH_DTYPE(dtype, (nchw_to_nhwc_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>(x, (T*)y, c, hw)));
+    return check_launch("nchw_to_nhwc");
+}
+int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int dtype, gim_stream_t s) {
+    int hw = h * wd;
+    if (n <= 0 || c <= 0 || hw <= 0) return GIM_OK;
+    GIM_REQUIRE(n <= 65535 && (c + 31) / 32 <= 65535, "nhwc_to_nchw: batch/channels too large for one launch");
+    dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+    GIM_DISPATCH_DTYPE(dtype, (nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)x, y, c, hw)));
+    return check_launch("nhwc_to_nchw");
+}
+int gim_copy_cols(const void* src, int src_ld, int src_off, void* dst, int dst_ld, int dst_off, long long rows, int c, int dtype, gim_stream_t s) {
+    long long total = rows * c;
+    if (total <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (copy_cols_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)src, src_ld, src_off, (T*)dst, dst_ld, dst_off, rows, c)));
+    return check_launch("copy_cols");
+}
+int gim_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, gim_stream_t s) {
+    if (n <= 0) return GIM_OK;
+    int grid = ew_grid(n, 256);
+    cudaStream_t st = (cudaStream_t)s;
+    if (dtype_in == GIM_F32 && dtype_out == GIM_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, n);
+    else if (dtype_in == GIM_BF16 && dtype_out == GIM_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)y, n);
+    else if (dtype_in == GIM_F32 && dtype_out == GIM_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
+    else if (dtype_in == GIM_BF16 && dtype_out == GIM_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, n);
+    else return fail(GIM_E_ARG, "cast: bad dtype");
+    return check_launch("cast");
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// InstanceNorm2d / ada_in as (statistics) + (per-(n,c) affine + LeakyReLU) so the apply step can later be folded into
+// the consumer conv's operand producer.  Statistics are always fp32; NHWC so a warp reads 32 adjacent channels.
+#include "common.cuh"
+
+namespace gim {
+
+// grid (ceil(c/32), n); block (32, 8).  Two passes over the (L2-resident) plane: exact mean, then M2.
+template <typename T>
+__global__ void __launch_bounds__(256) norm_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __restrict__ m2, int hw, int c) {
+    __shared__ float sh[8][33];
+    int ch = blockIdx.x * 32 + threadIdx.x;
+    long long img = blockIdx.y;
+    const T* xi = x + img * (long long)hw * c;
+    float s = 0.f;
+    if (ch < c) for (int p = threadIdx.y; p < hw; p += 8) s += to_f<T>(xi[(long long)p * c + ch]);
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    float mu = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mu += sh[j][threadIdx.x];
+    mu /= (float)hw;
+    __syncthreads();
+    float q = 0.f;
+    if (ch < c) for (int p = threadIdx.y; p < hw; p += 8) { float d = to_f<T>(xi[(long long)p * c + ch]) - mu; q += d * d; }
+    sh[threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0 && ch < c) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+        mean[img * c + ch] = mu;
+        m2[img * c + ch] = t;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                                                         T* __restrict__ y, long long total, int hw, int c, float slope) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    long long plane = (long long)hw * c;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % c);
+        long long k = (i / plane) * c + ch;
+        float v = a[k] * to_f<T>(x[i]) + b[k];
+        y[i] = from_f<T>(lrelu_f(v, slope));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ y,
+                                                              const float* __restrict__ mean, float* __restrict__ s1, float* __restrict__ s2,
+                                                              int hw, int c, float slope) {
+    __shared__ float sh1[8][33], sh2[8][33];
+    int ch = blockIdx.x * 32 + threadIdx.x;
+    long long img = blockIdx.y;
+    long long base = img * (long long)hw * c;
+    float a1 = 0.f, a2 = 0.f;
+    if (ch < c) {
+        float mu = mean[img * c + ch];
+        for (int p = threadIdx.y; p < hw; p += 8) {
+            long long i = base + (long long)p * c + ch;
+            float g = to_f<T>(gy[i]);
+            if (y != nullptr && !(to_f<T>(y[i]) > 0.f)) g *= slope;
+            a1 += g;
+            a2 += g * (to_f<T>(x[i]) - mu);
+        }
+    }
+    sh1[threadIdx.y][threadIdx.x] = a1;
+    sh2[threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0 && ch < c) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { t1 += sh1[j][threadIdx.x]; t2 += sh2[j][threadIdx.x]; }
+        s1[img * c + ch] = t1;
+        s2[img * c + ch] = t2;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ y,
+                                                             const float* __restrict__ mean, const float* __restrict__ A, const float* __restrict__ B,
+                                                             const float* __restrict__ C, T* __restrict__ gx, long long total, int hw, int c, float slope) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    long long plane = (long long)hw * c;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % c);
+        long long k = (i / plane) * c + ch;
+        float g = to_f<T>(gy[i]);
+        if (y != nullptr && !(to_f<T>(y[i]) > 0.f)) g *= slope;
+        gx[i] = from_f<T>(A[k] * g + B[k] * (to_f<T>(x[i]) - mean[k]) + C[k]);
+    }
+}
+
+__global__ void norm_coeffs_kernel(int mode, const float* __restrict__ mean, const float* __restrict__ m2, const float* __restrict__ p_scale,
+                                   const float* __restrict__ p_shift, float* __restrict__ a, float* __restrict__ b, int n, int hw, int c, float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    int ch = i % c;
+    float sc, sh, r;
+    if (mode == 0) {
+        r = rsqrtf(m2[i] / (float)hw + eps);
+        sc = p_scale[ch];
+        sh = p_shift[ch];
+    } else {
+        r = 1.f / (sqrtf(m2[i] / (float)(hw - 1)) + eps);
+        sc = p_scale[i];
+        sh = p_shift[i];
+    }
+    float aa = sc * r;
+    a[i] = aa;
+    b[i] = sh - mean[i] * aa;
+}
+
+__global__ void norm_bwd_coeffs_kernel(int mode, const float* __restrict__ m2, const float* __restrict__ s1, const float* __restrict__ s2,
+                                       const float* __restrict__ p_scale, float* __restrict__ A, float* __restrict__ B, float* __restrict__ C,
+                                       float* __restrict__ g_scale, float* __restrict__ g_shift, int n, int hw, int c, float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    int ch = i % c;
+    if (mode == 0) {
+        float r = rsqrtf(m2[i] / (float)hw + eps);
+        float w = p_scale[ch];
+        A[i] = w * r;
+        B[i] = -w * r * r * r * s2[i] / (float)hw;
+        C[i] = -w * r * s1[i] / (float)hw;
+    } else {
+        float sd = sqrtf(m2[i] / (float)(hw - 1));
+        float r = 1.f / (sd + eps);
+        float s = p_scale[i];
+        A[i] = s * r;
+        B[i] = sd > 0.f ? -r * r * s * s2[i] / ((float)(hw - 1) * sd) : 0.f;
+        C[i] = -s * r * s1[i] / (float)hw;
+        g_scale[i] = r * s2[i];
+        g_shift[i] = s1[i];
+    }
+}
+
+// InstanceNorm affine parameter gradients: reduce over the image axis (one thread per channel; n*c is tiny)
+__global__ void in_param_grad_kernel(const float* __restrict__ m2, const float* __restrict__ s1, const float* __restrict__ s2,
+                                     float* __restrict__ g_scale, float* __restrict__ g_shift, int n, int hw, int c, float eps) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    float gs = 0.f, gb = 0.f;
+    for (int img = 0; img < n; ++img) {
+        int i = img * c + ch;
+        gs += rsqrtf(m2[i] / (float)hw + eps) * s2[i];
+        gb += s1[i];
+    }
+    g_scale[ch] = gs;
+    g_shift[ch] = gb;
+}
+
+}  // namespace gim
+
+using namespace gim;
+
+extern "C" {
+
+int gim_norm_stats(const void* x, float* mean, float* m2, int n, int hw, int c, int dtype, gim_stream_t s) {
+    if (n <= 0 || c <= 0) return GIM_OK;
+    GIM_REQUIRE(hw >= 1 && n <= 65535, "norm_stats: bad shape");
+    dim3 grid((c + 31) / 32, n), block(32, 8);
+    GIM_DISPATCH_DTYPE(dtype, (norm_stats_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)x, mean, m2, hw, c)));
+    return check_launch("norm_stats");
+}
+int gim_affine_act_fwd(const void* x, const float* a, const float* b, void* y, int n, int hw, int c, float slope, int dtype, gim_stream_t s) {
+    long long total = (long long)n * hw * c;
+    if (total <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (affine_act_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, a, b, (T*)y, total, hw, c, slope)));
+    return check_launch("affine_act_fwd");
+}
+int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, float* s1, float* s2, int n, int hw, int c, float slope,
+                        int dtype, gim_stream_t s) {
+    if (n <= 0 || c <= 0) return GIM_OK;
+    GIM_REQUIRE(hw >= 1 && n <= 65535, "norm_bwd_reduce: bad shape");
+    dim3 grid((c + 31) / 32, n), block(32, 8);
+    GIM_DISPATCH_DTYPE(dtype, (norm_bwd_reduce_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)gy, (const T*)x, (const T*)y, mean, s1, s2, hw, c, slope)));
+    return check_launch("norm_bwd_reduce");
+}
+int gim_norm_bwd_apply(const void* gy, const void* x, const void* y, const float* mean, const float* A, const float* B, const float* C, void* gx,
+                       int n, int hw, int c, float slope, int dtype, gim_stream_t s) {
+    long long total = (long long)n * hw * c;
+    if (total <= 0) return GIM_OK;
+    GIM_DISPATCH_DTYPE(dtype, (norm_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)gy, (const T*)x, (const T*)y, mean, A, B, C,
+                                                                                                       (T*)gx, total, hw, c, slope)));
+    return check_launch("norm_bwd_apply");
+}
+int gim_norm_coeffs(int mode, const float* mean, const float* m2, const float* p_scale, const float* p_shift, float* a, float* b, int n, int hw, int c,
+                    float eps, gim_stream_t s) {
+    if (n * c <= 0) return GIM_OK;
+    GIM_REQUIRE(mode == 0 || hw > 1, "ada_in needs more than one pixel (unbiased std)");
+    norm_coeffs_kernel<<<(n * c + 255) / 256, 256, 0, (cudaStream_t)s>>>(mode, mean, m2, p_scale, p_shift, a, b, n, hw, c, eps);
+    return check_launch("norm_coeffs");
+}
+int gim_norm_bwd_coeffs(int mode, const float* m2, const float* s1, const float* s2, const float* p_scale, float* A, float* B, float* C,
+                        float* g_scale, float* g_shift, int n, int hw, int c, float eps, gim_stream_t s) {
+    if (n * c <= 0) return GIM_OK;
+    norm_bwd_coeffs_kernel<<<(n * c + 255) / 256, 256, 0, (cudaStream_t)s>>>(mode, m2, s1, s2, p_scale, A, B, C, g_scale, g_shift, n, hw, c, eps);
+    int rc = check_launch("norm_bwd_coeffs");
+    if (rc != GIM_OK || mode != 0) return rc;
+    in_param_grad_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(m2, s1, s2, g_scale, g_shift, n, hw, c, eps);
+    return check_launch("in_param_grad");
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+"""Image GIM networks -- same classes, constructor arguments, attribute names, forward signatures and state-dict schema as
+the reference's models/gim_img_models.py.  Module inputs/outputs are the reference's NCHW fp32 tensors; inside, activations
+are NHWC in the active precision and every op is a libgim_b200 kernel."""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import model_blocks as mb
+from . import ops
+from .gim_basic_models import GIMMeanStdFcStat
+
+
+def _as_nhwc(x):
+    """Accept the reference's NCHW fp32 image tensors at the module boundary; internal tensors are tagged NHWC."""
+    if isinstance(x, NHWC):
+        return x.t
+    return ops.to_nhwc(x)
+
+
+class NHWC:
+    """Marks an activation that is already in the internal NHWC layout (used between the kept-name modules)."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
+class Encoder(nn.Module):
+    """Reference gim_img_models.py:19-57: [N, C, S, S] -> [N, style_dim]."""
+
+    def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64, use_out_lrelu=True):
+        super().__init__()
+        self.img_size = img_size
+        self.img_channels = img_channels
+        self.style_dim = style_dim
+        self.use_out_lrelu = use_out_lrelu
+        self.n_down_blocks = int(math.log2(img_size)) - 2
+        self.min_n_channels = int(max(min_n_channels, style_dim / (2 ** (self.n_down_blocks - 1))))
+        self.channel_sizes = [img_channels] + [min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_down_blocks)]
+        self.att_loc = int(math.ceil(self.n_down_blocks / 2))
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.pool = nn.AdaptiveMaxPool2d((1, 1))
+        self.down_blocks = nn.ModuleList()
+        for i in range(self.n_down_blocks):
+            self.down_blocks.append(mb.ResBlockDown(self.channel_sizes[i], self.channel_sizes[i + 1]))
+        self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
+
+    def forward(self, x):
+        x = _as_nhwc(x)
+        for i in range(self.n_down_blocks):
+            if i == self.att_loc:
+                x = self.att(x)
+            x = self.down_blocks[i](x)
+        x = ops.GlobalMaxFn.apply(x)
+        if self.use_out_lrelu:
+            x = ops.lrelu(x)
+        return x
+
+
+class EnvDecoder(nn.Module):
+    """Reference gim_img_models.py:63-95: [N, style_dim] -> [N, C, S, S] (no output nonlinearity)."""
+
+    def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64):
+        super().__init__()
+        self.img_size = img_size
+        self.img_channels = img_channels
+        self.style_dim = style_dim
+        self.min_n_channels = min_n_channels
+        self.n_up_blocks = int(math.log2(img_size))
+        self.channel_sizes = list(
+            reversed([min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_up_blocks)])
+        ) + [img_channels]
+        self.att_loc = int(math.ceil(self.n_up_blocks / 2))
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.up_blocks = nn.ModuleList()
+        for i in range(self.n_up_blocks):
+            self.up_blocks.append(mb.ResBlockUp(self.channel_sizes[i], self.channel_sizes[i + 1]))
+        self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
+
+    def forward(self, x, nhwc_out=False):
+        n, c = x.shape
+        x = x.reshape(n, 1, 1, c)
+        if x.dtype != ops.act_dtype():
+            x = ops.to_nhwc(x.reshape(n, c, 1, 1))
+        for i in range(self.n_up_blocks):
+            if i == self.att_loc:
+                x = self.att(x)
+            x = self.up_blocks[i](x)
+        return NHWC(x) if nhwc_out else ops.from_nhwc(x)
+
+
+class Img2ImgDownModule(nn.Module):
+    """Reference gim_img_models.py:101-139."""
+
+    def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64):
+        super().__init__()
+        self.img_size = img_size
+        self.img_channels = img_channels
+        self.style_dim = style_dim
+        self.n_down_blocks = int(math.log2(img_size)) - 2
+        self.min_n_channels = int(max(min_n_channels, style_dim / (2 ** (self.n_down_blocks - 1))))
+        self.channel_sizes = [img_channels] + [min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_down_blocks)]
+        self.att_loc = int(math.ceil(self.n_down_blocks / 2))
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.pool = nn.AdaptiveMaxPool2d((1, 1))
+        self.down_blocks = nn.ModuleList()
+        self.in_layers = nn.ModuleList()
+        for i in range(self.n_down_blocks):
+            if i == 0:
+                self.down_blocks.append(mb.ResBlockDown(self.channel_sizes[i], self.channel_sizes[i + 1], conv_size=9, padding_size=4))
+            else:
+                self.down_blocks.append(mb.ResBlockDown(self.channel_sizes[i], self.channel_sizes[i + 1]))
+            self.in_layers.append(mb.InstanceNormAffine(self.channel_sizes[i + 1]))
+        self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
+
+    def forward(self, x):
+        for i in range(self.n_down_blocks):
+            if i == self.att_loc:
+                x = self.att(x)
+            x = self.down_blocks[i](x)
+            x = self.in_layers[i](x)
+        return x
+
+
+class Img2ImgAdaInResModule(nn.Module):
+    """Reference gim_img_models.py:142-162."""
+
+    def __init__(self, style_dim=512, n_blocks=5):
+        super().__init__()
+        self.style_dim = style_dim
+        self.n_blocks = n_blocks
+        self.res_blocks = nn.ModuleList()
+        for i in range(self.n_blocks):
+            self.res_blocks.append(mb.AdaResBlock2(channels=style_dim, style_dim=style_dim))
+
+    def forward(self, x, style):
+        for i in range(self.n_blocks):
+            x = self.res_blocks[i](x=x, style=style)
+        return x
+
+
+class Img2ImgAdaInUpModule(nn.Module):
+    """Reference gim_img_models.py:165-215 (tanh output)."""
+
+    def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64):
+        super().__init__()
+        self.img_size = img_size
+        self.img_channels = img_channels
+        self.style_dim = style_dim
+        self.n_up_blocks = int(math.log2(img_size)) - 2
+        self.min_n_channels = int(max(min_n_channels, style_dim / (2 ** (self.n_up_blocks - 1))))
+        self.channel_sizes = list(
+            reversed([min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_up_blocks)])
+        ) + [img_channels]
+        self.att_loc = int(math.ceil(self.n_up_blocks / 2))
+        self.up_blocks = nn.ModuleList()
+        for i in range(self.n_up_blocks):
+            last = i == (self.n_up_blocks - 1)
+            self.up_blocks.append(mb.AdaResBlockUp2(
+                in_channels=self.channel_sizes[i], out_channels=self.channel_sizes[i + 1], style_dim=style_dim,
+                conv_size=9 if last else 3, padding_size=4 if last else 1))
+        self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
+
+    def forward(self, x, style):
+        for i in range(self.n_up_blocks):
+            if i == self.att_loc:
+                x = self.att(x)
+            x = self.up_blocks[i](x=x, style=style)
+        return ops.TanhFn.apply(x)
+
+
+class AdaInImage2Image(nn.Module):
+    """Reference gim_img_models.py:218-257: [N, in_channels, S, S], style [N, style_dim] -> [N, out_channels, S, S]."""
+
+    def __init__(self, img_size, in_channels, out_channels, style_dim, n_adain_res_blocks=5, min_n_channels=64):
+        super().__init__()
+        self.img_size = img_size
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.style_dim = style_dim
+        self.n_adain_res_blocks = n_adain_res_blocks
+        self.min_n_channels = min_n_channels
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.sigmoid = nn.Sigmoid()
+        self.down_block = Img2ImgDownModule(img_size=img_size, img_channels=in_channels, style_dim=style_dim, min_n_channels=min_n_channels)
+        self.adain_res_block = Img2ImgAdaInResModule(style_dim=style_dim, n_blocks=n_adain_res_blocks)
+        self.adain_up_block = Img2ImgAdaInUpModule(img_size=img_size, img_channels=out_channels, style_dim=style_dim, min_n_channels=min_n_channels)
+
+    def forward(self, x, style):
+        x = _as_nhwc(x)
+        x = self.down_block(x)
+        x = self.adain_res_block(x=x, style=style)
+        x = self.adain_up_block(x=x, style=style)
+        return ops.from_nhwc(x)
+
+
+class GIMFaceDis(nn.Module):
+    """Reference gim_img_models.py:263-299."""
+
+    def __init__(self, src_dim, env_dim, stat):
+        super().__init__()
+        self.src_dim = src_dim
+        self.env_dim = env_dim
+        self.stat = stat
+        self.n_stats = stat.n_stats
+        mlp_input_dim = 2 * (self.n_stats * env_dim + src_dim)
+        self.mlp = mb.MLP((mlp_input_dim, env_dim + src_dim, 2 * (env_dim + src_dim), 1))
+        self.mlp.apply(mb.weights_init('kaiming'))
+
+    def forward(self, test_src, test_env, si_src, si_env):
+        test_src_mean = ops.set_mean(test_src)
+        si_src_mean = ops.set_mean(si_src)
+        test_env_stat = self.stat(test_env)
+        si_env_stat = self.stat(si_env)
+        x = torch.cat((test_src_mean, si_src_mean, test_env_stat, si_env_stat), dim=-1)
+        return self.mlp(x)
+
+
+class _EncodeMixin:
+    def _encode(self, encoder, sample):
+        batch_size, sample_size = sample.size(0), sample.size(1)
+        x = encoder(sample.reshape(batch_size * sample_size, *sample.size()[2:]))
+        return x.view(batch_size, sample_size, *x.size()[1:])
+
+    def src_encode_sample(self, sample):
+        return self._encode(self.src_encoder, sample)
+
+    def env_encode_sample(self, sample):
+        return self._encode(self.env_encoder, sample)
+
+
+class GIMFaceAuthenticator(nn.Module, _EncodeMixin):
+    """Reference gim_img_models.py:304-340."""
+
+    def __init__(self, src_encoder, env_encoder, dis):
+        super().__init__()
+        self.src_encoder = src_encoder
+        self.env_encoder = env_encoder
+        self.dis = dis
+
+    def forward(self, test_sample, si_sample):
+        test_src = self.src_encode_sample(test_sample)
+        si_src = self.src_encode_sample(si_sample)
+        test_env = self.env_encode_sample(test_sample)
+        si_env = self.env_encode_sample(si_sample)
+        return self.dis(test_src=test_src, test_env=test_env, si_src=si_src, si_env=si_env)
+
+
+class GIMFaceImpersonator(nn.Module, _EncodeMixin):
+    """Reference gim_img_models.py:346-423."""
+
+    def __init__(self, src_encoder, env_encoder, env_decoder, img2img, env_noise_mapper, use_img_att=False):
+        super().__init__()
+        self.src_encoder = src_encoder
+        self.env_encoder = env_encoder
+        self.env_decoder = env_decoder
+        self.img2img = img2img
+        self.env_noise_mapper = env_noise_mapper
+        self.style_dim = src_encoder.style_dim
+        assert src_encoder.style_dim == env_encoder.style_dim == env_decoder.style_dim == img2img.style_dim
+        self.use_img_att = use_img_att
+        self.img_att = mb.ImgAttention(img1_channels=self.src_encoder.img_channels, img2_channels=self.img2img.out_channels)
+
+    def forward(self, leaked_sample, n, remove_noise_mean=True):
+        batch_size, m, img_channels, img_size, _ = leaked_sample.size()
+        expanded_img = leaked_sample[:, 0].unsqueeze(1).expand(-1, n, -1, -1, -1)
+
+        src = ops.set_mean(self.src_encode_sample(leaked_sample))
+        env = ops.set_mean(self.env_encode_sample(leaked_sample))
+
+        z = torch.randn((batch_size, n, self.style_dim), device=leaked_sample.device)
+        w = self.env_noise_mapper(z)
+        noisy_env = ops.SetCenterAddFn.apply(w, env, bool(remove_noise_mean))
+
+        env_img = self.env_decoder(noisy_env.view(batch_size * n, self.style_dim), nhwc_out=True).t
+        exp_nhwc = ops.to_nhwc(expanded_img.reshape(batch_size * n, img_channels, img_size, img_size))
+        x = self.generate_img(env_img=NHWC(ops.CatChannelsFn.apply(env_img, exp_nhwc)), src=src, n=n)
+
+        if self.use_img_att:
+            x = self.img_att(x1=expanded_img.reshape(batch_size * n, *expanded_img.size()[2:]), x2=x.view(batch_size * n, *x.size()[2:]))
+            x = x.view(batch_size, n, *x.size()[1:])
+        return x
+
+    def generate_img(self, env_img, src, n=None):
+        if isinstance(env_img, NHWC):
+            batch_size = src.size(0)
+            x = env_img
+        else:
+            batch_size, n = env_img.size(0), env_img.size(1)
+            x = env_img.contiguous().view(batch_size * n, *env_img.size()[2:])
+        style = src.unsqueeze(1).expand(-1, n, -1).contiguous().view(batch_size * n, self.style_dim)
+        gen_img = self.img2img(x=x, style=style)
+        return gen_img.view(batch_size, n, *gen_img.size()[1:])
+
+
+def get_im(img_size, img_channels, style_dim, use_img_att=False, num_env_noise_layers=4):
+    """Reference gim_img_models.py:429-449."""
+    src_encoder = Encoder(img_size=img_size, img_channels=img_channels, style_dim=style_dim)
+    env_encoder = Encoder(img_size=img_size, img_channels=img_channels, style_dim=style_dim)
+    decoder = EnvDecoder(img_size=img_size, img_channels=img_channels, style_dim=style_dim)
+    img2img = AdaInImage2Image(img_size=img_size, in_channels=2 * img_channels, out_channels=img_channels, style_dim=style_dim)
+    env_noise_mapper = mb.MLP([style_dim for _ in range(num_env_noise_layers + 1)])
+    return GIMFaceImpersonator(src_encoder=src_encoder, env_encoder=env_encoder, env_decoder=decoder, img2img=img2img,
+                               env_noise_mapper=env_noise_mapper, use_img_att=use_img_att)
+
+
+def get_au(img_size, img_channels, style_dim):
+    """Reference gim_img_models.py:452-463."""
+    stat = GIMMeanStdFcStat(style_dim=style_dim, fc_n_stats=2, fc_hidden_layers=(style_dim * 2, style_dim * 3, style_dim * 2))
+    dis = GIMFaceDis(src_dim=style_dim, env_dim=style_dim, stat=stat)
+    src_encoder = Encoder(img_size=img_size, img_channels=img_channels, style_dim=style_dim)
+    env_encoder = Encoder(img_size=img_size, img_channels=img_channels, style_dim=style_dim)
+    return GIMFaceAuthenticator(src_encoder=src_encoder, env_encoder=env_encoder, dis=dis)

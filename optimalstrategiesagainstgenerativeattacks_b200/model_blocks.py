@@ -1,0 +1,280 @@
+"""Building blocks of the GIM image networks -- same constructors, attribute names and state-dict schema as the
+reference's models/model_blocks.py, every forward running on the libgim_b200 kernels (NHWC activations inside).
+
+Only the blocks the entry points instantiate are provided: weights_init, custom_std, MLP, ResBlockDown,
+SelfAttention, ImgAttConvBlock / ImgAttention (constructed for checkpoint parity), ada_in, ResBlockUp, AdaResBlock2,
+AdaResBlockUp2.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+SN_EPS = 1e-12
+
+
+def weights_init(init_type='kaiming'):
+    """Reference model_blocks.py:18-38 (applied to the discriminator MLPs with 'kaiming')."""
+    def init_fun(m):
+        if isinstance(m, (nn.Linear, SNConv2d)) and hasattr(m, 'weight'):
+            if init_type == 'gaussian':
+                nn.init.normal_(m.weight.data, 0.0, 0.02)
+            elif init_type == 'xavier':
+                nn.init.xavier_normal_(m.weight.data, gain=math.sqrt(2))
+            elif init_type == 'kaiming':
+                nn.init.kaiming_normal_(m.weight.data, a=0.2)
+            elif init_type == 'orthogonal':
+                nn.init.orthogonal_(m.weight.data, gain=math.sqrt(2))
+            elif init_type == 'default':
+                pass
+            else:
+                assert 0, "Unsupported initialization: {}".format(init_type)
+            if hasattr(m, 'bias') and m.bias is not None:
+                nn.init.constant_(m.bias.data, 0.0)
+    return init_fun
+
+
+def custom_std(x):
+    """Reference model_blocks.py:41-48 on [batch, sample, latent] fp32."""
+    return ops.set_std(x)
+
+
+def ada_in(feature, mean_style, std_style, eps=1e-5):
+    """Reference model_blocks.py:611-630; `feature` is an NHWC activation here, styles [batch, channels(,1)]."""
+    n, _, _, c = feature.shape
+    return ops.ada_in(feature, mean_style.reshape(n, c), std_style.reshape(n, c), eps)
+
+
+class Linear(nn.Linear):
+    """nn.Linear with the forward on the C-ABI GEMM (+ fused bias / LeakyReLU)."""
+
+    def forward(self, x, slope=1.0):
+        return ops.linear(x, self.weight, self.bias, slope)
+
+
+class MLP(nn.Module):
+    """Reference model_blocks.py:77-94: Linear / LeakyReLU(0.2) alternating, keys `model.{0,2,4,..}.{weight,bias}`."""
+
+    def __init__(self, layer_dims):
+        super().__init__()
+        assert len(layer_dims) >= 2
+        layers = []
+        inp_dim = layer_dims[0]
+        for out_dim in layer_dims[1:-1]:
+            layers.append(Linear(inp_dim, out_dim))
+            layers.append(nn.LeakyReLU(0.2))
+            inp_dim = out_dim
+        layers.append(Linear(inp_dim, layer_dims[-1]))
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x):
+        mods = list(self.model)
+        i = 0
+        while i < len(mods):
+            fused = i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU)
+            x = mods[i](x, mods[i + 1].negative_slope if fused else 1.0)
+            i += 2 if fused else 1
+        return x
+
+
+class SNConv2d(nn.Module):
+    """nn.utils.spectral_norm(nn.Conv2d(cin, cout, k, padding=(k-1)//2)) -- parameters `bias`, `weight_orig`, buffers
+    `weight_u`, `weight_v`, initialised with the same RNG draws as torch (Conv2d.reset_parameters, then u, v)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding=0):
+        super().__init__()
+        assert padding == (kernel_size - 1) // 2, "the GIM path only uses 'same' convolutions"
+        conv = nn.Conv2d(in_channels, out_channels, kernel_size, padding=padding)
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.bias = nn.Parameter(conv.bias.data)
+        self.weight_orig = nn.Parameter(conv.weight.data)
+        w = conv.weight.data
+        height, width = w.shape[0], w[0].numel()
+        u = F.normalize(w.new_empty(height).normal_(0, 1), dim=0, eps=SN_EPS)
+        v = F.normalize(w.new_empty(width).normal_(0, 1), dim=0, eps=SN_EPS)
+        self.register_buffer('weight_u', u)
+        self.register_buffer('weight_v', v)
+
+    def effective_weight(self):
+        """Packed fp32 [k*k, cout, cin] weight W/sigma; runs the power iteration when self.training."""
+        return ops.SpectralNormFn.apply(self.weight_orig, (self.weight_u, self.weight_v), self.training, SN_EPS)
+
+    def forward(self, x):
+        return ops.Conv2dFn.apply(x, self.effective_weight(), self.bias, self.kernel_size)
+
+
+class InstanceNormAffine(nn.Module):
+    """nn.InstanceNorm2d(channels, affine=True) (no running stats): keys `weight`, `bias`."""
+
+    def __init__(self, channels, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+
+    def forward(self, x, slope=1.0):
+        return ops.instance_norm(x, self.weight, self.bias, self.eps, slope)
+
+
+class ResBlockDown(nn.Module):
+    """Reference model_blocks.py:486-514.  AvgPool(left) + AvgPool(right) is one fused pool-of-sum kernel."""
+
+    def __init__(self, in_channel, out_channel, conv_size=3, padding_size=1):
+        super().__init__()
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.avg_pool2d = nn.AvgPool2d(2)
+        self.conv_l1 = SNConv2d(in_channel, out_channel, 1)
+        self.conv_r1 = SNConv2d(in_channel, out_channel, conv_size, padding=padding_size)
+        self.conv_r2 = SNConv2d(out_channel, out_channel, conv_size, padding=padding_size)
+
+    def forward(self, x):
+        out_res = self.conv_l1(x)
+        out = ops.lrelu(x)
+        out = self.conv_r1(out)
+        out = ops.lrelu(out)
+        out = self.conv_r2(out)
+        return ops.avg_pool2_add(out_res, out)
+
+
+class SelfAttention(nn.Module):
+    """Reference model_blocks.py:517-549 (softmax over the key axis, gamma * out + x)."""
+
+    def __init__(self, in_channel):
+        super().__init__()
+        self.conv_f = SNConv2d(in_channel, in_channel // 8, 1)
+        self.conv_g = SNConv2d(in_channel, in_channel // 8, 1)
+        self.conv_h = SNConv2d(in_channel, in_channel, 1)
+        self.softmax = nn.Softmax(-2)
+        self.gamma = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        n, h, w, c = x.shape
+        f = self.conv_f(x).reshape(n, h * w, -1)          # keys    [n, N, c/8]
+        g = self.conv_g(x).reshape(n, h * w, -1)          # queries [n, N, c/8]
+        hp = self.conv_h(x).reshape(n, h * w, c)          # values  [n, N, c]
+        p = ops.matmul(g, f, False, True, torch.float32)  # p[j, i] = <g_j, f_i> = attention_map[i, j]
+        a = ops.SoftmaxRowsFn.apply(p)                    # softmax over i  (reference: dim=-2 of [i, j])
+        out = ops.matmul(a, hp, False, False, x.dtype).reshape(n, h, w, c)
+        return ops.AddFn.apply(ops.ScaleDevFn.apply(out, self.gamma), x)
+
+
+class ImgAttConvBlock(nn.Module):
+    """Reference model_blocks.py:551-580 -- constructed for checkpoint parity; only runs when use_img_att=True."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.conv_l1 = SNConv2d(in_channels, out_channels, 1)
+        self.conv_r1 = SNConv2d(in_channels, out_channels, 9, padding=4)
+        self.conv_r2 = SNConv2d(out_channels, out_channels, 3, padding=1)
+
+    def forward(self, x):
+        out = self.conv_r1(ops.lrelu(x))
+        out = self.conv_r2(ops.lrelu(out))
+        return ops.AddFn.apply(self.conv_l1(x), out)
+
+
+class ImgAttention(nn.Module):
+    """Reference model_blocks.py:583-608.  The CLI default is use_img_att=False (train_gim_on_imgs.py); the blend itself
+    (channel dot products + 2-way softmax) is not on the north-star path and is not implemented."""
+
+    def __init__(self, img1_channels, img2_channels):
+        super().__init__()
+        self.q1conv = ImgAttConvBlock(img1_channels + img2_channels, img1_channels)
+        self.q2conv = ImgAttConvBlock(img1_channels + img2_channels, img1_channels)
+        self.k1conv = ImgAttConvBlock(img1_channels, img1_channels)
+        self.k2conv = ImgAttConvBlock(img2_channels, img1_channels)
+        self.v2conv = ImgAttConvBlock(img2_channels, img1_channels)
+
+    def forward(self, x1, x2):
+        raise NotImplementedError("use_img_att=True is outside the hot path this build covers (SURVEY.md section 2)")
+
+
+class ResBlockUp(nn.Module):
+    """Reference model_blocks.py:733-773.  conv_l1 is 1x1, so conv(up(x)) == up(conv(x)) pixel for pixel: the conv runs at
+    the low resolution (4x fewer FLOPs)."""
+
+    def __init__(self, in_channel, out_channel, out_size=None, scale=2, conv_size=3, padding_size=1, use_norm=True):
+        super().__init__()
+        assert out_size is None and scale == 2
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.upsample = nn.Upsample(size=out_size, scale_factor=scale)
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.conv_l1 = SNConv2d(in_channel, out_channel, 1)
+        self.in1 = InstanceNormAffine(in_channel)
+        self.in2 = InstanceNormAffine(out_channel)
+        self.conv_r1 = SNConv2d(in_channel, out_channel, conv_size, padding=padding_size)
+        self.conv_r2 = SNConv2d(out_channel, out_channel, conv_size, padding=padding_size)
+
+    def forward(self, x):
+        out_res = ops.upsample2(self.conv_l1(x))
+        out = self.in1(x, 0.2)
+        out = ops.upsample2(out)
+        out = self.conv_r1(out)
+        out = self.in2(out, 0.2)
+        out = self.conv_r2(out)
+        return ops.AddFn.apply(out, out_res)
+
+
+class AdaResBlock2(nn.Module):
+    """Reference model_blocks.py:776-814."""
+
+    def __init__(self, channels, style_dim):
+        super().__init__()
+        self.style_dim = style_dim
+        self.channels = channels
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.lin1_mean = Linear(style_dim, channels)
+        self.lin1_std = Linear(style_dim, channels)
+        self.lin2_mean = Linear(style_dim, channels)
+        self.lin2_std = Linear(style_dim, channels)
+        self.conv1 = SNConv2d(channels, channels, 3, padding=1)
+        self.conv2 = SNConv2d(channels, channels, 3, padding=1)
+
+    def forward(self, x, style):
+        mean_st1 = self.lin1_mean(style)
+        std_st1 = self.lin1_std(style)
+        mean_st2 = self.lin2_mean(style)
+        std_st2 = self.lin2_std(style)
+        out = self.conv1(x)
+        out = ops.ada_in(out, mean_st1, std_st1, 1e-5, 0.2)
+        out = self.conv2(out)
+        out = ops.ada_in(out, mean_st2, std_st2, 1e-5)
+        return ops.AddFn.apply(out, x)
+
+
+class AdaResBlockUp2(nn.Module):
+    """Reference model_blocks.py:817-865 (same 1x1-conv/upsample commutation as ResBlockUp)."""
+
+    def __init__(self, in_channels, out_channels, style_dim, out_size=None, scale=2, conv_size=3, padding_size=1):
+        super().__init__()
+        assert out_size is None and scale == 2
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.style_dim = style_dim
+        self.upsample = nn.Upsample(size=out_size, scale_factor=scale)
+        self.lrelu = nn.LeakyReLU(0.2)
+        self.lin1_mean = Linear(style_dim, in_channels)
+        self.lin1_std = Linear(style_dim, in_channels)
+        self.lin2_mean = Linear(style_dim, out_channels)
+        self.lin2_std = Linear(style_dim, out_channels)
+        self.conv_l1 = SNConv2d(in_channels, out_channels, 1)
+        self.conv_r1 = SNConv2d(in_channels, out_channels, conv_size, padding=padding_size)
+        self.conv_r2 = SNConv2d(out_channels, out_channels, conv_size, padding=padding_size)
+
+    def forward(self, x, style):
+        mean_st1 = self.lin1_mean(style)
+        std_st1 = self.lin1_std(style)
+        mean_st2 = self.lin2_mean(style)
+        std_st2 = self.lin2_std(style)
+        out_res = ops.upsample2(self.conv_l1(x))
+        out = ops.ada_in(x, mean_st1, std_st1, 1e-5, 0.2)
+        out = ops.upsample2(out)
+        out = self.conv_r1(out)
+        out = ops.ada_in(out, mean_st2, std_st2, 1e-5, 0.2)
+        out = self.conv_r2(out)
+        return ops.AddFn.apply(out, out_res)

@@ -1,0 +1,854 @@
+"""Differentiable operators of the GIM hot path, each a thin torch.autograd.Function over the C-ABI kernels.
+
+Design rule: the backward of every operator that sits on the authenticator path is itself written with these
+operators, so the set is closed under differentiation -- that is what lets `compute_grad2` (R1 penalty,
+training/utils.py:115-124 of the reference) build a second-order graph through hand-written kernels.
+  conv / conv-transpose / weight-grad   are closed among themselves,
+  pool2 <-> unpool2, gmax-scatter <-> gather, colsum <-> row-broadcast, set-sum <-> set-broadcast, matmul, scale/dot,
+  softmax and set-std carry an explicit second-order kernel.
+Operators that only occur in the attacker (InstanceNorm, ada_in, tanh, channel concat) are first order.
+
+Activations are NHWC tensors of the active precision (`set_precision`): float32 (parity path, CUDA-core FFMA) or
+bfloat16 (tcgen05 tensor-core path).  Feature vectors, statistics, weights and weight gradients are float32.
+"""
+import contextlib
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _cabi as C
+
+LRELU_SLOPE = 0.2
+_state = {"act_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False}
+
+
+def set_precision(name):
+    """'fp32' (rel 1e-4 parity path) or 'bf16' (tensor-core path, rel 2e-2)."""
+    _state["act_dtype"] = {"fp32": torch.float32, "bf16": torch.bfloat16}[name]
+
+
+def get_precision():
+    return "fp32" if _state["act_dtype"] == torch.float32 else "bf16"
+
+
+def act_dtype():
+    return _state["act_dtype"]
+
+
+def set_conv_algo(algo):
+    _state["conv_algo"] = {"auto": C.ALGO_AUTO, "simt": C.ALGO_SIMT, "tcgen05": C.ALGO_TCGEN05}[algo]
+
+
+@contextlib.contextmanager
+def input_grads_only():
+    """Inside, conv backward skips weight/bias gradients (used for the R1 input-gradient pass, whose weight
+    gradients nobody reads)."""
+    old = _state["input_grads_only"]
+    _state["input_grads_only"] = True
+    try:
+        yield
+    finally:
+        _state["input_grads_only"] = old
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# convolution triple
+# ------------------------------------------------------------------------------------------------------------
+def _weight_as(w32, dtype, flip):
+    taps, co, ci = w32.shape
+    if not flip and dtype == torch.float32:
+        return w32
+    out = _empty((taps, ci, co) if flip else (taps, co, ci), dtype, w32)
+    C.call("gim_weight_flip" if flip else "gim_weight_cast", C.ptr(w32), C.ptr(out), taps, co, ci, C.dtype_code(out))
+    return out
+
+
+def _conv_raw(x, w_t, bias, ks):
+    n, h, w, ci = x.shape
+    co = w_t.shape[1]
+    y = _empty((n, h, w, co), x.dtype, x)
+    C.call("gim_conv2d_fwd", C.ptr(x), C.ptr(w_t), C.ptr(bias), C.ptr(y), n, h, w, ci, co, ks, C.dtype_code(x), _state["conv_algo"])
+    return y
+
+
+class Conv2dFn(Function):
+    """y[n,h,w,co] = b[co] + sum x[n,h+r-p,w+s-p,ci] w[t,co,ci] -- nn.Conv2d(stride 1, 'same') of model_blocks.py:492-495."""
+
+    @staticmethod
+    def forward(ctx, x, w32, bias, ks):
+        x = _c(x)
+        w32 = _c(w32)
+        ctx.ks = ks
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w32)
+        return _conv_raw(x, _weight_as(w32, x.dtype, False), bias, ks)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w32 = ctx.saved_tensors
+        gy = _c(gy)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvTransposeFn.apply(gy, w32, ctx.ks)
+        if not _state["input_grads_only"]:
+            if ctx.needs_input_grad[1]:
+                gw = WgradFn.apply(x, gy, ctx.ks)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = ColSumFn.apply(gy)
+        return gx, gw, gb, None
+
+
+class ConvTransposeFn(Function):
+    """out[n,q,ci] = sum g[n,q-t,co] w[t,co,ci]  (the conv input-gradient) = conv(g, flip(w)^T)."""
+
+    @staticmethod
+    def forward(ctx, g, w32, ks):
+        g = _c(g)
+        w32 = _c(w32)
+        ctx.ks = ks
+        ctx.save_for_backward(g, w32)
+        return _conv_raw(g, _weight_as(w32, g.dtype, True), None, ks)
+
+    @staticmethod
+    def backward(ctx, gout):
+        g, w32 = ctx.saved_tensors
+        gout = _c(gout)
+        gg = gw = None
+        if ctx.needs_input_grad[0]:
+            gg = Conv2dFn.apply(gout, w32, None, ctx.ks)
+        if ctx.needs_input_grad[1]:
+            gw = WgradFn.apply(gout, g, ctx.ks)
+        return gg, gw, None
+
+
+class WgradFn(Function):
+    """gw[t,co,ci] = sum_{n,p} g[n,p,co] x[n,p+t,ci]  (fp32 out)."""
+
+    @staticmethod
+    def forward(ctx, x, g, ks):
+        x = _c(x)
+        g = _c(g)
+        ctx.ks = ks
+        ctx.save_for_backward(x, g)
+        n, h, w, ci = x.shape
+        co = g.shape[3]
+        gw = _empty((ks * ks, co, ci), torch.float32, x)
+        C.call("gim_conv2d_wgrad", C.ptr(x), C.ptr(g), C.ptr(gw), n, h, w, ci, co, ks, C.dtype_code(x), _state["conv_algo"])
+        return gw
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, g = ctx.saved_tensors
+        gout = _c(gout)
+        gx = gg = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvTransposeFn.apply(g, gout, ctx.ks)
+        if ctx.needs_input_grad[1]:
+            gg = Conv2dFn.apply(x, gout, None, ctx.ks)
+        return gx, gg, None
+
+
+class ColSumFn(Function):
+    """[..., c] -> fp32 [c] (bias gradients)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.shape = x.shape
+        ctx.dtype = x.dtype
+        c = x.shape[-1]
+        out = _empty((c,), torch.float32, x)
+        C.call("gim_colsum", C.ptr(x), C.ptr(out), x.numel() // c, c, C.dtype_code(x))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return RowBroadcastFn.apply(g, ctx.shape, ctx.dtype)
+
+
+class RowBroadcastFn(Function):
+    @staticmethod
+    def forward(ctx, v, shape, dtype):
+        out = v.to(dtype).expand(shape).contiguous()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ColSumFn.apply(g), None, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# spectral norm
+# ------------------------------------------------------------------------------------------------------------
+class SpectralNormFn(Function):
+    """weight_orig [co,ci,k,k] -> W/sigma packed fp32 [k*k,co,ci]; one power iteration in place on (u, v) when training.
+    torch.nn.utils.spectral_norm semantics (n_power_iterations=1, eps=1e-12, dim=0), u/v constants in the backward."""
+
+    @staticmethod
+    def forward(ctx, weight_orig, uv, training, eps):
+        u, v = uv                                   # buffers, passed in a tuple so autograd ignores them
+        co, ci, k, _ = weight_orig.shape
+        w = _c(weight_orig)
+        w_sn = _empty((k * k, co, ci), torch.float32, w)
+        aux = _empty((co + ci * k * k + 1,), torch.float32, w)      # u_used | v_used | sigma
+        scratch = _empty((co + ci * k * k + 8,), torch.float32, w)
+        u_used, v_used, sigma = aux[:co], aux[co:co + ci * k * k], aux[co + ci * k * k:]
+        C.call("gim_sn_forward", C.ptr(w), C.ptr(u), C.ptr(v), 1 if training else 0, eps, C.ptr(w_sn), sigma.data_ptr(),
+               u_used.data_ptr(), v_used.data_ptr(), C.ptr(scratch), co, ci, k)
+        ctx.save_for_backward(w, aux)
+        ctx.dims = (co, ci, k)
+        return w_sn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        w, aux = ctx.saved_tensors
+        co, ci, k = ctx.dims
+        g = _c(g)
+        gw = torch.empty_like(w)
+        scratch = _empty((8,), torch.float32, w)
+        j = ci * k * k
+        C.call("gim_sn_backward", C.ptr(g), C.ptr(w), aux[:co].data_ptr(), aux[co:co + j].data_ptr(), aux[co + j:].data_ptr(),
+               C.ptr(gw), C.ptr(scratch), co, ci, k)
+        return gw, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# pointwise / resampling / layout
+# ------------------------------------------------------------------------------------------------------------
+class LReluFn(Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = _c(x)
+        y = torch.empty_like(x)
+        C.call("gim_lrelu_fwd", C.ptr(x), C.ptr(y), x.numel(), slope, C.dtype_code(x))
+        ctx.slope = slope
+        ctx.save_for_backward(y)          # sign(y) == sign(x): keep the tensor the consumer keeps anyway
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return LReluBwdFn.apply(gy, y.detach(), ctx.slope), None
+
+
+class LReluBwdFn(Function):
+    """gx = g * (ref > 0 ? 1 : slope); piecewise linear => zero second derivative w.r.t. ref."""
+
+    @staticmethod
+    def forward(ctx, g, ref, slope):
+        g = _c(g)
+        gx = torch.empty_like(g)
+        C.call("gim_lrelu_bwd", C.ptr(g), C.ptr(ref), C.ptr(gx), g.numel(), slope, C.dtype_code(g))
+        ctx.slope = slope
+        ctx.save_for_backward(ref)
+        return gx
+
+    @staticmethod
+    def backward(ctx, gg):
+        (ref,) = ctx.saved_tensors
+        return LReluBwdFn.apply(gg, ref, ctx.slope), None, None
+
+
+def lrelu(x, slope=LRELU_SLOPE):
+    return LReluFn.apply(x, slope)
+
+
+class TanhFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        C.call("gim_tanh_fwd", C.ptr(x), C.ptr(y), x.numel(), C.dtype_code(x))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gy = _c(gy)
+        gx = torch.empty_like(gy)
+        C.call("gim_tanh_bwd", C.ptr(gy), C.ptr(y), C.ptr(gx), gy.numel(), C.dtype_code(gy))
+        return gx
+
+
+class AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a = _c(a)
+        b = _c(b)
+        out = torch.empty_like(a)
+        C.call("gim_axpby", C.ptr(a), C.ptr(b), C.ptr(out), a.numel(), 1.0, 1.0, C.dtype_code(a))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class ScaleDevFn(Function):
+    """y = s * x with s a 1-element fp32 device tensor (SelfAttention.gamma, model_blocks.py:548)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        x = _c(x)
+        y = torch.empty_like(x)
+        C.call("gim_scale_dev", C.ptr(x), C.ptr(s), C.ptr(y), x.numel(), C.dtype_code(x))
+        ctx.save_for_backward(x, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, s = ctx.saved_tensors
+        gx = ScaleDevFn.apply(gy, s) if ctx.needs_input_grad[0] else None
+        gs = DotFn.apply(gy, x).reshape(s.shape) if ctx.needs_input_grad[1] else None
+        return gx, gs
+
+
+class DotFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a = _c(a)
+        b = _c(b)
+        out = _empty((1,), torch.float32, a)
+        C.call("gim_dot", C.ptr(a), C.ptr(b), C.ptr(out), a.numel(), C.dtype_code(a))
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = _c(g.reshape(1).float())
+        ga = ScaleDevFn.apply(b, g) if ctx.needs_input_grad[0] else None
+        gb = ScaleDevFn.apply(a, g) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+class Pool2Fn(Function):
+    """y = scale * sum over 2x2 windows of (a [+ b]); AvgPool2d(2) with the residual add folded in (model_blocks.py:497-514)."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        a = _c(a)
+        n, h, w, c = a.shape
+        if b is not None:
+            b = _c(b)
+        y = _empty((n, h // 2, w // 2, c), a.dtype, a)
+        C.call("gim_pool2_sum", C.ptr(a), C.ptr(b), C.ptr(y), n, h, w, c, scale, C.dtype_code(a))
+        ctx.hw = (h, w)
+        ctx.scale = scale
+        ctx.two = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        g = Unpool2Fn.apply(gy, ctx.hw[0], ctx.hw[1], ctx.scale)
+        return g, (g if ctx.two else None), None
+
+
+class Unpool2Fn(Function):
+    """gx[n,h,w,c] = scale * g[n,h//2,w//2,c]: nearest Upsample(x2) (scale 1) and the AvgPool backward (scale 1/4)."""
+
+    @staticmethod
+    def forward(ctx, g, h, w, scale):
+        g = _c(g)
+        n, _, _, c = g.shape
+        gx = _empty((n, h, w, c), g.dtype, g)
+        C.call("gim_unpool2_bcast", C.ptr(g), C.ptr(gx), n, h, w, c, scale, C.dtype_code(g))
+        ctx.scale = scale
+        return gx
+
+    @staticmethod
+    def backward(ctx, gg):
+        return Pool2Fn.apply(gg, None, ctx.scale), None, None, None
+
+
+def avg_pool2_add(a, b=None):
+    return Pool2Fn.apply(a, b, 0.25)
+
+
+def upsample2(x):
+    return Unpool2Fn.apply(x, 2 * x.shape[1], 2 * x.shape[2], 1.0)
+
+
+class ToNHWCFn(Function):
+    """NCHW fp32 (the reference's tensor layout) -> NHWC activation dtype."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        x = _c(x.float())
+        n, c, h, w = x.shape
+        y = _empty((n, h, w, c), dtype, x)
+        C.call("gim_nchw_to_nhwc", C.ptr(x), C.ptr(y), n, c, h, w, C.dtype_code(y))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return FromNHWCFn.apply(g), None
+
+
+class FromNHWCFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        ctx.dtype = x.dtype
+        y = _empty((n, c, h, w), torch.float32, x)
+        C.call("gim_nhwc_to_nchw", C.ptr(x), C.ptr(y), n, c, h, w, C.dtype_code(x))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToNHWCFn.apply(g, ctx.dtype)
+
+
+def to_nhwc(x):
+    return ToNHWCFn.apply(x, act_dtype())
+
+
+def from_nhwc(x):
+    return FromNHWCFn.apply(x)
+
+
+class CatChannelsFn(Function):
+    """torch.cat((a, b), dim=channel) on NHWC tensors (gim_img_models.py:385)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a = _c(a)
+        b = _c(b)
+        ca, cb = a.shape[-1], b.shape[-1]
+        out = _empty(a.shape[:-1] + (ca + cb,), a.dtype, a)
+        rows = a.numel() // ca
+        C.call("gim_copy_cols", C.ptr(a), ca, 0, C.ptr(out), ca + cb, 0, rows, ca, C.dtype_code(a))
+        C.call("gim_copy_cols", C.ptr(b), cb, 0, C.ptr(out), ca + cb, ca, rows, cb, C.dtype_code(a))
+        ctx.split = (ca, cb)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = _c(g)
+        ca, cb = ctx.split
+        rows = g.numel() // (ca + cb)
+        ga = _empty(g.shape[:-1] + (ca,), g.dtype, g)
+        gb = _empty(g.shape[:-1] + (cb,), g.dtype, g)
+        C.call("gim_copy_cols", C.ptr(g), ca + cb, 0, C.ptr(ga), ca, 0, rows, ca, C.dtype_code(g))
+        C.call("gim_copy_cols", C.ptr(g), ca + cb, ca, C.ptr(gb), cb, 0, rows, cb, C.dtype_code(g))
+        return ga, gb
+
+
+# ------------------------------------------------------------------------------------------------------------
+# InstanceNorm2d / ada_in (attacker only: first order)
+# ------------------------------------------------------------------------------------------------------------
+class _NormFn(Function):
+    """mode 0: InstanceNorm2d(affine, eps in the rsqrt, biased var) -- model_blocks.py:747-748, gim_img_models.py:126.
+    mode 1: ada_in (unbiased std + eps) -- model_blocks.py:611-630.  Optional fused LeakyReLU(slope)."""
+
+    @staticmethod
+    def forward(ctx, x, p_scale, p_shift, mode, eps, slope):
+        x = _c(x)
+        n, h, w, c = x.shape
+        hw = h * w
+        p_scale = _c(p_scale.float())
+        p_shift = _c(p_shift.float())
+        st = _empty((4, n, c), torch.float32, x)          # mean | m2 | a | b
+        C.call("gim_norm_stats", C.ptr(x), st[0].data_ptr(), st[1].data_ptr(), n, hw, c, C.dtype_code(x))
+        C.call("gim_norm_coeffs", mode, st[0].data_ptr(), st[1].data_ptr(), C.ptr(p_scale), C.ptr(p_shift),
+               st[2].data_ptr(), st[3].data_ptr(), n, hw, c, eps)
+        y = torch.empty_like(x)
+        C.call("gim_affine_act_fwd", C.ptr(x), st[2].data_ptr(), st[3].data_ptr(), C.ptr(y), n, hw, c, slope, C.dtype_code(x))
+        ctx.cfg = (mode, eps, slope)
+        ctx.save_for_backward(x, y, st, p_scale)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, y, st, p_scale = ctx.saved_tensors
+        mode, eps, slope = ctx.cfg
+        gy = _c(gy)
+        n, h, w, c = x.shape
+        hw = h * w
+        yref = C.ptr(y) if slope != 1.0 else None
+        red = _empty((5, n, c), torch.float32, x)         # s1 | s2 | A | B | C
+        C.call("gim_norm_bwd_reduce", C.ptr(gy), C.ptr(x), yref, st[0].data_ptr(), red[0].data_ptr(), red[1].data_ptr(),
+               n, hw, c, slope, C.dtype_code(x))
+        if mode == 0:
+            g_scale = _empty((c,), torch.float32, x)
+            g_shift = _empty((c,), torch.float32, x)
+        else:
+            g_scale = _empty((n, c), torch.float32, x)
+            g_shift = _empty((n, c), torch.float32, x)
+        C.call("gim_norm_bwd_coeffs", mode, st[1].data_ptr(), red[0].data_ptr(), red[1].data_ptr(), C.ptr(p_scale),
+               red[2].data_ptr(), red[3].data_ptr(), red[4].data_ptr(), C.ptr(g_scale), C.ptr(g_shift), n, hw, c, eps)
+        gx = torch.empty_like(x)
+        C.call("gim_norm_bwd_apply", C.ptr(gy), C.ptr(x), yref, st[0].data_ptr(), red[2].data_ptr(), red[3].data_ptr(),
+               red[4].data_ptr(), C.ptr(gx), n, hw, c, slope, C.dtype_code(x))
+        return gx, g_scale, g_shift, None, None, None
+
+
+def instance_norm(x, weight, bias, eps=1e-5, slope=1.0):
+    return _NormFn.apply(x, weight, bias, 0, eps, slope)
+
+
+def ada_in(x, mean_style, std_style, eps=1e-5, slope=1.0):
+    return _NormFn.apply(x, std_style, mean_style, 1, eps, slope)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# small dense algebra
+# ------------------------------------------------------------------------------------------------------------
+def _mm_raw(a, b, ta, tb, out_dtype):
+    a = _c(a)
+    b = _c(b)
+    batched = a.dim() == 3
+    if not batched:
+        a3, b3 = a.unsqueeze(0), b.unsqueeze(0)
+    else:
+        a3, b3 = a, b
+    bt = a3.shape[0]
+    m, k = (a3.shape[2], a3.shape[1]) if ta else (a3.shape[1], a3.shape[2])
+    k2, n = (b3.shape[2], b3.shape[1]) if tb else (b3.shape[1], b3.shape[2])
+    if k != k2 or b3.shape[0] != bt:
+        raise RuntimeError("matmul shape mismatch %s %s" % (tuple(a.shape), tuple(b.shape)))
+    out = _empty((bt, m, n), out_dtype, a)
+    lda, ldb = a3.shape[2], b3.shape[2]
+    sam, sak = (1, lda) if ta else (lda, 1)
+    sbk, sbn = (1, ldb) if tb else (ldb, 1)
+    C.call("gim_gemm_strided", C.ptr(a3), C.dtype_code(a3), a3.shape[1] * a3.shape[2], sam, sak,
+           C.ptr(b3), C.dtype_code(b3), b3.shape[1] * b3.shape[2], sbk, sbn,
+           C.ptr(out), C.dtype_code(out), m * n, n, m, n, k, bt, 1.0, 0.0)
+    return out if batched else out[0]
+
+
+class MatMulFn(Function):
+    """C = op(A) @ op(B), 2-D or batched 3-D, mixed fp32/bf16 operands, fp32 accumulation."""
+
+    @staticmethod
+    def forward(ctx, a, b, ta, tb, out_dtype):
+        ctx.cfg = (ta, tb)
+        ctx.save_for_backward(a, b)
+        return _mm_raw(a, b, ta, tb, out_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ta, tb = ctx.cfg
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            if not ta:
+                ga = MatMulFn.apply(g, b, False, not tb, a.dtype)
+            else:
+                ga = MatMulFn.apply(b, g, tb, True, a.dtype)
+        if ctx.needs_input_grad[1]:
+            if not tb:
+                gb = MatMulFn.apply(a, g, not ta, False, b.dtype)
+            else:
+                gb = MatMulFn.apply(g, a, True, ta, b.dtype)
+        return ga, gb, None, None, None
+
+
+def matmul(a, b, ta=False, tb=False, out_dtype=torch.float32):
+    return MatMulFn.apply(a, b, ta, tb, out_dtype)
+
+
+class BiasActFn(Function):
+    """y = LeakyReLU_slope(x + bias) on fp32 [rows, c] (slope 1 = no activation)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, slope):
+        x = _c(x)
+        y = torch.empty_like(x)
+        c = x.shape[-1]
+        C.call("gim_bias_act_fwd", C.ptr(x), C.ptr(bias), C.ptr(y), x.numel() // c, c, slope)
+        ctx.slope = slope
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        g = gy if ctx.slope == 1.0 else LReluBwdFn.apply(gy, y.detach(), ctx.slope)
+        gb = ColSumFn.apply(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        return g, gb, None
+
+
+def linear(x, weight, bias, slope=1.0):
+    """nn.Linear (+ optional LeakyReLU) on the last dim; x fp32 [..., in]."""
+    shp = x.shape
+    y = matmul(x.reshape(-1, shp[-1]), weight, False, True)
+    y = BiasActFn.apply(y, bias, slope)
+    return y.reshape(shp[:-1] + (weight.shape[0],))
+
+
+class SoftmaxRowsFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        cols = x.shape[-1]
+        C.call("gim_softmax_rows_fwd", C.ptr(x), C.ptr(y), x.numel() // cols, cols)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return SoftmaxBwdFn.apply(gy, y)
+
+
+class SoftmaxBwdFn(Function):
+    """gx = y * (g - sum(g*y)); symmetric in g, explicit kernel for d/dy."""
+
+    @staticmethod
+    def forward(ctx, g, y):
+        g = _c(g)
+        gx = torch.empty_like(g)
+        cols = g.shape[-1]
+        C.call("gim_softmax_rows_bwd", C.ptr(g), C.ptr(y), C.ptr(gx), g.numel() // cols, cols)
+        ctx.save_for_backward(g, y)
+        return gx
+
+    @staticmethod
+    def backward(ctx, gg):
+        g, y = ctx.saved_tensors
+        gg = _c(gg)
+        d_g = SoftmaxBwdFn.apply(gg, y) if ctx.needs_input_grad[0] else None
+        d_y = None
+        if ctx.needs_input_grad[1]:
+            d_y = _SoftmaxBwdBwdY.apply(gg, g, y)
+        return d_g, d_y
+
+
+class _SoftmaxBwdBwdY(Function):
+    @staticmethod
+    def forward(ctx, gg, g, y):
+        out = torch.empty_like(y)
+        cols = y.shape[-1]
+        C.call("gim_softmax_rows_bwd_bwd", C.ptr(_c(gg)), C.ptr(_c(g)), C.ptr(y), C.ptr(out), y.numel() // cols, cols)
+        return out
+
+    @staticmethod
+    def backward(ctx, *a):
+        raise RuntimeError("third-order derivative through softmax is not implemented (not needed by the GIM path)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# set statistics over the sample axis
+# ------------------------------------------------------------------------------------------------------------
+class SetSumFn(Function):
+    """[b, s, d] -> scale * sum_s  (mean when scale = 1/s): GIMMeanStat gim_basic_models.py:28-34."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = _c(x)
+        b, s, d = x.shape
+        out = _empty((b, d), torch.float32, x)
+        C.call("gim_set_stats_fwd", C.ptr(x), C.ptr(out), None, d, b, s, d, scale, 0.0)
+        ctx.s = s
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return SetBroadcastFn.apply(g, ctx.s, ctx.scale), None
+
+
+class SetBroadcastFn(Function):
+    @staticmethod
+    def forward(ctx, g, s, scale):
+        g = _c(g)
+        b, d = g.shape
+        dummy = g                                            # x is only read when g_std is given
+        out = _empty((b, s, d), torch.float32, g)
+        C.call("gim_set_stats_bwd", C.ptr(g), None, d, C.ptr(dummy), C.ptr(out), b, s, d, scale, 0.0)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, gg):
+        return SetSumFn.apply(gg, ctx.scale), None, None
+
+
+class SetStdFn(Function):
+    """custom_std model_blocks.py:41-48: sqrt(var_unbiased + 1e-8), zeros if the set has one element."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = _c(x)
+        b, s, d = x.shape
+        out = _empty((b, d), torch.float32, x)
+        C.call("gim_set_stats_fwd", C.ptr(x), None, C.ptr(out), d, b, s, d, 1.0, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return SetStdBwdFn.apply(g, x, ctx.eps), None
+
+
+class SetStdBwdFn(Function):
+    @staticmethod
+    def forward(ctx, g, x, eps):
+        g = _c(g)
+        b, s, d = x.shape
+        gx = torch.empty_like(x)
+        C.call("gim_set_stats_bwd", None, C.ptr(g), d, C.ptr(x), C.ptr(gx), b, s, d, 1.0, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(g, x)
+        return gx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ggx):
+        g, x = ctx.saved_tensors
+        b, s, d = x.shape
+        ggx = _c(ggx)
+        gg_std = torch.empty_like(g)
+        g_x = torch.empty_like(x)
+        C.call("gim_set_std_bwd_bwd", C.ptr(ggx), C.ptr(g), d, C.ptr(x), C.ptr(gg_std), C.ptr(g_x), b, s, d, ctx.eps)
+        return gg_std, g_x, None
+
+
+def set_mean(x):
+    return SetSumFn.apply(x, 1.0 / x.shape[1])
+
+
+def set_std(x, eps=1e-8):
+    return SetStdFn.apply(x, eps)
+
+
+class SetCenterAddFn(Function):
+    """y = x - mean_s(x) (if center) + add[:, None]  (gim_img_models.py:378-380; gim_gaussian_models.py:84-88)."""
+
+    @staticmethod
+    def forward(ctx, x, add, center):
+        x = _c(x)
+        b, s, d = x.shape
+        y = torch.empty_like(x)
+        C.call("gim_set_center_add", C.ptr(x), C.ptr(_c(add)) if add is not None else None, C.ptr(y), b, s, d, 1 if center else 0)
+        ctx.center = center
+        ctx.has_add = add is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = SetCenterAddFn.apply(g, None, True) if ctx.center else g
+        ga = SetSumFn.apply(g, 1.0) if (ctx.has_add and ctx.needs_input_grad[1]) else None
+        return gx, ga, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# encoder tail, losses
+# ------------------------------------------------------------------------------------------------------------
+class GlobalMaxFn(Function):
+    """AdaptiveMaxPool2d((1,1)) + flatten (gim_img_models.py:53-54): NHWC activation -> fp32 [n, c]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = _empty((n, c), torch.float32, x)
+        idx = _empty((n, c), torch.int32, x)
+        C.call("gim_gmax_fwd", C.ptr(x), C.ptr(y), C.ptr(idx), n, h * w, c, C.dtype_code(x))
+        ctx.shape = x.shape
+        ctx.dtype = x.dtype
+        ctx.idx = idx
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return ScatterIdxFn.apply(g, ctx.idx, ctx.shape, ctx.dtype)
+
+
+class ScatterIdxFn(Function):
+    @staticmethod
+    def forward(ctx, g, idx, shape, dtype):
+        g = _c(g)
+        n, h, w, c = shape
+        gx = _empty(shape, dtype, g)
+        C.call("gim_scatter_idx", C.ptr(g), C.ptr(idx), C.ptr(gx), n, h * w, c, C.dtype_code(gx))
+        ctx.idx = idx
+        return gx
+
+    @staticmethod
+    def backward(ctx, gg):
+        return GatherIdxFn.apply(gg, ctx.idx), None, None, None
+
+
+class GatherIdxFn(Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = _empty((n, c), torch.float32, x)
+        C.call("gim_gather_idx", C.ptr(x), C.ptr(idx), C.ptr(y), n, h * w, c, C.dtype_code(x))
+        ctx.idx = idx
+        ctx.shape = x.shape
+        ctx.dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return ScatterIdxFn.apply(g, ctx.idx, ctx.shape, ctx.dtype), None
+
+
+class BCEWithLogitsFn(Function):
+    """F.binary_cross_entropy_with_logits(x, full(target), reduction='none') -- gan_loss gim_img_trainer.py:90-94."""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        x = _c(x)
+        loss = torch.empty_like(x)
+        C.call("gim_bce_logits_fwd", C.ptr(x), float(target), C.ptr(loss), x.numel())
+        ctx.target = float(target)
+        ctx.save_for_backward(x)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _c(g)
+        gx = torch.empty_like(x)
+        C.call("gim_bce_logits_bwd", C.ptr(g), C.ptr(x), ctx.target, C.ptr(gx), x.numel())
+        return gx, None
+
+
+class RowsSqSumFn(Function):
+    """[b, ...] -> fp32 [b] sum of squares per episode (compute_grad2 training/utils.py:122)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        b = x.shape[0]
+        out = _empty((b,), torch.float32, x)
+        C.call("gim_rows_sqsum", C.ptr(x), C.ptr(out), b, x.numel() // b, C.dtype_code(x))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _c(g.float())
+        b = x.shape[0]
+        gx = torch.empty_like(x)
+        C.call("gim_rows_scale", C.ptr(x), C.ptr(g), C.ptr(gx), b, x.numel() // b, 2.0, C.dtype_code(x))
+        return gx

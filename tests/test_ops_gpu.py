@@ -1,0 +1,312 @@
+"""GPU: every C-ABI operator (forward, backward and -- on the authenticator path -- double backward) against a float64
+torch-CPU statement of the same op.  fp32 gate 1e-4 (north_star), bf16 gate 2e-2."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(autouse=True)
+def _cuda_only():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from optimalstrategiesagainstgenerativeattacks_b200 import ops
+    ops.set_precision("fp32")
+    ops.set_conv_algo("auto")
+    yield
+    ops.set_precision("fp32")
+    ops.set_conv_algo("auto")
+
+
+def ops_mod():
+    from optimalstrategiesagainstgenerativeattacks_b200 import ops
+    return ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g, dtype=torch.float64) * scale)
+
+
+def to_dev_nhwc(x64, dtype):
+    """NCHW float64 CPU -> NHWC device tensor (leaf)."""
+    return x64.permute(0, 2, 3, 1).contiguous().to("cuda", dtype).requires_grad_()
+
+
+def nchw(t):
+    return t.detach().double().cpu().permute(0, 3, 1, 2)
+
+
+def pack_w(w64):
+    """OIHW -> packed fp32 [k*k, co, ci]."""
+    co, ci, k, _ = w64.shape
+    return w64.permute(2, 3, 0, 1).reshape(k * k, co, ci).contiguous().to("cuda", torch.float32).requires_grad_()
+
+
+def unpack_w(gw, k):
+    taps, co, ci = gw.shape
+    return gw.detach().double().cpu().reshape(k, k, co, ci).permute(2, 3, 0, 1)
+
+
+CONV_SHAPES = [  # n, ci, co, k, h, w
+    (2, 3, 64, 3, 16, 16), (3, 64, 64, 3, 8, 8), (2, 6, 64, 9, 16, 16), (2, 64, 3, 9, 16, 16), (2, 64, 16, 1, 7, 5),
+    (1, 1, 128, 3, 32, 32), (5, 128, 128, 3, 4, 4), (2, 64, 128, 3, 13, 13), (130, 32, 8, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_fwd_bwd_double_bwd(shape, prec, tol):
+    ops = ops_mod()
+    ops.set_precision(prec)
+    dt = ops.act_dtype()
+    n, ci, co, k, h, w = shape
+    x64 = rnd(n, ci, h, w, seed=1).requires_grad_()
+    w64 = (rnd(co, ci, k, k, seed=2) / np.sqrt(ci * k * k)).requires_grad_()
+    b64 = rnd(co, seed=3, scale=0.1).requires_grad_()
+    probe = rnd(n, co, h, w, seed=4)
+    y64 = F.conv2d(x64, w64, b64, padding=(k - 1) // 2)
+    # first order + an R1-style second-order term: || d(sum(y*probe))/dx ||^2
+    (gx64,) = torch.autograd.grad((y64 * probe).sum(), x64, create_graph=True)
+    total64 = (y64 * probe).sum() + 0.5 * gx64.pow(2).sum()
+    gX, gW, gB = torch.autograd.grad(total64, (x64, w64, b64))
+
+    x = to_dev_nhwc(x64.detach(), dt)
+    wp = pack_w(w64.detach())
+    b = b64.detach().to("cuda", torch.float32).requires_grad_()
+    pr = probe.permute(0, 2, 3, 1).contiguous().to("cuda", dt)
+    y = ops.Conv2dFn.apply(x, wp, b, k)
+    assert rel_err(nchw(y), y64) < tol
+    s = ops.DotFn.apply(y, pr)
+    (gx,) = torch.autograd.grad(s.sum(), x, create_graph=True)
+    assert rel_err(nchw(gx), gx64) < tol
+    total = s.sum() + 0.5 * ops.RowsSqSumFn.apply(gx.reshape(1, -1)).sum()
+    dX, dW, dB = torch.autograd.grad(total, (x, wp, b))
+    assert rel_err(nchw(dX), gX) < tol
+    assert rel_err(unpack_w(dW, k), gW) < tol
+    assert rel_err(dB, gB) < tol
+
+
+def test_spectral_norm_state_machine_and_grad():
+    ops = ops_mod()
+    from oracle import gim_oracle as O
+    for (co, ci, k) in [(8, 6, 3), (64, 128, 1), (128, 128, 9), (3, 64, 9)]:
+        p = {"c.weight_orig": rnd(co, ci, k, k, seed=5).requires_grad_(), "c.weight_u": F.normalize(rnd(co, seed=6), dim=0),
+             "c.weight_v": F.normalize(rnd(ci * k * k, seed=7), dim=0)}
+        w = p["c.weight_orig"].detach().to("cuda", torch.float32).requires_grad_()
+        u = p["c.weight_u"].to("cuda", torch.float32).clone()
+        v = p["c.weight_v"].to("cuda", torch.float32).clone()
+        probe = rnd(k * k, co, ci, seed=8)
+        for step, training in enumerate([True, True, False, True]):
+            ref = O.sn_weight(p, "c", training)                      # OIHW
+            ref_packed = ref.permute(2, 3, 0, 1).reshape(k * k, co, ci)
+            got = ops.SpectralNormFn.apply(w, (u, v), training, 1e-12)
+            assert rel_err(got, ref_packed) < 1e-5, (co, ci, k, step)
+            assert rel_err(u, p["c.weight_u"]) < 1e-5 and rel_err(v, p["c.weight_v"]) < 1e-5
+        (g_ref,) = torch.autograd.grad((ref_packed * probe).sum(), p["c.weight_orig"])
+        (g_got,) = torch.autograd.grad((got * probe.to("cuda", torch.float32)).sum(), w)
+        assert rel_err(g_got, g_ref) < 1e-4
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-6), ("bf16", 1e-2)])
+def test_pointwise_and_resampling(prec, tol):
+    ops = ops_mod()
+    ops.set_precision(prec)
+    dt = ops.act_dtype()
+    x64 = rnd(3, 5, 13, 9, seed=1).requires_grad_()
+    r64 = rnd(3, 5, 13, 9, seed=2).requires_grad_()
+    x, r = to_dev_nhwc(x64.detach(), dt), to_dev_nhwc(r64.detach(), dt)
+    xq, rq = nchw(x).requires_grad_(), nchw(r).requires_grad_()       # the rounded inputs the device actually sees
+    # leaky relu + avg-pool-of-sum (odd sizes floor) + nearest upsample + tanh, one chain
+    ref = torch.tanh(F.interpolate(F.avg_pool2d(F.leaky_relu(xq, 0.2) + rq, 2), scale_factor=2, mode="nearest"))
+    got = ops.TanhFn.apply(ops.upsample2(ops.avg_pool2_add(ops.lrelu(x), r)))
+    assert got.shape == (3, 12, 8, 5)
+    assert rel_err(nchw(got), ref) < max(tol, 1e-6)
+    probe = rnd(*ref.shape, seed=3)
+    gr = torch.autograd.grad((ref * probe).sum(), (xq, rq))
+    gg = torch.autograd.grad(ops.DotFn.apply(got, probe.permute(0, 2, 3, 1).contiguous().to("cuda", dt)).sum(), (x, r))
+    assert rel_err(nchw(gg[0]), gr[0]) < max(tol, 1e-5) and rel_err(nchw(gg[1]), gr[1]) < max(tol, 1e-5)
+    # layout round trip
+    img = rnd(4, 3, 10, 7, seed=4).float().cuda()
+    assert rel_err(ops.from_nhwc(ops.to_nhwc(img)), img) < (1e-7 if prec == "fp32" else 4e-3)
+    # channel concat
+    a, b = rnd(2, 3, 4, 4, seed=5), rnd(2, 6, 4, 4, seed=6)
+    cat = ops.CatChannelsFn.apply(to_dev_nhwc(a, dt), to_dev_nhwc(b, dt))
+    assert rel_err(nchw(cat), torch.cat((a, b), 1)) < (1e-7 if prec == "fp32" else 4e-3)
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+@pytest.mark.parametrize("shape", [(3, 16, 8, 8), (2, 64, 1, 1), (2, 70, 16, 16), (4, 512, 2, 2)])
+def test_instance_norm_and_ada_in(shape, prec, tol):
+    from oracle import gim_oracle as O
+    ops = ops_mod()
+    ops.set_precision(prec)
+    dt = ops.act_dtype()
+    n, c, h, w = shape
+    x = to_dev_nhwc(rnd(n, c, h, w, seed=1) + 0.5, dt)
+    xq = nchw(x).requires_grad_()
+    probe = rnd(n, c, h, w, seed=9)
+    pr = probe.permute(0, 2, 3, 1).contiguous().to("cuda", dt)
+    wt, bs = (1 + 0.1 * rnd(c, seed=2)).requires_grad_(), (0.1 * rnd(c, seed=3)).requires_grad_()
+    ref = O.lrelu(O.instance_norm(xq, wt, bs))
+    wd, bd = wt.detach().float().cuda().requires_grad_(), bs.detach().float().cuda().requires_grad_()
+    got = ops.instance_norm(x, wd, bd, 1e-5, 0.2)
+    assert rel_err(nchw(got), ref) < tol
+    gr = torch.autograd.grad((ref * probe).sum(), (xq, wt, bs))
+    gg = torch.autograd.grad(ops.DotFn.apply(got, pr).sum(), (x, wd, bd))
+    if h * w > 1:
+        assert rel_err(nchw(gg[0]), gr[0]) < tol * 5
+    else:
+        assert float(gg[0].abs().max()) == 0.0
+    assert rel_err(gg[1], gr[1]) < tol * 5 + 1e-6 and rel_err(gg[2], gr[2]) < tol * 5
+    if h * w > 1:
+        ms, ss = rnd(n, c, seed=4).requires_grad_(), (1 + 0.2 * rnd(n, c, seed=5)).requires_grad_()
+        xq2 = nchw(x).requires_grad_()
+        ref = O.ada_in(xq2, ms, ss)
+        msd, ssd = ms.detach().float().cuda().requires_grad_(), ss.detach().float().cuda().requires_grad_()
+        x2 = x.detach().clone().requires_grad_()
+        got = ops.ada_in(x2, msd, ssd, 1e-5)
+        assert rel_err(nchw(got), ref) < tol
+        gr = torch.autograd.grad((ref * probe).sum(), (xq2, ms, ss))
+        gg = torch.autograd.grad(ops.DotFn.apply(got, pr).sum(), (x2, msd, ssd))
+        assert rel_err(nchw(gg[0]), gr[0]) < tol * 5
+        assert rel_err(gg[1], gr[1]) < tol * 5 and rel_err(gg[2], gr[2]) < tol * 5
+
+
+def test_matmul_linear_softmax_with_double_backward():
+    ops = ops_mod()
+    for ta in (False, True):
+        for tb in (False, True):
+            a64 = rnd(3, *((17, 70) if ta else (70, 17)), seed=1).requires_grad_()
+            b64 = rnd(3, *((33, 17) if tb else (17, 33)), seed=2).requires_grad_()
+            ref = torch.matmul(a64.transpose(1, 2) if ta else a64, b64.transpose(1, 2) if tb else b64)
+            a, b = a64.detach().float().cuda().requires_grad_(), b64.detach().float().cuda().requires_grad_()
+            got = ops.matmul(a, b, ta, tb)
+            assert rel_err(got, ref) < 1e-5
+            probe = rnd(*ref.shape, seed=3)
+            gr = torch.autograd.grad((ref * probe).sum(), (a64, b64))
+            gg = torch.autograd.grad((got * probe.float().cuda()).sum(), (a, b))
+            assert rel_err(gg[0], gr[0]) < 1e-5 and rel_err(gg[1], gr[1]) < 1e-5
+    # attention-shaped chain with second order: softmax(g f^T) h
+    f64, g64, h64 = (rnd(2, 20, 8, seed=s).requires_grad_() for s in (4, 5, 6))
+    def chain(f, g, h, mm, sm):
+        return mm(sm(mm(g, f, False, True)), h, False, False)
+    ref = chain(f64, g64, h64, lambda a, b, ta, tb: torch.matmul(a, b.transpose(1, 2) if tb else b), lambda t: torch.softmax(t, -1))
+    f, g, h = (t.detach().float().cuda().requires_grad_() for t in (f64, g64, h64))
+    got = chain(f, g, h, ops.matmul, ops.SoftmaxRowsFn.apply)
+    assert rel_err(got, ref) < 1e-5
+    probe = rnd(*ref.shape, seed=7)
+    g1r = torch.autograd.grad((ref * probe).sum(), (f64, g64), create_graph=True)
+    g2r = torch.autograd.grad(sum(t.pow(2).sum() for t in g1r), (f64, g64, h64))
+    g1 = torch.autograd.grad((got * probe.float().cuda()).sum(), (f, g), create_graph=True)
+    g2 = torch.autograd.grad(sum(ops.RowsSqSumFn.apply(t.reshape(1, -1)).sum() for t in g1), (f, g, h))
+    for a_, b_ in zip(g1 + g2, g1r + g2r):
+        assert rel_err(a_, b_) < 1e-4
+    # linear + fused bias / leaky relu, second order through the mask
+    x64, w64, b64 = rnd(9, 40, seed=8).requires_grad_(), rnd(24, 40, seed=9).requires_grad_(), rnd(24, seed=10).requires_grad_()
+    ref = F.leaky_relu(F.linear(x64, w64, b64), 0.2)
+    x, w, b = (t.detach().float().cuda().requires_grad_() for t in (x64, w64, b64))
+    got = ops.linear(x, w, b, 0.2)
+    assert rel_err(got, ref) < 1e-5
+    (gxr,) = torch.autograd.grad(ref.sum(), x64, create_graph=True)
+    gr = torch.autograd.grad(gxr.pow(2).sum(), (w64,))
+    (gx,) = torch.autograd.grad(got.sum(), x, create_graph=True)
+    gg = torch.autograd.grad(ops.RowsSqSumFn.apply(gx.reshape(1, -1)).sum(), (w,))
+    assert rel_err(gx, gxr) < 1e-5 and rel_err(gg[0], gr[0]) < 1e-4
+
+
+def test_set_statistics_with_double_backward():
+    from oracle import gim_oracle as O
+    ops = ops_mod()
+    for (b, s, d) in [(4, 5, 64), (3, 1, 10), (7, 10, 33)]:
+        x64 = rnd(b, s, d, seed=1).requires_grad_()
+        x = x64.detach().float().cuda().requires_grad_()
+        ref = torch.cat((x64.mean(1), O.custom_std(x64)), -1)
+        got = torch.cat((ops.set_mean(x), ops.set_std(x)), -1)
+        assert rel_err(got, ref) < 1e-5 or (s == 1 and float(got[:, d:].abs().max()) == 0)
+        if s == 1:
+            continue
+        probe = rnd(b, 2 * d, seed=2)
+        (g1r,) = torch.autograd.grad((ref * probe).sum(), x64, create_graph=True)
+        (g2r,) = torch.autograd.grad(g1r.pow(2).sum(), x64)
+        (g1,) = torch.autograd.grad((got * probe.float().cuda()).sum(), x, create_graph=True)
+        (g2,) = torch.autograd.grad(ops.RowsSqSumFn.apply(g1.reshape(1, -1)).sum(), x)
+        assert rel_err(g1, g1r) < 1e-5 and rel_err(g2, g2r) < 1e-4
+    w64, add64 = rnd(3, 4, 6, seed=3).requires_grad_(), rnd(3, 6, seed=4).requires_grad_()
+    ref = w64 - w64.mean(1, keepdim=True) + add64.unsqueeze(1)
+    w, add = w64.detach().float().cuda().requires_grad_(), add64.detach().float().cuda().requires_grad_()
+    got = ops.SetCenterAddFn.apply(w, add, True)
+    probe = rnd(3, 4, 6, seed=5)
+    gr = torch.autograd.grad((ref * probe).sum(), (w64, add64))
+    gg = torch.autograd.grad((got * probe.float().cuda()).sum(), (w, add))
+    assert rel_err(got, ref) < 1e-6 and rel_err(gg[0], gr[0]) < 1e-6 and rel_err(gg[1], gr[1]) < 1e-6
+
+
+def test_global_max_bce_rows():
+    ops = ops_mod()
+    x64 = rnd(3, 40, 6, 5, seed=1).requires_grad_()
+    x = to_dev_nhwc(x64.detach(), torch.float32)
+    ref = F.leaky_relu(torch.amax(x64, dim=(2, 3)), 0.2)
+    got = ops.lrelu(ops.GlobalMaxFn.apply(x))
+    assert rel_err(got, ref) < 1e-6
+    probe = rnd(3, 40, seed=2)
+    (gr,) = torch.autograd.grad((ref * probe).sum(), x64)
+    (gg,) = torch.autograd.grad((got * probe.float().cuda()).sum(), x, create_graph=True)
+    assert rel_err(nchw(gg), gr) < 1e-6
+    # second order: scatter's backward is a gather of the same indices
+    x64b = x64.detach().clone().requires_grad_()
+    xb = to_dev_nhwc(x64b.detach(), torch.float32)
+    (g1r,) = torch.autograd.grad(F.leaky_relu(torch.amax(x64b, dim=(2, 3)), 0.2).pow(2).sum(), x64b, create_graph=True)
+    (g2r,) = torch.autograd.grad((g1r * x64b).sum(), x64b)
+    (g1,) = torch.autograd.grad(ops.lrelu(ops.GlobalMaxFn.apply(xb)).pow(2).sum(), xb, create_graph=True)
+    (g2,) = torch.autograd.grad(ops.DotFn.apply(g1, xb).sum(), xb)
+    assert rel_err(nchw(g1), g1r) < 1e-6 and rel_err(nchw(g2), g2r) < 1e-6
+    z64 = rnd(11, 1, seed=3).requires_grad_()
+    z = z64.detach().float().cuda().requires_grad_()
+    for target in (0.0, 1.0):
+        ref = F.binary_cross_entropy_with_logits(z64, torch.full_like(z64, target), reduction="none")
+        got = ops.BCEWithLogitsFn.apply(z, target)
+        assert rel_err(got, ref) < 1e-6
+        assert rel_err(torch.autograd.grad(got.sum(), z)[0], torch.autograd.grad(ref.sum(), z64)[0]) < 1e-6
+
+
+def test_fused_adam_matches_torch_adam():
+    from optimalstrategiesagainstgenerativeattacks_b200.fused_adam import FusedAdam
+    shapes = [(7,), (64, 3, 3, 3), (513,), (128, 130), (1,)]
+    ref_p = [torch.nn.Parameter(rnd(*s, seed=i).float()) for i, s in enumerate(shapes)]
+    dev_p = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref_p]
+    ref = torch.optim.Adam([{"params": ref_p[:3], "lr": 1e-2}, {"params": ref_p[3:], "lr": 3e-3}], betas=(0.0, 0.99))
+    opt = FusedAdam([{"params": dev_p[:3], "lr": 1e-2}, {"params": dev_p[3:], "lr": 3e-3}], betas=(0.0, 0.99))
+    for it in range(5):
+        for i, (a, b) in enumerate(zip(ref_p, dev_p)):
+            if i == 4:
+                continue                      # never receives a gradient: must be skipped, no state
+            g = rnd(*a.shape, seed=100 * it + i).float()
+            a.grad = g.clone()
+            b.grad = g.clone().cuda() if b.grad is None else b.grad.copy_(g.cuda())
+        ref.step()
+        opt.step()
+    for a, b in zip(ref_p, dev_p):
+        assert rel_err(b, a) < 2e-6
+    sd = opt.state_dict()
+    assert set(sd["state"].keys()) == {0, 1, 2, 3} and float(sd["state"][0]["step"]) == 5.0
+    assert rel_err(sd["state"][1]["exp_avg_sq"], ref.state_dict()["state"][1]["exp_avg_sq"]) < 1e-6
+    # round trip through torch's own optimizer state format
+    opt2 = FusedAdam([{"params": dev_p[:3], "lr": 1e-2}, {"params": dev_p[3:], "lr": 3e-3}], betas=(0.0, 0.99))
+    opt2.load_state_dict(sd)
+    for i, (a, b) in enumerate(zip(ref_p, dev_p)):
+        if i != 4:
+            g = rnd(*a.shape, seed=999 + i).float()
+            a.grad = g.clone()
+            b.grad.copy_(g.cuda())
+    ref.step()
+    opt2.step()
+    for a, b in zip(ref_p, dev_p):
+        assert rel_err(b, a) < 2e-6

@@ -1,0 +1,283 @@
+"""GPU parity of the drop-in modules / trainers (called through the C ABI) against
+  (1) the golden vectors: the UNMODIFIED reference evaluated in float64 (oracle/make_golden.py), and
+  (2) the CPU oracle run here in float32 -- its distance from the float64 truth is the noise floor of the algorithm itself
+      and sets the tolerance for ill-conditioned quantities (deep attacker gradients, post-Adam parameters).
+Gates (north_star): fp32 path rel 1e-4, bf16 tensor-core path rel 2e-2.
+"""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import gim_oracle as O
+from oracle.fill import fill_state_dict, seeded
+
+pytestmark = pytest.mark.gpu
+
+TOLS = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+@pytest.fixture(autouse=True)
+def _cuda_only():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from optimalstrategiesagainstgenerativeattacks_b200 import ops
+    ops.set_precision("fp32")
+    yield
+    ops.set_precision("fp32")
+
+
+@contextlib.contextmanager
+def inject_randn(zs):
+    real = torch.randn
+    queue = list(zs)
+
+    def fake(*a, **k):
+        return queue.pop(0).clone()
+    torch.randn = fake
+    try:
+        yield
+    finally:
+        torch.randn = real
+
+
+def pkg():
+    import optimalstrategiesagainstgenerativeattacks_b200 as g
+    from optimalstrategiesagainstgenerativeattacks_b200 import (gim_gaussian_models, gim_gaussian_trainer, gim_img_models, gim_img_trainer,
+                                                               training_steps, utils)
+    return g, gim_img_models, gim_gaussian_models, gim_img_trainer, gim_gaussian_trainer, training_steps, utils
+
+
+def load(module, schema, seed):
+    module.load_state_dict(fill_state_dict([(k, s) for k, s in schema], seed))
+    return module.cuda()
+
+
+def oracle_params(schema, seed, dtype=torch.float32):
+    p = {k: v.to(dtype) for k, v in fill_state_dict([(k, s) for k, s in schema], seed).items()}
+    for k, v in p.items():
+        if not k.endswith(("weight_u", "weight_v")):
+            v.requires_grad_()
+    return p
+
+
+def rows(named):
+    out = []
+    for _, prm in named:
+        g = prm.grad
+        out.append([np.nan, np.nan] if g is None else [g.double().sum().item(), g.double().norm().item()])
+    return np.asarray(out)
+
+
+def rows_err(got, want):
+    """max over tensors of |norm difference| relative to the tensor's norm (tensors with ~zero true gradient are scaled by the
+    largest norm instead: their values are rounding noise in every implementation)."""
+    got, want = np.asarray(got), np.asarray(want)
+    nan = np.isnan(want[:, 1])
+    assert (np.isnan(got[:, 1]) == nan).all(), "set of parameters that receive gradients differs"
+    scale = np.maximum(want[~nan, 1], 1e-4 * np.nanmax(want[:, 1]))
+    return float((np.abs(got[~nan, 1] - want[~nan, 1]) / scale).max())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_authenticator_small_vs_reference(schemas, prec):
+    g, M = pkg()[0], pkg()[1]
+    g.set_precision(prec)
+    tol = TOLS[prec]
+    gold = load_golden("au_s16")
+    s = schemas["s16"]
+    au = load(M.get_au(16, 3, 64), s["au"], 11).train()
+    test = seeded((2, 3, 3, 16, 16), 12, 0.5, 1.0).cuda().requires_grad_()
+    si = seeded((2, 2, 3, 16, 16), 13, 0.5, 1.0).cuda().requires_grad_()
+    out = au(test, si)
+    assert out.shape == (2, 1) and rel_err(out, gold["out"]) < tol
+    loss = g.ops.BCEWithLogitsFn.apply(out, 1.0).mean()
+    loss.backward()
+    assert rel_err(loss, gold["loss"]) < tol
+    # noise floor of the same algorithm in fp32 on the CPU
+    p = oracle_params(s["au"], 11)
+    t32, s32 = test.detach().cpu().requires_grad_(), si.detach().cpu().requires_grad_()
+    O.gan_loss(O.authenticator(p, t32, s32), 1.0).mean().backward()
+    floor = max(rel_err(t32.grad, gold["g_test"]), rel_err(s32.grad, gold["g_si"]))
+    gtol = max(tol, 3 * floor)
+    assert rel_err(test.grad, gold["g_test"]) < gtol and rel_err(si.grad, gold["g_si"]) < gtol
+    assert rows_err(rows(au.named_parameters()), gold["grads"]) < 3 * gtol
+    assert rel_err(au.dis.mlp.model[4].weight.grad, gold["g_mlp_last"]) < gtol
+    # spectral-norm state after one train-mode call, and the eval-mode output (no power iteration)
+    assert rel_err(au.src_encoder.down_blocks[0].conv_r1.weight_u, gold["u_after"]) < 1e-5
+    assert rel_err(au.src_encoder.down_blocks[0].conv_r1.weight_v, gold["v_after"]) < 1e-5
+    au.eval()
+    with torch.no_grad():
+        assert rel_err(au(test.detach(), si.detach()), gold["out_eval"]) < tol
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_impersonator_small_vs_reference(schemas, prec):
+    g, M = pkg()[0], pkg()[1]
+    g.set_precision(prec)
+    tol = TOLS[prec]
+    gold = load_golden("im_s16")
+    s = schemas["s16"]
+    im = load(M.get_im(16, 3, 64), s["im"], 21).train()
+    leaked = seeded((2, 2, 3, 16, 16), 22, 0.5, 1.0).cuda()
+    z = seeded((2, 3, 64), 24).cuda()
+    with inject_randn([z]):
+        fake = im(leaked, 3, True)
+    p = oracle_params(s["im"], 21)
+    fake32 = O.impersonator(p, leaked.cpu(), 3, z.cpu())
+    floor = rel_err(fake32, gold["fake"])
+    assert fake.shape == (2, 3, 3, 16, 16) and rel_err(fake, gold["fake"]) < max(tol, 3 * floor)
+    probe = seeded(tuple(fake.shape), 25)
+    (fake * probe.cuda()).sum().backward()
+    (fake32 * probe).sum().backward()
+    names = s["im_params"]
+    floor_rows = rows_err(rows([(n, p[n]) for n in names]), gold["grads"])
+    assert rows_err(rows(im.named_parameters()), gold["grads"]) < max(3 * tol, 3 * floor_rows)
+    gfloor = rel_err(p["env_noise_mapper.model.6.weight"].grad, gold["g_noise_last"])
+    assert rel_err(im.env_noise_mapper.model[6].weight.grad, gold["g_noise_last"]) < max(tol, 3 * gfloor)
+    assert all(prm.grad is None for prm in im.img_att.parameters())
+
+
+@pytest.mark.parametrize("name,seed,size,ch,b,n,k", [("O", 51, 32, 1, 1, 2, 2), ("V", 71, 64, 3, 1, 1, 1)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_full_size_networks_forward(schemas, prec, name, seed, size, ch, b, n, k):
+    """BASELINE.json configs 2 (Omniglot-shaped, S=32 as the reference runs it) and 3 (VoxCeleb2-shaped) at full width."""
+    g, M = pkg()[0], pkg()[1]
+    g.set_precision(prec)
+    tol = TOLS[prec]
+    gold = load_golden("au_" + name)
+    au = load(M.get_au(size, ch, 512), schemas[name]["au"], seed).train()
+    test = seeded((b, n, ch, size, size), seed + 1, 0.5, 1.0).cuda()
+    si = seeded((b, k, ch, size, size), seed + 2, 0.5, 1.0).cuda()
+    with torch.no_grad():
+        assert rel_err(au(test, si), gold["out"]) < tol
+        au.eval()
+        assert rel_err(au(test, si), gold["out_eval"]) < tol
+    del au
+    gold = load_golden("im_" + name)
+    seed += 10
+    im = load(M.get_im(size, ch, 512), schemas[name]["im"], seed).train()
+    leaked = seeded((1, 1, ch, size, size), seed + 1, 0.5, 1.0).cuda()
+    z = seeded((1, 1, 512), seed + 3).cuda()
+    with torch.no_grad(), inject_randn([z]):
+        fake = im(leaked, 1, True)
+    p = oracle_params(schemas[name]["im"], seed)
+    with torch.no_grad():
+        floor = rel_err(O.impersonator(p, leaked.cpu(), 1, z.cpu()), gold["fake"])
+    assert rel_err(fake, gold["fake"]) < max(tol, 3 * floor)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,reg,seed", [("steps_s16_r1", 10.0, 31), ("steps_s16_noreg", 0.0, 41)])
+def test_training_iterations_vs_reference(schemas, tmp_path, prec, name, reg, seed):
+    """Two full G-step + D-step iterations (R1 on/off) through the kept trainer API: loss curves and post-Adam parameters."""
+    g, M, _, T, _, S, U = pkg()
+    g.set_precision(prec)
+    tol = TOLS[prec]
+    gold = load_golden(name)
+    s = schemas["s16"]
+    b, m, n, k = 2, 2, 3, 2
+    au = load(M.get_au(16, 3, 64), s["au"], seed)
+    im = load(M.get_im(16, 3, 64), s["im"], seed + 10)
+    tr = U.DataParallelMock(T.GIMImgTrainer(str(tmp_path), m, n, k, au, im, 1e-3, 1e-3, 1e-4, reg_param=reg))
+    assert [len(gr["params"]) for gr in tr.module.impersonator_opt.param_groups] == s["im_groups"]
+    rec = {key: [] for key in ("im_loss", "au_loss", "loss_real", "loss_fake", "reg", "out_real", "out_fake")}
+    for it in range(2):
+        leaked = seeded((b, m, 3, 16, 16), seed + 100 * it + 1, 0.5, 1.0).cuda()
+        real = seeded((b, n, 3, 16, 16), seed + 100 * it + 2, 0.5, 1.0).cuda()
+        si = seeded((b, k, 3, 16, 16), seed + 100 * it + 3, 0.5, 1.0).cuda()
+        z = seeded((b, n, 64), seed + 100 * it + 4).cuda()
+        tr.module.do_global_step()
+        tr.module.update_learning_rate()
+        with inject_randn([z]):
+            im_loss, fake, _ = S.im_train_step(tr, leaked, si)
+        o = S.au_train_step(tr, real, fake, si)
+        rec["im_loss"].append(im_loss.item())
+        for key, val in zip(("au_loss", "loss_real", "loss_fake", "reg", "out_real", "out_fake"), o[:6]):
+            rec[key].append(val.item())
+        if it == 0:
+            assert rel_err(fake, gold["fake0"]) < max(tol, 3e-4)
+    # iteration 0 is a pure function of the inputs; iteration 1 also carries the Adam update (sign-like for tiny gradients)
+    for key, v in rec.items():
+        assert abs(v[0] - gold[key][0]) <= (5 * tol) * max(abs(gold[key][0]), 1e-2), (key, v, gold[key])
+        assert abs(v[1] - gold[key][1]) <= (50 * tol) * max(abs(gold[key][1]), 1e-2), (key, v, gold[key])
+    for mod, key in ((au, "au_params"), (im, "im_params")):
+        got = np.asarray([[v.double().sum().item(), v.double().norm().item()] for v in mod.state_dict().values()])
+        assert np.abs(got[:, 1] - gold[key][:, 1]).max() / np.abs(gold[key][:, 1]).max() < max(10 * tol, 2e-3)
+    # checkpoint round trip in the reference's schema
+    tr.module.save(epoch=0)
+    ck = torch.load(str(tmp_path / "ckpts" / "model_00000001.pt"), map_location="cpu", weights_only=False)
+    assert set(ck) == {"global_step", "last_epoch", "authenticator", "impersonator", "authenticator_opt", "impersonator_opt"}
+    assert list(ck["authenticator"].keys()) == [k_ for k_, _ in s["au"]] and list(ck["impersonator"].keys()) == [k_ for k_, _ in s["im"]]
+    assert len(ck["impersonator_opt"]["param_groups"]) == 6 and ck["global_step"] == {"global_step": 1}
+
+
+def test_gaussian_vs_reference(schemas, tmp_path):
+    g, _, GM, _, GT, S, U = pkg()
+    for name, seed, (m, n, k), reg, iters in (("gauss_d10", 91, (1, 5, 10), 0.0, 3), ("gauss_d10_r1", 95, (2, 3, 4), 1.0, 2)):
+        gold = load_golden(name)
+        d, b = 10, 16
+        au = load(GM.get_au(d), schemas["gauss10"]["au"], seed)
+        im = load(GM.get_im(d), schemas["gauss10"]["im"], seed + 10)
+        real = seeded((b, n, d), seed + 1).cuda().requires_grad_()
+        si = seeded((b, k, d), seed + 2).cuda()
+        out = au(real, si)
+        out.sum().backward()
+        assert rel_err(out, gold["au_out"]) < 1e-5 and rel_err(real.grad, gold["au_g_real"]) < 1e-4
+        assert rows_err(rows(au.named_parameters()), gold["au_grads"]) < 1e-4
+        au.zero_grad(set_to_none=True)
+        with inject_randn([seeded((b, n, d), seed + 3).cuda()]):
+            fake = im(seeded((b, m, d), seed + 5).cuda(), n, True)
+        assert rel_err(fake, gold["fake"]) < 1e-5
+        tr = U.DataParallelMock(GT.GIMGaussianTrainer(str(tmp_path), m, n, k, au, im, 1e-2, 1e-2, reg_param=reg))
+        for it in range(iters):
+            real = seeded((b, n, d), seed + 100 * it + 1).cuda()
+            si = seeded((b, k, d), seed + 100 * it + 2).cuda()
+            leaked = seeded((b, m, d), seed + 100 * it + 5).cuda()
+            tr.module.do_global_step()
+            with inject_randn([seeded((b, n, d), seed + 100 * it + 3).cuda()]):
+                im_loss, fake, _ = S.im_train_step(tr, leaked, si)
+            o = S.au_train_step(tr, real, fake, si)
+            assert abs(im_loss.item() - gold["im_loss"][it]) < 2e-4 * max(1.0, abs(gold["im_loss"][it]))
+            assert abs(o[0].item() - gold["au_loss"][it]) < 2e-4 * max(1.0, abs(gold["au_loss"][it]))
+            assert abs(o[3].item() - gold["reg"][it]) < 2e-4 * max(1.0, abs(gold["reg"][it]))
+        for key, v in au.state_dict().items():
+            assert rel_err(v, gold["au_final." + key]) < 1e-3, key
+        for key, v in im.state_dict().items():
+            # the mapper bias has an identically-zero true gradient (it cancels in w - mean(w)); Adam turns the rounding
+            # noise into +-lr steps in every implementation, the reference included
+            bound = 1e-3 if key != "env_noise_mapper.model.0.bias" else None
+            if bound is None:
+                assert float((v.cpu().double() - torch.from_numpy(gold["im_final." + key])).abs().max()) <= 1.01 * iters * 1e-2 * 2
+            else:
+                assert rel_err(v, gold["im_final." + key]) < bound, key
+        assert all(prm.grad is None for prm in im.out_mlp.parameters())
+
+
+def test_spectral_norm_call_counts_follow_reference_state_machine(schemas, tmp_path):
+    """Per training iteration every authenticator conv runs 5 power iterations (2 in the G-step, 3 in the D-step) and every
+    attacker conv 1; u after one iteration must equal the oracle's."""
+    g, M, _, T, _, S, U = pkg()
+    s = schemas["s16"]
+    seed = 41
+    au = load(M.get_au(16, 3, 64), s["au"], seed)
+    im = load(M.get_im(16, 3, 64), s["im"], seed + 10)
+    tr = U.DataParallelMock(T.GIMImgTrainer(str(tmp_path), 2, 3, 2, au, im, 0.0, 0.0, 0.0, reg_param=0.0))
+    pa, pi = oracle_params(s["au"], seed), oracle_params(s["im"], seed + 10)
+    leaked = seeded((2, 2, 3, 16, 16), 1, 0.5, 1.0)
+    real = seeded((2, 3, 3, 16, 16), 2, 0.5, 1.0)
+    si = seeded((2, 2, 3, 16, 16), 3, 0.5, 1.0)
+    z = seeded((2, 3, 64), 4)
+    with inject_randn([z.cuda()]):
+        _, fake, _ = S.im_train_step(tr, leaked.cuda(), si.cuda())
+    S.au_train_step(tr, real.cuda(), fake, si.cuda())
+    with torch.no_grad():
+        f32 = O.impersonator(pi, leaked, 3, z)
+        O.authenticator(pa, f32, si)
+        O.img_authenticator_forward(pa, f32, real, si, 0.0)
+    for key in ("src_encoder.down_blocks.1.conv_r2.weight_u", "env_encoder.att.conv_h.weight_v"):
+        assert rel_err(au.state_dict()[key], pa[key]) < 1e-4, key
+    for key in ("img2img.adain_res_block.res_blocks.2.conv1.weight_u", "env_decoder.up_blocks.0.conv_r1.weight_v"):
+        assert rel_err(im.state_dict()[key], pi[key]) < 1e-4, key
