@@ -91,8 +91,8 @@ int gim_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, g
 /* ---- InstanceNorm2d / ada_in (model_blocks.py:611-630, 747-748; gim_img_models.py:126) ---- */
 /* per (n,c): mean and M2 = sum (x-mean)^2 over the hw pixels */
 int gim_norm_stats(const void* x, float* mean, float* m2, int n, int hw, int c, int dtype, gim_stream_t stream);
-/* y = act(a[n,c]*x + b[n,c]),  act = LeakyReLU(slope) if slope != 1 */
-int gim_affine_act_fwd(const void* x, const float* a, const float* b, void* y, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
+/* y = act(a[n,c]*(x - mean[n,c]) + b[n,c]),  act = LeakyReLU(slope) if slope != 1 */
+int gim_affine_act_fwd(const void* x, const float* mean, const float* a, const float* b, void* y, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
 /* s1[n,c] = sum gyh, s2[n,c] = sum gyh*(x-mean), gyh = gy * act'(y)   (y = forward output, NULL if no act) */
 int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, float* s1, float* s2,
                         int n, int hw, int c, float slope, int dtype, gim_stream_t stream);

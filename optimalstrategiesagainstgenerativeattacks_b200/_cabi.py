@@ -40,7 +40,7 @@ PROTOTYPES = {
     "gim_copy_cols": "piipiiliip",
     "gim_cast": "pipilp",
     "gim_norm_stats": "pppiiiip",
-    "gim_affine_act_fwd": "ppppiiifip",
+    "gim_affine_act_fwd": "pppppiiifip",
     "gim_norm_bwd_reduce": "ppppppiiifip",
     "gim_norm_bwd_apply": "ppppppppiiifip",
     "gim_norm_coeffs": "ippppppiiifp",

@@ -1,8 +1,353 @@
-// placeholder until the tcgen05 path lands (next commit): reports "unsupported" so GIM_ALGO_AUTO takes the CUDA-core path
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) fed by TMA.
+//
+//   forward / input-gradient:  Y[pix][co] = sum_{tap,ci} X[pix + tap][ci] * W[tap][co][ci]
+//     A operand = a 128-pixel tile of the NHWC activation, fetched per filter tap as ONE 4-D TMA box
+//                 {64 ch, bw, bh, bn} at the tap-shifted coordinates -- the zero 'same' padding is TMA out-of-bounds fill,
+//                 so there is no im2col buffer and no halo logic.  128 rows x 128 B, SWIZZLE_128B, K-major.
+//     B operand = W[tap][n0..n0+BN][c0..c0+64], a 2-D TMA box, K-major.
+//     D         = 128 x BN fp32 accumulator in tensor memory; epilogue warps read it back with tcgen05.ld, add the bias and
+//                 write NHWC bf16 or fp32.
+//   Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
+//   (warp w owns TMEM lanes 32*(w%4)..+31).  A ring of kStages smem slots with full/empty mbarriers decouples TMA from MMA.
+//
+//   weight-gradient:  dW[tap][co][ci] = sum_pix dY[pix][co] * X[pix + tap][ci]   (see the second half of this file)
+#include <cuda.h>
 #include "common.cuh"
+
 namespace gim {
-bool conv_tc_supported(int, int, int, int, int, int, int) { return false; }
-bool wgrad_tc_supported(int, int, int, int, int, int, int) { return false; }
-int conv_fwd_tc(const void*, const void*, const float*, void*, int, int, int, int, int, int, cudaStream_t) { return fail(GIM_E_UNSUPPORTED, "tcgen05 conv not built"); }
-int conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t) { return fail(GIM_E_UNSUPPORTED, "tcgen05 wgrad not built"); }
+
+// ----------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();      // a lost arrival must fail loudly, not hang the GPU
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs have completed (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (sm_100 format, version 1), SWIZZLE_128B.
+//   K-major operand : rows of 128 B (64 bf16 along K); 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major operand: 64 MN elements contiguous (128 B) per K index, 8 K-rows = one 1024 B atom (SBO), next 64-wide MN block at LBO.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16: D fp32, A/B bf16, M=128, N=n; a_mn / b_mn = 1 for MN-major operands
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n, uint32_t a_mn, uint32_t b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// forward / input-gradient kernel
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                      // bf16 elements = one 128-byte swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
+
+struct ConvTcParams {
+    int n, h, w, cin, cout, ks;
+    int bw, bh, bn;                              // pixel-tile box, bw*bh*bn == 128
+    int tiles_w, tiles_h, tiles_n;
+    int block_n;                                 // N tile (output channels per CTA)
+    int stages;
+    int out_f32;                                 // 1: y is fp32, 0: bf16
+};
+
+template <int kDummy>
+__global__ void __launch_bounds__(192, 1) conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                                                             const float* __restrict__ bias, void* __restrict__ y, const ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B needs 1024-byte alignment
+    const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
+    uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tmem_full_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int tn = t;
+    const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tn * p.bn;
+    const int n0 = blockIdx.y * p.block_n;
+    const int pad = (p.ks - 1) / 2;
+    const int kc_per_tap = p.cin / kBlockK;
+    const int num_kb = p.ks * p.ks * kc_per_tap;
+    const uint32_t tmem_cols = p.block_n < 32 ? 32u : (uint32_t)p.block_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t round = kb / p.stages;
+                mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+                const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+                const int r = tap / p.ks, q = tap - r * p.ks;
+                uint8_t* sa = smem + s * stage_bytes;
+                uint8_t* sb = sa + kATileBytes;
+                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                tma_load_4d(sa, &map_x, &full_bar[s], kc * kBlockK, w0 + q - pad, h0 + r - pad, img0);
+                tma_load_2d(sb, &map_w, &full_bar[s], kc * kBlockK, tap * p.cout + n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t round = kb / p.stages;
+                mbar_wait(&full_bar[s], round & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t da = make_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t db = make_desc_sw128(sb + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // ---- epilogue: TMEM -> registers -> (+bias) -> global NHWC ----
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+        const int m = quarter * 32 + lane;           // tile row = pixel within the box
+        const int lw = m % p.bw, lh = (m / p.bw) % p.bh, ln = m / (p.bw * p.bh);
+        const int ww = w0 + lw, hh = h0 + lh, img = img0 + ln;
+        const bool valid = ww < p.w && hh < p.h && img < p.n;
+        const long long pix = ((long long)img * p.h + hh) * p.w + ww;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (valid) {
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(&bias[n0 + c0 + j]) : 0.f);
+                if (p.out_f32) {
+                    float4* dst = reinterpret_cast<float4*>((float*)y + pix * p.cout + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>((bf16*)y + pix * p.cout + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        uint4 o;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+                        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                        o.x = *reinterpret_cast<uint32_t*>(&b0);
+                        o.y = *reinterpret_cast<uint32_t*>(&b1);
+                        o.z = *reinterpret_cast<uint32_t*>(&b2);
+                        o.w = *reinterpret_cast<uint32_t*>(&b3);
+                        dst[j] = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// host side: TMA descriptors
+// ----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static void pixel_box(int h, int w, int& bw, int& bh, int& bn) {
+    bw = next_pow2(w);
+    if (bw > kBlockM) bw = kBlockM;
+    bh = next_pow2(h);
+    if (bh > kBlockM / bw) bh = kBlockM / bw;
+    bn = kBlockM / (bw * bh);
+}
+
+// 4-D map over an NHWC bf16 tensor, box {64 ch, bw, bh, bn}, 128B swizzle, zero OOB fill
+static bool make_act_map(CUtensorMap* map, const void* x, int n, int h, int w, int c, int bw, int bh, int bn) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// 2-D map over a row-major bf16 matrix [rows][cols], box {64 cols, box_rows}
+static bool make_mat_map(CUtensorMap* map, const void* m, long long rows, int cols, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(m), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int pick_block_n(int cout) {
+    if (cout >= 128 && cout % 128 == 0) return 128;
+    if (cout == 64 || cout == 32 || cout == 16) return cout;
+    return 0;
+}
+
+bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype) {
+    if (dtype != GIM_BF16) return false;
+    if (cin % kBlockK != 0) return false;
+    if (pick_block_n(cout) == 0) return false;
+    if (ks < 1 || !(ks & 1) || ks > 15) return false;
+    return n > 0 && h > 0 && wd > 0;
+}
+
+int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, int out_f32,
+                   cudaStream_t st) {
+    ConvTcParams p;
+    p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
+    pixel_box(h, wd, p.bw, p.bh, p.bn);
+    p.tiles_w = (wd + p.bw - 1) / p.bw;
+    p.tiles_h = (h + p.bh - 1) / p.bh;
+    p.tiles_n = (n + p.bn - 1) / p.bn;
+    p.block_n = pick_block_n(cout);
+    p.out_f32 = out_f32;
+    const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+    CUtensorMap map_x, map_w;
+    if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
+    if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.block_n)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
+    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail(GIM_E_CUDA, "conv_fwd_tc: cannot raise dynamic shared memory limit");
+        attr_set = true;
+    }
+    long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    if (tiles > 2147483647LL) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
+    dim3 grid((unsigned)tiles, cout / p.block_n);
+    conv_fwd_tc_kernel<0><<<grid, 192, smem, st>>>(map_x, map_w, bias, y, p);
+    return check_launch("conv_fwd_tc");
+}
+
+int conv_fwd_tc(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
+    return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ks, 0, st);
+}
+
+// weight gradient on tensor cores: next commit
+bool wgrad_tc_supported(int, int, int, int, int, int, int) { return false; }
+int conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t) {
+    return fail(GIM_E_UNSUPPORTED, "tcgen05 wgrad not built");
+}
+
+}  // namespace gim

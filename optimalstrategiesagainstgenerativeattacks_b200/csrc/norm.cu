@@ -34,14 +34,14 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const T* __restrict__ x
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
-                                                         T* __restrict__ y, long long total, int hw, int c, float slope) {
+__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ a,
+                                                         const float* __restrict__ b, T* __restrict__ y, long long total, int hw, int c, float slope) {
     long long stride = (long long)gridDim.x * blockDim.x;
     long long plane = (long long)hw * c;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         int ch = (int)(i % c);
         long long k = (i / plane) * c + ch;
-        float v = a[k] * to_f<T>(x[i]) + b[k];
+        float v = a[k] * (to_f<T>(x[i]) - mean[k]) + b[k];      // centred form: exact for the degenerate 1x1 map
         y[i] = from_f<T>(lrelu_f(v, slope));
     }
 }
@@ -107,9 +107,8 @@ __global__ void norm_coeffs_kernel(int mode, const float* __restrict__ mean, con
         sc = p_scale[i];
         sh = p_shift[i];
     }
-    float aa = sc * r;
-    a[i] = aa;
-    b[i] = sh - mean[i] * aa;
+    a[i] = sc * r;
+    b[i] = sh;
 }
 
 __global__ void norm_bwd_coeffs_kernel(int mode, const float* __restrict__ m2, const float* __restrict__ s1, const float* __restrict__ s2,
@@ -164,10 +163,11 @@ int gim_norm_stats(const void* x, float* mean, float* m2, int n, int hw, int c, 
     GIM_DISPATCH_DTYPE(dtype, (norm_stats_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)x, mean, m2, hw, c)));
     return check_launch("norm_stats");
 }
-int gim_affine_act_fwd(const void* x, const float* a, const float* b, void* y, int n, int hw, int c, float slope, int dtype, gim_stream_t s) {
+int gim_affine_act_fwd(const void* x, const float* mean, const float* a, const float* b, void* y, int n, int hw, int c, float slope, int dtype,
+                       gim_stream_t s) {
     long long total = (long long)n * hw * c;
     if (total <= 0) return GIM_OK;
-    GIM_DISPATCH_DTYPE(dtype, (affine_act_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, a, b, (T*)y, total, hw, c, slope)));
+    GIM_DISPATCH_DTYPE(dtype, (affine_act_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, mean, a, b, (T*)y, total, hw, c, slope)));
     return check_launch("affine_act_fwd");
 }
 int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, float* s1, float* s2, int n, int hw, int c, float slope,

@@ -467,7 +467,7 @@ class _NormFn(Function):
         C.call("gim_norm_coeffs", mode, st[0].data_ptr(), st[1].data_ptr(), C.ptr(p_scale), C.ptr(p_shift),
                st[2].data_ptr(), st[3].data_ptr(), n, hw, c, eps)
         y = torch.empty_like(x)
-        C.call("gim_affine_act_fwd", C.ptr(x), st[2].data_ptr(), st[3].data_ptr(), C.ptr(y), n, hw, c, slope, C.dtype_code(x))
+        C.call("gim_affine_act_fwd", C.ptr(x), st[0].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), C.ptr(y), n, hw, c, slope, C.dtype_code(x))
         ctx.cfg = (mode, eps, slope)
         ctx.save_for_backward(x, y, st, p_scale)
         return y

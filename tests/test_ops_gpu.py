@@ -310,3 +310,32 @@ def test_fused_adam_matches_torch_adam():
     opt2.step()
     for a, b in zip(ref_p, dev_p):
         assert rel_err(b, a) < 2e-6
+
+
+TC_SHAPES = [  # n, ci, co, k, h, w  -- every tensor-core-eligible layer family of the O (32x32x1) and V (64x64x3) networks
+    (3, 64, 64, 3, 16, 16), (2, 128, 128, 3, 32, 32), (5, 256, 256, 3, 16, 16), (3, 512, 512, 3, 8, 8), (9, 512, 512, 3, 4, 4),
+    (2, 128, 128, 9, 32, 32), (2, 64, 64, 9, 64, 64), (3, 128, 256, 3, 16, 16), (4, 256, 128, 1, 16, 16), (2, 128, 16, 1, 16, 16),
+    (2, 256, 32, 1, 8, 8), (130, 512, 512, 3, 1, 1), (33, 512, 512, 3, 2, 2), (1, 64, 128, 3, 52, 52), (2, 128, 256, 3, 13, 13),
+    (1, 64, 64, 3, 105, 105),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tcgen05_matches_cuda_core(shape):
+    """The tcgen05/TMEM/TMA implicit GEMM against the CUDA-core kernel on identical bf16 operands (forward and dgrad form)."""
+    ops = ops_mod()
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi as C
+    ops.set_precision("bf16")
+    n, ci, co, k, h, w = shape
+    assert C.conv_tc_supported(n, h, w, ci, co, k, C.BF16)
+    x = (rnd(n, h, w, ci, seed=1)).to("cuda", torch.bfloat16)
+    wp = (rnd(k * k, co, ci, seed=2) / np.sqrt(ci * k * k)).to("cuda", torch.float32)
+    b = rnd(co, seed=3).to("cuda", torch.float32)
+    outs = {}
+    for algo in ("simt", "tcgen05"):
+        ops.set_conv_algo(algo)
+        with torch.no_grad():
+            outs[algo] = ops.Conv2dFn.apply(x, wp, b, k).float()
+        torch.cuda.synchronize()
+    assert rel_err(outs["tcgen05"], outs["simt"]) < 4e-3
+    assert float((outs["tcgen05"] - outs["simt"]).abs().max()) < 0.05 * float(outs["simt"].abs().max())
