@@ -37,6 +37,7 @@ int         gim_version(void);
 const char* gim_last_error(void);
 /* 1 if the tcgen05/TMA implicit-GEMM path can take this conv shape/dtype, else 0 */
 int         gim_conv2d_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype);
+int         gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype);
 /* counts kernel launches issued through this library since the last reset (bench.py `gpu_launches`) */
 long long   gim_launch_count(int reset);
 

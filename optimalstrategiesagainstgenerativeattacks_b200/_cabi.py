@@ -63,7 +63,7 @@ PROTOTYPES = {
     "gim_rows_scale": "pppilfip",
     "gim_adam_multi": "pilppfff" + "fp",
 }
-OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_launch_count")
+OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_launch_count")
 
 _lib = None
 
@@ -85,6 +85,8 @@ def lib():
         L.gim_last_error.restype = ctypes.c_char_p
         L.gim_conv2d_tc_supported.argtypes = [_I] * 7
         L.gim_conv2d_tc_supported.restype = _I
+        L.gim_conv2d_wgrad_tc_supported.argtypes = [_I] * 7
+        L.gim_conv2d_wgrad_tc_supported.restype = _I
         L.gim_launch_count.argtypes = [_I]
         L.gim_launch_count.restype = _L
         _lib = L
@@ -131,3 +133,7 @@ def launch_count(reset=False):
 
 def conv_tc_supported(n, h, w, cin, cout, k, dtype):
     return bool(lib().gim_conv2d_tc_supported(n, h, w, cin, cout, k, dtype))
+
+
+def wgrad_tc_supported(n, h, w, cin, cout, k, dtype):
+    return bool(lib().gim_conv2d_wgrad_tc_supported(n, h, w, cin, cout, k, dtype))

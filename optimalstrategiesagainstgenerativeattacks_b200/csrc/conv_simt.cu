@@ -282,6 +282,10 @@ int gim_conv2d_tc_supported(int n, int h, int w, int cin, int cout, int ksize, i
     return conv_tc_supported(n, h, w, cin, cout, ksize, dtype) ? 1 : 0;
 }
 
+int gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype) {
+    return wgrad_tc_supported(n, h, w, cin, cout, ksize, dtype) ? 1 : 0;
+}
+
 int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo,
                    gim_stream_t s) {
     GIM_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv2d_fwd: empty shape");

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(192, 1) conv_fwd_tc_kernel(const __grid_consta
     const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tn * p.bn;
     const int n0 = blockIdx.y * p.block_n;
     const int pad = (p.ks - 1) / 2;
-    const int kc_per_tap = p.cin / kBlockK;
+    const int kc_per_tap = (p.cin + kBlockK - 1) / kBlockK;      // a ragged last K block is zero-filled by TMA (OOB channels)
     const int num_kb = p.ks * p.ks * kc_per_tap;
     const uint32_t tmem_cols = p.block_n < 32 ? 32u : (uint32_t)p.block_n;
 
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(192, 1) conv_fwd_tc_kernel(const __grid_consta
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
-            if (valid) {
+            if (valid && n0 + c0 < p.cout) {
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(&bias[n0 + c0 + j]) : 0.f);
@@ -296,14 +296,16 @@ static bool make_mat_map(CUtensorMap* map, const void* m, long long rows, int co
 }
 
 static int pick_block_n(int cout) {
-    if (cout >= 128 && cout % 128 == 0) return 128;
-    if (cout == 64 || cout == 32 || cout == 16) return cout;
-    return 0;
+    if (cout % 16 != 0) return 0;
+    if (cout >= 128) return 128;           // a ragged last N tile reads the next tap's rows; its columns are never stored
+    if (cout > 64) return 128;
+    if (cout > 32) return 64;
+    return cout > 16 ? 32 : 16;
 }
 
 bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype) {
     if (dtype != GIM_BF16) return false;
-    if (cin % kBlockK != 0) return false;
+    if (cin % 8 != 0) return false;        // TMA needs 16-byte global strides
     if (pick_block_n(cout) == 0) return false;
     if (ks < 1 || !(ks & 1) || ks > 15) return false;
     return n > 0 && h > 0 && wd > 0;
@@ -335,7 +337,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     }
     long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     if (tiles > 2147483647LL) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
-    dim3 grid((unsigned)tiles, cout / p.block_n);
+    dim3 grid((unsigned)tiles, (cout + p.block_n - 1) / p.block_n);
     conv_fwd_tc_kernel<0><<<grid, 192, smem, st>>>(map_x, map_w, bias, y, p);
     return check_launch("conv_fwd_tc");
 }
@@ -344,10 +346,174 @@ int conv_fwd_tc(const void* x, const void* w, const float* bias, void* y, int n,
     return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ks, 0, st);
 }
 
-// weight gradient on tensor cores: next commit
-bool wgrad_tc_supported(int, int, int, int, int, int, int) { return false; }
-int conv_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t) {
-    return fail(GIM_E_UNSUPPORTED, "tcgen05 wgrad not built");
+// ----------------------------------------------------------------------------------------------------------------
+// weight gradient:  dW[tap][co][ci] = sum_pix dY[pix][co] * X[pix + tap][ci]
+//   GEMM per filter tap with M = co (128), N = ci (64 or 128), K = pixels.  Both operands are "MN-major": a TMA box
+//   {64 ch, bw, bh, bn} lands as 128 pixel rows of 128 B -- exactly the canonical SWIZZLE_128B MN-major layout with the pixel
+//   index as K (8-pixel groups 1024 B apart = SBO; the next 64-channel block one box further = LBO).  dY at the tile
+//   position, X at the tap-shifted position (zero padding and ragged tiles = TMA OOB fill; channels beyond Cout/Cin also
+//   read as zeros, so any channel count that is a multiple of 8 works).  Split-K over pixel tiles across the grid; each CTA
+//   accumulates its range in TMEM and adds its partial tile into the fp32 gradient with red.global.add.
+// ----------------------------------------------------------------------------------------------------------------
+struct WgradTcParams {
+    int n, h, w, cin, cout, ks;
+    int bw, bh, bn, tiles_w, tiles_h, tiles_n;
+    int block_n;                 // ci per CTA: 64 or 128
+    int co_tiles, ci_tiles;
+    int stages;
+    int tiles_per_split;         // pixel tiles per CTA
+    int total_tiles;
+};
+
+template <int kDummy>
+__global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
+                                                               float* __restrict__ gw, const WgradTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = 2 * kATileBytes;                               // 128 co = two 64-channel boxes
+    const int b_bytes = (p.block_n / 64) * kATileBytes;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tmem_full_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x;
+    const int tap = t % (p.ks * p.ks); t /= (p.ks * p.ks);
+    const int co_t = t % p.co_tiles;
+    const int ci_t = t / p.co_tiles;
+    const int co0 = co_t * 128, ci0 = ci_t * p.block_n;
+    const int pad = (p.ks - 1) / 2;
+    const int dr = tap / p.ks - pad, dq = tap % p.ks - pad;
+    const int tile_begin = blockIdx.y * p.tiles_per_split;
+    int tile_end = tile_begin + p.tiles_per_split;
+    if (tile_end > p.total_tiles) tile_end = p.total_tiles;
+    const int num_kb = tile_end - tile_begin;                          // >= 1 by construction of the grid
+    const uint32_t tmem_cols = (uint32_t)p.block_n;                    // 64 or 128: powers of two >= 32
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_gy);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t round = kb / p.stages;
+                mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+                int tt = tile_begin + kb;
+                const int tw = tt % p.tiles_w; tt /= p.tiles_w;
+                const int th = tt % p.tiles_h; tt /= p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tt * p.bn;
+                uint8_t* sa = smem + s * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                tma_load_4d(sa, &map_gy, &full_bar[s], co0, w0, h0, img0);
+                tma_load_4d(sa + kATileBytes, &map_gy, &full_bar[s], co0 + 64, w0, h0, img0);
+                for (int j = 0; j < p.block_n / 64; ++j)
+                    tma_load_4d(sb + j * kATileBytes, &map_x, &full_bar[s], ci0 + 64 * j, w0 + dq, h0 + dr, img0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 1, 1);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t round = kb / p.stages;
+                mbar_wait(&full_bar[s], round & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+#pragma unroll
+                for (int k = 0; k < kBlockM / 16; ++k) {             // 128 pixels per stage = 8 MMAs of K = 16
+                    const uint64_t da = make_desc_sw128(sa + k * 2048, kATileBytes, 1024);
+                    const uint64_t db = make_desc_sw128(sb + k * 2048, kATileBytes, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int co = co0 + quarter * 32 + lane;
+        float* dst_row = gw + ((long long)tap * p.cout + co) * p.cin + ci0;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (co < p.cout) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (ci0 + c0 + j < p.cin) atomicAdd(dst_row + c0 + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype) {
+    if (dtype != GIM_BF16) return false;
+    if (cin % 8 != 0 || cout % 8 != 0) return false;
+    if (ks < 1 || !(ks & 1) || ks > 15) return false;
+    return n > 0 && h > 0 && wd > 0;
+}
+
+int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
+    WgradTcParams p;
+    p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
+    pixel_box(h, wd, p.bw, p.bh, p.bn);
+    p.tiles_w = (wd + p.bw - 1) / p.bw;
+    p.tiles_h = (h + p.bh - 1) / p.bh;
+    p.tiles_n = (n + p.bn - 1) / p.bn;
+    long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    if (total > 2147483647LL) return fail(GIM_E_ARG, "conv_wgrad_tc: too many tiles");
+    p.total_tiles = (int)total;
+    p.block_n = cin > 64 ? 128 : 64;
+    p.co_tiles = (cout + 127) / 128;
+    p.ci_tiles = (cin + p.block_n - 1) / p.block_n;
+    const int stage_bytes = 2 * kATileBytes + (p.block_n / 64) * kATileBytes;
+    p.stages = (200 * 1024) / stage_bytes;
+    const long long out_tiles = (long long)ks * ks * p.co_tiles * p.ci_tiles;
+    long long want = ((long long)num_sms() * 2 + out_tiles - 1) / out_tiles;        // ~2 waves of CTAs over the chip
+    long long max_split = (total + 3) / 4;                                         // at least ~4 pixel tiles per CTA
+    if (max_split < 1) max_split = 1;
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    p.tiles_per_split = (int)((total + want - 1) / want);
+    const int splits = (int)((total + p.tiles_per_split - 1) / p.tiles_per_split);
+    CUtensorMap map_gy, map_x;
+    if (!make_act_map(&map_gy, gy, n, h, wd, cout, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(gy) failed");
+    if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed");
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail(GIM_E_CUDA, "conv_wgrad_tc: cannot raise dynamic shared memory limit");
+        attr_set = true;
+    }
+    if (out_tiles > 2147483647LL) return fail(GIM_E_ARG, "conv_wgrad_tc: too many output tiles");
+    dim3 grid((unsigned)out_tiles, splits);
+    conv_wgrad_tc_kernel<0><<<grid, 192, smem, st>>>(map_gy, map_x, gw, p);
+    return check_launch("conv_wgrad_tc");
 }
 
 }  // namespace gim

@@ -1,0 +1,55 @@
+"""Data parallelism over independent episodes: one process per GPU, episodes sharded evenly, ONE gradient all-reduce(sum)
+per optimizer step over a flat fp32 bucket (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests), the 1/world
+scale folded into the fused Adam kernel.  Replaces the reference's nn.DataParallel (training/gim_img_training.py:406-411),
+whose math it reproduces: the mean over the global batch.  Nothing else crosses GPUs: spectral-norm
+u/v stay identical on all ranks because they depend only on the (replicated) weights and the call count.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch, rank, world):
+    """Rank r owns episodes [r*B/W, (r+1)*B/W); B % W == 0 as the reference enforces (gim_img_training.py:377)."""
+    if global_batch % world != 0:
+        raise ValueError("global batch %d is not divisible by world size %d" % (global_batch, world))
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+class FlatGradBucket:
+    """Re-homes the .grad of every parameter that receives gradients into one contiguous fp32 buffer (so the collective is a
+    single call and gradient addresses are stable for the fused Adam pointer table / CUDA graphs)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.grad is not None]      # unused parameters (img_att, out_mlp) are not waited on
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
+        off = 0
+        for p in self.params:
+            view = self.flat[off:off + p.numel()].view_as(p)
+            view.copy_(p.grad)
+            p.grad = view
+            off += p.numel()
+
+    def all_reduce(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+
+def attach(optimizer, group=None):
+    """Make `optimizer.step()` all-reduce its gradients first and apply the mean (grad_scale = 1/world)."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    optimizer.grad_scale = 1.0 / world
+    inner_step = optimizer.step
+    state = {"bucket": None}
+
+    def step(closure=None):
+        if world > 1:
+            if state["bucket"] is None:
+                state["bucket"] = FlatGradBucket([p for g in optimizer.param_groups for p in g["params"]])
+            state["bucket"].all_reduce(group)
+        return inner_step(closure)
+
+    optimizer.step = step
+    return optimizer

@@ -72,11 +72,48 @@ def _weight_as(w32, dtype, flip):
     return out
 
 
+_profile = None      # bench.py: {"kind": [ (flops, start_event, end_event), ... ]} while a profiling pass is active
+
+
+def conv_profile_begin():
+    global _profile
+    _profile = {}
+
+
+def conv_profile_end():
+    """-> {kind: {"flops", "ms", "launches"}} summed over the launches recorded since conv_profile_begin()."""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, recs in prof.items():
+        out[kind] = {"flops": float(sum(r[0] for r in recs)), "ms": float(sum(r[1].elapsed_time(r[2]) for r in recs)), "launches": len(recs)}
+    return out
+
+
+def _timed_call(kind, flops, name, *args):
+    if _profile is None:
+        C.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    C.call(name, *args)
+    e1.record()
+    _profile.setdefault(kind, []).append((flops, e0, e1))
+
+
+def _conv_kind(n, h, w, ci, co, ks, x, wgrad):
+    tc = _state["conv_algo"] != C.ALGO_SIMT and (C.wgrad_tc_supported if wgrad else C.conv_tc_supported)(n, h, w, ci, co, ks, C.dtype_code(x))
+    return ("tcgen05" if tc else "cuda_core") + ("_wgrad" if wgrad else "")
+
+
 def _conv_raw(x, w_t, bias, ks):
     n, h, w, ci = x.shape
     co = w_t.shape[1]
     y = _empty((n, h, w, co), x.dtype, x)
-    C.call("gim_conv2d_fwd", C.ptr(x), C.ptr(w_t), C.ptr(bias), C.ptr(y), n, h, w, ci, co, ks, C.dtype_code(x), _state["conv_algo"])
+    kind = _conv_kind(n, h, w, ci, co, ks, x, False) if _profile is not None else None
+    _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_fwd", C.ptr(x), C.ptr(w_t), C.ptr(bias), C.ptr(y), n, h, w, ci, co, ks,
+                C.dtype_code(x), _state["conv_algo"])
     return y
 
 
@@ -142,7 +179,9 @@ class WgradFn(Function):
         n, h, w, ci = x.shape
         co = g.shape[3]
         gw = _empty((ks * ks, co, ci), torch.float32, x)
-        C.call("gim_conv2d_wgrad", C.ptr(x), C.ptr(g), C.ptr(gw), n, h, w, ci, co, ks, C.dtype_code(x), _state["conv_algo"])
+        kind = _conv_kind(n, h, w, ci, co, ks, x, True) if _profile is not None else None
+        _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_wgrad", C.ptr(x), C.ptr(g), C.ptr(gw), n, h, w, ci, co, ks,
+                    C.dtype_code(x), _state["conv_algo"])
         return gw
 
     @staticmethod

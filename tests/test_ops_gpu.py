@@ -234,10 +234,11 @@ def test_set_statistics_with_double_backward():
         if s == 1:
             continue
         probe = rnd(b, 2 * d, seed=2)
+        q = rnd(b, s, d, seed=3)          # (sum g1^2 is ~independent of x for the std term, so contract with a random tensor)
         (g1r,) = torch.autograd.grad((ref * probe).sum(), x64, create_graph=True)
-        (g2r,) = torch.autograd.grad(g1r.pow(2).sum(), x64)
+        (g2r,) = torch.autograd.grad((g1r * q).sum(), x64)
         (g1,) = torch.autograd.grad((got * probe.float().cuda()).sum(), x, create_graph=True)
-        (g2,) = torch.autograd.grad(ops.RowsSqSumFn.apply(g1.reshape(1, -1)).sum(), x)
+        (g2,) = torch.autograd.grad(ops.DotFn.apply(g1, q.float().cuda()).sum(), x)
         assert rel_err(g1, g1r) < 1e-5 and rel_err(g2, g2r) < 1e-4
     w64, add64 = rnd(3, 4, 6, seed=3).requires_grad_(), rnd(3, 6, seed=4).requires_grad_()
     ref = w64 - w64.mean(1, keepdim=True) + add64.unsqueeze(1)
@@ -316,7 +317,7 @@ TC_SHAPES = [  # n, ci, co, k, h, w  -- every tensor-core-eligible layer family 
     (3, 64, 64, 3, 16, 16), (2, 128, 128, 3, 32, 32), (5, 256, 256, 3, 16, 16), (3, 512, 512, 3, 8, 8), (9, 512, 512, 3, 4, 4),
     (2, 128, 128, 9, 32, 32), (2, 64, 64, 9, 64, 64), (3, 128, 256, 3, 16, 16), (4, 256, 128, 1, 16, 16), (2, 128, 16, 1, 16, 16),
     (2, 256, 32, 1, 8, 8), (130, 512, 512, 3, 1, 1), (33, 512, 512, 3, 2, 2), (1, 64, 128, 3, 52, 52), (2, 128, 256, 3, 13, 13),
-    (1, 64, 64, 3, 105, 105),
+    (1, 64, 64, 3, 105, 105), (2, 16, 128, 1, 16, 16), (3, 32, 256, 1, 8, 8), (2, 64, 64, 1, 4, 4),
 ]
 
 
@@ -331,11 +332,15 @@ def test_conv_tcgen05_matches_cuda_core(shape):
     x = (rnd(n, h, w, ci, seed=1)).to("cuda", torch.bfloat16)
     wp = (rnd(k * k, co, ci, seed=2) / np.sqrt(ci * k * k)).to("cuda", torch.float32)
     b = rnd(co, seed=3).to("cuda", torch.float32)
-    outs = {}
+    gy = (rnd(n, h, w, co, seed=4)).to("cuda", torch.bfloat16)
+    outs, wg = {}, {}
     for algo in ("simt", "tcgen05"):
         ops.set_conv_algo(algo)
         with torch.no_grad():
             outs[algo] = ops.Conv2dFn.apply(x, wp, b, k).float()
+            wg[algo] = ops.WgradFn.apply(x, gy, k)
         torch.cuda.synchronize()
     assert rel_err(outs["tcgen05"], outs["simt"]) < 4e-3
     assert float((outs["tcgen05"] - outs["simt"]).abs().max()) < 0.05 * float(outs["simt"].abs().max())
+    assert C.wgrad_tc_supported(n, h, w, ci, co, k, C.BF16)
+    assert rel_err(wg["tcgen05"], wg["simt"]) < 1e-4          # same bf16 operands, fp32 accumulation in both

@@ -77,6 +77,10 @@ def rows_err(got, want, names=None):
     got, want = np.asarray(got), np.asarray(want)
     nan = np.isnan(want[:, 1])
     assert (np.isnan(got[:, 1]) == nan).all(), "set of parameters that receive gradients differs"
+    nan = nan.copy()
+    # parameters whose TRUE gradient is identically zero (conv biases feeding InstanceNorm/ada_in, the last noise-mapper bias under
+    # mean removal) carry pure rounding noise in every implementation, the reference's fp32 included: not comparable, skipped
+    nan = nan | (want[:, 1] < 1e-9 * np.nanmax(want[:, 1]))
     scale = np.maximum(want[~nan, 1], 1e-4 * np.nanmax(want[:, 1]))
     err = np.abs(got[~nan, 1] - want[~nan, 1]) / scale
     if names is not None:
