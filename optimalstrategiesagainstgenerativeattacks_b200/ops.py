@@ -107,14 +107,65 @@ def _conv_kind(n, h, w, ci, co, ks, x, wgrad):
     return ("tcgen05" if tc else "cuda_core") + ("_wgrad" if wgrad else "")
 
 
+def _pad_last(t, cp):
+    """Zero-pad the channel (last) dim of a contiguous tensor to cp (skinny layers -> tensor-core friendly widths)."""
+    c = t.shape[-1]
+    if c == cp:
+        return t
+    out = torch.zeros(t.shape[:-1] + (cp,), dtype=t.dtype, device=t.device)
+    C.call("gim_copy_cols", C.ptr(t), c, 0, C.ptr(out), cp, 0, t.numel() // c, c, C.dtype_code(t))
+    return out
+
+
+def _narrow_last(t, c):
+    cp = t.shape[-1]
+    if c == cp:
+        return t
+    out = torch.empty(t.shape[:-1] + (c,), dtype=t.dtype, device=t.device)
+    C.call("gim_copy_cols", C.ptr(t), cp, 0, C.ptr(out), c, 0, out.numel() // c, c, C.dtype_code(t))
+    return out
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _use_tc(x):
+    return x.dtype == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT
+
+
 def _conv_raw(x, w_t, bias, ks):
+    """x [n,h,w,ci], w_t [taps,co,ci] (activation dtype), bias fp32|None.  On the bf16 path skinny channel counts (image / last
+    layers: 1, 2, 3, 6) are zero-padded to 8 (inputs) / 16 (outputs) so that every conv runs on the tcgen05 kernel."""
     n, h, w, ci = x.shape
     co = w_t.shape[1]
+    if _use_tc(x) and (ci % 8 or co % 16):
+        cip, cop = _round_up(ci, 8), _round_up(co, 16)
+        wp = torch.zeros((w_t.shape[0], cop, cip), dtype=w_t.dtype, device=w_t.device)
+        wp[:, :co, :ci] = w_t
+        bp = None
+        if bias is not None:
+            bp = torch.zeros((cop,), dtype=torch.float32, device=x.device)
+            bp[:co] = bias
+        return _narrow_last(_conv_raw(_pad_last(x, cip), wp, bp, ks), co)
     y = _empty((n, h, w, co), x.dtype, x)
     kind = _conv_kind(n, h, w, ci, co, ks, x, False) if _profile is not None else None
     _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_fwd", C.ptr(x), C.ptr(w_t), C.ptr(bias), C.ptr(y), n, h, w, ci, co, ks,
                 C.dtype_code(x), _state["conv_algo"])
     return y
+
+
+def _wgrad_raw(x, g, ks):
+    n, h, w, ci = x.shape
+    co = g.shape[3]
+    if _use_tc(x) and (ci % 8 or co % 8):
+        gwp = _wgrad_raw(_pad_last(x, _round_up(ci, 8)), _pad_last(g, _round_up(co, 8)), ks)
+        return gwp[:, :co, :ci].contiguous()
+    gw = _empty((ks * ks, co, ci), torch.float32, x)
+    kind = _conv_kind(n, h, w, ci, co, ks, x, True) if _profile is not None else None
+    _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_wgrad", C.ptr(x), C.ptr(g), C.ptr(gw), n, h, w, ci, co, ks,
+                C.dtype_code(x), _state["conv_algo"])
+    return gw
 
 
 class Conv2dFn(Function):
@@ -176,12 +227,7 @@ class WgradFn(Function):
         g = _c(g)
         ctx.ks = ks
         ctx.save_for_backward(x, g)
-        n, h, w, ci = x.shape
-        co = g.shape[3]
-        gw = _empty((ks * ks, co, ci), torch.float32, x)
-        kind = _conv_kind(n, h, w, ci, co, ks, x, True) if _profile is not None else None
-        _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_wgrad", C.ptr(x), C.ptr(g), C.ptr(gw), n, h, w, ci, co, ks,
-                    C.dtype_code(x), _state["conv_algo"])
+        gw = _wgrad_raw(x, g, ks)
         return gw
 
     @staticmethod
