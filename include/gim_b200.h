@@ -42,9 +42,10 @@ int         gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout
 long long   gim_launch_count(int reset);
 
 /* ---- convolution: nn.Conv2d forward / input-grad / weight-grad (model_blocks.py:497-514, 753-773, 795-865) ---- */
-/* y[n,h,w,co] = bias[co] + sum_{r,s,ci} x[n,h+r-p,w+s-p,ci] * w[r*k+s][co][ci];  x,y,w: dtype; bias fp32 or NULL */
+/* y[n,h,w,co] = bias[co] + sum_{r,s,ci} x[n,h+r-p,w+s-p,ci] * w[r*k+s][co][ci];  x,w: dtype; y: out_dtype (fp32 accumulate
+ * either way: bf16 operands with an fp32 result is the mixed-precision tensor-core path); bias fp32 or NULL */
 int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y,
-                   int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t stream);
+                   int n, int h, int wd, int cin, int cout, int ksize, int dtype, int out_dtype, int algo, gim_stream_t stream);
 /* gw[t][co][ci] (fp32) = sum_{n,h,w} gy[n,h,w,co] * x[n,h+r-p,w+s-p,ci]  (overwrites gw) */
 int gim_conv2d_wgrad(const void* x, const void* gy, float* gw,
                      int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t stream);

@@ -8,9 +8,9 @@ namespace gim {
 constexpr int BK = 16;
 
 // y[pix][co] = bias[co] + sum_kf A(pix,kf) * w[tap(kf)][co][ci(kf)],  kf = tap*cin + ci flattened so tiny-Cin layers waste nothing.
-template <typename T, int BM, int BN>
+template <typename T, typename TO, int BM, int BN>
 __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
-                                                            T* __restrict__ y, int n, int h, int wd, int cin, int cout, int ks) {
+                                                            TO* __restrict__ y, int n, int h, int wd, int cin, int cout, int ks) {
     static_assert((BM / 4) * (BN / 4) == 256, "tile must map onto 256 threads of 4x4 outputs");
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(const T* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int co = n0 + tx * 4 + j;
-            if (co < cout) y[g * cout + co] = from_f<T>(acc[i][j] + (bias ? bias[co] : 0.f));
+            if (co < cout) y[g * cout + co] = from_f<TO>(acc[i][j] + (bias ? bias[co] : 0.f));
         }
     }
 }
@@ -232,15 +232,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
     }
 }
 
-template <typename T>
+template <typename T, typename TO>
 static int conv_fwd_simt(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
     long long npix = (long long)n * h * wd;
     if (cout <= 16) {
         dim3 grid((unsigned)((npix + 255) / 256), (cout + 15) / 16);
-        conv_fwd_simt_kernel<T, 256, 16><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, (T*)y, n, h, wd, cin, cout, ks);
+        conv_fwd_simt_kernel<T, TO, 256, 16><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, (TO*)y, n, h, wd, cin, cout, ks);
     } else {
         dim3 grid((unsigned)((npix + 63) / 64), (cout + 63) / 64);
-        conv_fwd_simt_kernel<T, 64, 64><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, (T*)y, n, h, wd, cin, cout, ks);
+        conv_fwd_simt_kernel<T, TO, 64, 64><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, (TO*)y, n, h, wd, cin, cout, ks);
     }
     return check_launch("conv_fwd_simt");
 }
@@ -267,7 +267,8 @@ static int conv_wgrad_simt(const void* x, const void* gy, float* gw, int n, int 
 }
 
 // implemented in conv_tc.cu
-int conv_fwd_tc(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st);
+int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, int out_f32,
+                   cudaStream_t st);
 int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st);
 bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
 bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
@@ -286,16 +287,21 @@ int gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout, int ks
     return wgrad_tc_supported(n, h, w, cin, cout, ksize, dtype) ? 1 : 0;
 }
 
-int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo,
-                   gim_stream_t s) {
+int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ksize, int dtype,
+                   int out_dtype, int algo, gim_stream_t s) {
     GIM_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv2d_fwd: empty shape");
     GIM_REQUIRE(ksize >= 1 && (ksize & 1), "conv2d_fwd: kernel size must be odd ('same' padding)");
     GIM_REQUIRE((long long)n * h * wd / 64 + 1 < 2147483647LL, "conv2d_fwd: too many pixels");
     cudaStream_t st = (cudaStream_t)s;
     bool tc_ok = conv_tc_supported(n, h, wd, cin, cout, ksize, dtype);
     if (algo == GIM_ALGO_TCGEN05 && !tc_ok) return fail(GIM_E_UNSUPPORTED, "conv2d_fwd: shape/dtype not supported by the tcgen05 path");
-    if ((algo == GIM_ALGO_TCGEN05) || (algo == GIM_ALGO_AUTO && tc_ok)) return conv_fwd_tc(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
-    GIM_DISPATCH_DTYPE(dtype, return conv_fwd_simt<T>(x, w, bias, y, n, h, wd, cin, cout, ksize, st));
+    GIM_REQUIRE(out_dtype == GIM_F32 || out_dtype == dtype, "conv2d_fwd: output must be fp32 or the operand dtype");
+    if ((algo == GIM_ALGO_TCGEN05) || (algo == GIM_ALGO_AUTO && tc_ok))
+        return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ksize, out_dtype == GIM_F32 ? 1 : 0, st);
+    if (dtype == GIM_F32) return conv_fwd_simt<float, float>(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
+    if (dtype == GIM_BF16 && out_dtype == GIM_F32) return conv_fwd_simt<bf16, float>(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
+    if (dtype == GIM_BF16) return conv_fwd_simt<bf16, bf16>(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
+    return fail(GIM_E_ARG, "conv2d_fwd: bad dtype");
 }
 
 int gim_conv2d_wgrad(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t s) {

@@ -119,7 +119,7 @@ struct ConvTcParams {
 };
 
 template <int kDummy>
-__global__ void __launch_bounds__(192, 1) conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+__global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                                              const float* __restrict__ bias, void* __restrict__ y, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B needs 1024-byte alignment
@@ -322,8 +322,9 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     p.block_n = pick_block_n(cout);
     p.out_f32 = out_f32;
     const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
-    int stages = (200 * 1024) / stage_bytes;
-    if (stages > 8) stages = 8;
+    // two CTAs per SM (<= ~110 KB each): one CTA's epilogue overlaps the other's MMA main loop
+    int stages = (104 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
     p.stages = stages;
     CUtensorMap map_x, map_w;
     if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
@@ -342,9 +343,6 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     return check_launch("conv_fwd_tc");
 }
 
-int conv_fwd_tc(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
-    return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ks, 0, st);
-}
 
 // ----------------------------------------------------------------------------------------------------------------
 // weight gradient:  dW[tap][co][ci] = sum_pix dY[pix][co] * X[pix + tap][ci]

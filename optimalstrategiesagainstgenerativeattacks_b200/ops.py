@@ -12,6 +12,7 @@ Activations are NHWC tensors of the active precision (`set_precision`): float32 
 bfloat16 (tcgen05 tensor-core path).  Feature vectors, statistics, weights and weight gradients are float32.
 """
 import contextlib
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -20,20 +21,29 @@ from torch.autograd.function import once_differentiable
 from . import _cabi as C
 
 LRELU_SLOPE = 0.2
-_state = {"act_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False}
+_state = {"operand_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False}
 
 
 def set_precision(name):
-    """'fp32' (rel 1e-4 parity path) or 'bf16' (tensor-core path, rel 2e-2)."""
-    _state["act_dtype"] = {"fp32": torch.float32, "bf16": torch.bfloat16}[name]
+    """'fp32': everything float32, CUDA-core FFMA convolutions (rel 1e-4 parity path).
+    'bf16': mixed precision -- every convolution / Linear operand (activation, gradient, weight) is rounded to bfloat16
+    once and multiplied on the tcgen05 tensor cores with fp32 accumulation; everything else (conv results, residual
+    sums, pooling, norm statistics, losses, optimizer) stays float32 (rel 2e-2 path)."""
+    _state["operand_dtype"] = {"fp32": torch.float32, "bf16": torch.bfloat16}[name]
+    _cast_memo.clear()
 
 
 def get_precision():
-    return "fp32" if _state["act_dtype"] == torch.float32 else "bf16"
+    return "fp32" if _state["operand_dtype"] == torch.float32 else "bf16"
 
 
 def act_dtype():
-    return _state["act_dtype"]
+    """Storage dtype of activations between operators (always float32; bf16 only exists as conv operands)."""
+    return torch.float32
+
+
+def operand_dtype():
+    return _state["operand_dtype"]
 
 
 def set_conv_algo(algo):
@@ -58,6 +68,25 @@ def _empty(shape, dtype, like):
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+_cast_memo = {}     # id(tensor) -> (weakref, version, operand copy): conv_l1 / attention convs / dgrad+wgrad share one cast
+
+
+def _operand(t):
+    """The tensor as a conv/GEMM operand of the active precision (one rounding to bf16 on the tensor-core path)."""
+    od = _state["operand_dtype"]
+    if t.dtype == od:
+        return t
+    hit = _cast_memo.get(id(t))
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    out = torch.empty(t.shape, dtype=od, device=t.device)
+    C.call("gim_cast", C.ptr(t), C.dtype_code(t), C.ptr(out), C.dtype_code(out), t.numel())
+    if len(_cast_memo) >= 4:
+        _cast_memo.clear()
+    _cast_memo[id(t)] = (weakref.ref(t), t._version, out)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -135,8 +164,8 @@ def _use_tc(x):
 
 
 def _conv_raw(x, w_t, bias, ks):
-    """x [n,h,w,ci], w_t [taps,co,ci] (activation dtype), bias fp32|None.  On the bf16 path skinny channel counts (image / last
-    layers: 1, 2, 3, 6) are zero-padded to 8 (inputs) / 16 (outputs) so that every conv runs on the tcgen05 kernel."""
+    """x [n,h,w,ci], w_t [taps,co,ci] (both operand dtype), bias fp32|None -> fp32 [n,h,w,co].  On the bf16 path skinny channel
+    counts (image / last layers: 1, 2, 3, 6) are zero-padded to 8 (inputs) / 16 (outputs) so every conv runs on tcgen05."""
     n, h, w, ci = x.shape
     co = w_t.shape[1]
     if _use_tc(x) and (ci % 8 or co % 16):
@@ -148,10 +177,10 @@ def _conv_raw(x, w_t, bias, ks):
             bp = torch.zeros((cop,), dtype=torch.float32, device=x.device)
             bp[:co] = bias
         return _narrow_last(_conv_raw(_pad_last(x, cip), wp, bp, ks), co)
-    y = _empty((n, h, w, co), x.dtype, x)
+    y = _empty((n, h, w, co), torch.float32, x)
     kind = _conv_kind(n, h, w, ci, co, ks, x, False) if _profile is not None else None
     _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_fwd", C.ptr(x), C.ptr(w_t), C.ptr(bias), C.ptr(y), n, h, w, ci, co, ks,
-                C.dtype_code(x), _state["conv_algo"])
+                C.dtype_code(x), C.F32, _state["conv_algo"])
     return y
 
 
@@ -178,7 +207,7 @@ class Conv2dFn(Function):
         ctx.ks = ks
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, w32)
-        return _conv_raw(x, _weight_as(w32, x.dtype, False), bias, ks)
+        return _conv_raw(_operand(x), _weight_as(w32, operand_dtype(), False), bias, ks)
 
     @staticmethod
     def backward(ctx, gy):
@@ -204,7 +233,7 @@ class ConvTransposeFn(Function):
         w32 = _c(w32)
         ctx.ks = ks
         ctx.save_for_backward(g, w32)
-        return _conv_raw(g, _weight_as(w32, g.dtype, True), None, ks)
+        return _conv_raw(_operand(g), _weight_as(w32, operand_dtype(), True), None, ks)
 
     @staticmethod
     def backward(ctx, gout):
@@ -227,7 +256,7 @@ class WgradFn(Function):
         g = _c(g)
         ctx.ks = ks
         ctx.save_for_backward(x, g)
-        gw = _wgrad_raw(x, g, ks)
+        gw = _wgrad_raw(_operand(x), _operand(g), ks)
         return gw
 
     @staticmethod
@@ -498,7 +527,7 @@ class FromNHWCFn(Function):
 
 
 def to_nhwc(x):
-    return ToNHWCFn.apply(x, act_dtype())
+    return ToNHWCFn.apply(x, torch.float32)
 
 
 def from_nhwc(x):
@@ -671,11 +700,20 @@ class BiasActFn(Function):
 
 
 def linear(x, weight, bias, slope=1.0):
-    """nn.Linear (+ optional LeakyReLU) on the last dim; x fp32 [..., in]."""
+    """nn.Linear (+ optional LeakyReLU) on the last dim; x fp32 [..., in].  On the bf16 path a Linear is a 1x1 convolution over
+    `rows` one-pixel images, so it runs on the same tcgen05 implicit-GEMM kernels (forward, input- and weight-gradient)."""
     shp = x.shape
-    y = matmul(x.reshape(-1, shp[-1]), weight, False, True)
-    y = BiasActFn.apply(y, bias, slope)
-    return y.reshape(shp[:-1] + (weight.shape[0],))
+    x2 = x.reshape(-1, shp[-1])
+    rows, k = x2.shape
+    n = weight.shape[0]
+    if _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and k % 8 == 0 and n % 16 == 0 and rows >= 16:
+        y = Conv2dFn.apply(x2.reshape(rows, 1, 1, k), weight.reshape(1, n, k), bias, 1).reshape(rows, n)
+        if slope != 1.0:
+            y = LReluFn.apply(y, slope)
+    else:
+        y = matmul(x2, weight, False, True)
+        y = BiasActFn.apply(y, bias, slope)
+    return y.reshape(shp[:-1] + (n,))
 
 
 class SoftmaxRowsFn(Function):

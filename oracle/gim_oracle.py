@@ -36,6 +36,64 @@ def lrelu(x):
 
 
 # ---------------------------------------------------------------------------------------------
+# Optional emulation of the build's bf16 tensor-core numerics (NOT part of the reference): every conv / Linear operand --
+# activation, weight and the incoming gradient in the backward -- is rounded to bfloat16 once, products accumulate in fp32,
+# everything else stays fp32.  tests/test_parity_gpu.py uses it to separate "implementation error" (CUDA path vs this
+# emulation: tight) from "arithmetic error" (this emulation vs the float64 reference: what bf16 operands cost).
+# ---------------------------------------------------------------------------------------------
+OPERAND_BF16 = False
+
+
+def set_operand_rounding(flag):
+    global OPERAND_BF16
+    OPERAND_BF16 = bool(flag)
+
+
+def _r(t):
+    return t.bfloat16().to(t.dtype)
+
+
+class _ConvBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, padding):
+        xr, wr = _r(x), _r(w)
+        ctx.save_for_backward(xr, wr)
+        ctx.padding = padding
+        ctx.has_bias = b is not None
+        return F.conv2d(xr, wr, b, stride=1, padding=padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, wr = ctx.saved_tensors
+        gb = gy.sum(dim=(0, 2, 3)) if ctx.has_bias else None
+        gyr = _r(gy)
+        gx = torch.nn.grad.conv2d_input(xr.shape, wr, gyr, stride=1, padding=ctx.padding)
+        gw = torch.nn.grad.conv2d_weight(xr, wr.shape, gyr, stride=1, padding=ctx.padding)
+        return gx, gw, gb, None
+
+
+class _LinearBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xr, wr = _r(x), _r(w)
+        ctx.save_for_backward(xr, wr)
+        return F.linear(xr, wr, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, wr = ctx.saved_tensors
+        gyr = _r(gy)
+        g2 = gyr.reshape(-1, gyr.shape[-1])
+        return gyr @ wr, g2.t() @ xr.reshape(-1, xr.shape[-1]), gy.reshape(-1, gy.shape[-1]).sum(0)
+
+
+def conv2d_op(x, w, b, padding):
+    if OPERAND_BF16:
+        return _ConvBF16.apply(x, w, b, padding)
+    return F.conv2d(x, w, b, stride=1, padding=padding)
+
+
+# ---------------------------------------------------------------------------------------------
 # spectral norm (torch.nn.utils.spectral_norm, old-style hook; call sites model_blocks.py:492-495,
 # 522-526, 750-751, 792-793, 836-840).  One power iteration per forward call in train mode,
 # in place on weight_u / weight_v; sigma = u^T W v with u, v treated as constants.
@@ -59,7 +117,7 @@ def sn_weight(p, prefix, training=True):
 
 def sn_conv(p, prefix, x, padding, training=True):
     w = sn_weight(p, prefix, training)
-    return F.conv2d(x, w, p[prefix + ".bias"], stride=1, padding=padding)
+    return conv2d_op(x, w, p[prefix + ".bias"], padding)
 
 
 def avg_pool2(x):
@@ -91,7 +149,11 @@ def ada_in(x, mean_style, std_style):
 
 
 def linear(p, prefix, x):
-    return F.linear(x, p[prefix + ".weight"], p[prefix + ".bias"])
+    w, b = p[prefix + ".weight"], p[prefix + ".bias"]
+    rows = x.numel() // x.shape[-1]
+    if OPERAND_BF16 and w.shape[1] % 8 == 0 and w.shape[0] % 16 == 0 and rows >= 16:     # the layers the build runs on tensor cores
+        return _LinearBF16.apply(x, w, b)
+    return F.linear(x, w, b)
 
 
 def mlp(p, prefix, x, n_layers):
