@@ -69,15 +69,31 @@ class FusedAdam(torch.optim.Adam):
         if key != self._table_key:
             self._build(active, device)
             self._table_key = key
-        lrs = [float(g["lr"]) for g in self.param_groups]
-        if lrs != self._lrs_host:
-            self._lrs_dev = torch.tensor(lrs, dtype=torch.float32, device=device)
-            self._lrs_host = lrs
+        self._device = device
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lrs()
         (b1, b2), eps = next(iter(betas)), next(iter(epss))
         C.call("gim_adam_multi", self._table_dev.data_ptr(), self._n, self._max_numel, self._lrs_dev.data_ptr(),
                self._step_dev.data_ptr(), b1, b2, eps, float(self.grad_scale))
-        self._steps_done += 1
+        if not torch.cuda.is_current_stream_capturing():
+            self._steps_done += 1
         return loss
+
+    def sync_lrs(self):
+        """Upload the per-group learning rates if a scheduler changed them (in place: the device array is referenced by
+        captured CUDA graphs)."""
+        lrs = [float(g["lr"]) for g in self.param_groups]
+        if lrs != self._lrs_host and getattr(self, "_device", None) is not None:
+            if self._lrs_dev is None:
+                self._lrs_dev = torch.tensor(lrs, dtype=torch.float32, device=self._device)
+            else:
+                self._lrs_dev.copy_(torch.tensor(lrs, dtype=torch.float32))
+            self._lrs_host = lrs
+
+    def note_graph_steps(self, n):
+        """Account for optimizer steps executed by CUDA-graph replays (the host-side counter is only used for state_dict)."""
+        if self._steps_done is not None:
+            self._steps_done += n
 
     def state_dict(self):
         # publish the device-side step count in torch's per-parameter `step` entries
