@@ -285,6 +285,11 @@ def run_ours(args):
     iteration(*dev_pool[0])                       # eager, so that events can bracket each launch
     torch.cuda.synchronize()
     prof = ops.conv_profile_end()
+    shapes = prof.pop("_shapes", {})
+    if rank == 0 and os.environ.get("GIM_PROFILE_SHAPES"):
+        for key, (fl, ms, cnt) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:40]:
+            print("shape %-14s n=%-6d h=%-3d w=%-3d ci=%-4d co=%-4d k=%d  x%-3d %8.3f ms %7.1f TFLOP/s" % (key + (cnt, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0)),
+                  file=sys.stderr)
 
     if rank != 0:
         if world > 1:

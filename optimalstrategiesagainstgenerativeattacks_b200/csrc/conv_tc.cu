@@ -56,6 +56,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
                  "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(src)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -93,9 +102,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // shared-memory matrix descriptor (sm_100 format, version 1), SWIZZLE_128B.
 //   K-major operand : rows of 128 B (64 bf16 along K); 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major operand: 64 MN elements contiguous (128 B) per K index, 8 K-rows = one 1024 B atom (SBO), next 64-wide MN block at LBO.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-           (1ull << 46) | (2ull << 61);
+           (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_desc(saddr, lbo_bytes, sbo_bytes, 2);      // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
 }
 // instruction descriptor, kind::f16: D fp32, A/B bf16, M=128, N=n; a_mn / b_mn = 1 for MN-major operands
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t n, uint32_t a_mn, uint32_t b_mn) {
@@ -116,14 +128,18 @@ struct ConvTcParams {
     int block_n;                                 // N tile (output channels per CTA)
     int stages;
     int out_f32;                                 // 1: y is fp32, 0: bf16
+    int tma_store;                               // 1: epilogue stages the tile in smem (128B-swizzled) and writes it with TMA
+    int block_k;                                 // K elements per stage: 64 (128-byte rows, SWIZZLE_128B) or 16 (32-byte rows, SWIZZLE_32B)
 };
 
 template <int kDummy>
 __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                                                             const float* __restrict__ bias, void* __restrict__ y, const ConvTcParams p) {
+                                                             const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias,
+                                                             void* __restrict__ y, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B needs 1024-byte alignment
-    const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
+    const int a_bytes = kBlockM * p.block_k * 2;
+    const int stage_bytes = (a_bytes + p.block_n * p.block_k * 2 + 1023) & ~1023;
     uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* tmem_full_bar = empty_bar + p.stages;
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
     const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tn * p.bn;
     const int n0 = blockIdx.y * p.block_n;
     const int pad = (p.ks - 1) / 2;
-    const int kc_per_tap = (p.cin + kBlockK - 1) / kBlockK;      // a ragged last K block is zero-filled by TMA (OOB channels)
+    const int kc_per_tap = (p.cin + p.block_k - 1) / p.block_k;  // a ragged last K block is zero-filled by TMA (OOB channels)
     const int num_kb = p.ks * p.ks * kc_per_tap;
     const uint32_t tmem_cols = p.block_n < 32 ? 32u : (uint32_t)p.block_n;
 
@@ -164,10 +180,10 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
                 const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
                 const int r = tap / p.ks, q = tap - r * p.ks;
                 uint8_t* sa = smem + s * stage_bytes;
-                uint8_t* sb = sa + kATileBytes;
-                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                tma_load_4d(sa, &map_x, &full_bar[s], kc * kBlockK, w0 + q - pad, h0 + r - pad, img0);
-                tma_load_2d(sb, &map_w, &full_bar[s], kc * kBlockK, tap * p.cout + n0);
+                uint8_t* sb = sa + a_bytes;
+                mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + p.block_n * p.block_k * 2));
+                tma_load_4d(sa, &map_x, &full_bar[s], kc * p.block_k, w0 + q - pad, h0 + r - pad, img0);
+                tma_load_2d(sb, &map_w, &full_bar[s], kc * p.block_k, tap * p.cout + n0);
             }
         }
     } else if (warp == 1) {
@@ -179,12 +195,16 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
                 mbar_wait(&full_bar[s], round & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * stage_bytes);
-                const uint32_t sb = sa + kATileBytes;
+                const uint32_t sb = sa + a_bytes;
+                if (p.block_k == 64) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t da = make_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t db = make_desc_sw128(sb + k * 32, 16, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = make_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t db = make_desc_sw128(sb + k * 32, 16, 1024);
+                        umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                } else {                                  // 16 K elements: rows of 32 B, 8-row groups 256 B apart, SWIZZLE_32B
+                    umma_bf16(tmem_base, make_desc(sa, 16, 256, 6), make_desc(sb, 16, 256, 6), idesc, kb != 0 ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
             }
@@ -200,6 +220,55 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
         const int ww = w0 + lw, hh = h0 + lh, img = img0 + ln;
         const bool valid = ww < p.w && hh < p.h && img < p.n;
         const long long pix = ((long long)img * p.h + hh) * p.w + ww;
+        if (p.tma_store) {
+            // Stage the tile in the (now idle) pipeline buffers as 128-byte-swizzled boxes of 128 rows x 128 B and let TMA write
+            // them: coalesced full-line stores, image-border clipping by the tensor map, no per-lane address math.
+            const int cols_per_box = p.out_f32 ? 32 : 64;
+            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                uint32_t v[32];
+                {
+                    uint32_t lo[16], hi[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, lo);
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c0 + 16), hi);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { v[j] = lo[j]; v[16 + j] = hi[j]; }
+                }
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + ((bias && n0 + c0 + j < p.cout) ? __ldg(&bias[n0 + c0 + j]) : 0.f);
+                if (p.out_f32) {
+                    uint8_t* box = smem + (c0 / 32) * (kBlockM * 128) + m * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(box + ((j ^ (m & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint8_t* box = smem + (c0 / 64) * (kBlockM * 128) + m * 128;
+                    const int jb = (c0 % 64) / 8;            // first 16-byte chunk of this 32-column group inside the 64-column box
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+                        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                        o.x = *reinterpret_cast<uint32_t*>(&b0);
+                        o.y = *reinterpret_cast<uint32_t*>(&b1);
+                        o.z = *reinterpret_cast<uint32_t*>(&b2);
+                        o.w = *reinterpret_cast<uint32_t*>(&b3);
+                        *reinterpret_cast<uint4*>(box + (((jb + j) ^ (m & 7)) << 4)) = o;
+                    }
+                }
+            }
+            fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA (async proxy)
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
+            if (warp == 2 && lane == 0) {
+                const int nbox = (p.block_n + cols_per_box - 1) / cols_per_box;
+                for (int b = 0; b < nbox; ++b)
+                    if (n0 + b * cols_per_box < p.cout) tma_store_4d(&map_y, smem + b * (kBlockM * 128), n0 + b * cols_per_box, w0, h0, img0);
+                tma_store_commit_wait();                       // smem must stay valid until TMA has read it
+            }
+        } else {
         for (int c0 = 0; c0 < p.block_n; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
@@ -229,6 +298,7 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
                     }
                 }
             }
+        }
         }
     }
     tc_fence_before();
@@ -273,26 +343,41 @@ static void pixel_box(int h, int w, int& bw, int& bh, int& bn) {
 }
 
 // 4-D map over an NHWC bf16 tensor, box {64 ch, bw, bh, bn}, 128B swizzle, zero OOB fill
-static bool make_act_map(CUtensorMap* map, const void* x, int n, int h, int w, int c, int bw, int bh, int bn) {
+static bool make_act_map(CUtensorMap* map, const void* x, int n, int h, int w, int c, int bw, int bh, int bn, int box_k = kBlockK) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    cuuint32_t box[4] = {(cuuint32_t)box_k, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               box_k == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// 4-D map over the NHWC output (fp32: box of 32 columns, bf16: 64 columns = 128 B), 128B swizzle; TMA clips at the tensor border
+static bool make_out_map(CUtensorMap* map, void* y, int n, int h, int w, int c, int bw, int bh, int bn, int out_f32) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t es = out_f32 ? 4 : 2;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c * es, (cuuint64_t)w * c * es, (cuuint64_t)h * w * c * es};
+    cuuint32_t box[4] = {(cuuint32_t)(out_f32 ? 32 : 64), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // 2-D map over a row-major bf16 matrix [rows][cols], box {64 cols, box_rows}
-static bool make_mat_map(CUtensorMap* map, const void* m, long long rows, int cols, int box_rows) {
+static bool make_mat_map(CUtensorMap* map, const void* m, long long rows, int cols, int box_rows, int box_k = kBlockK) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(m), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               box_k == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int pick_block_n(int cout) {
@@ -321,14 +406,19 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     p.tiles_n = (n + p.bn - 1) / p.bn;
     p.block_n = pick_block_n(cout);
     p.out_f32 = out_f32;
-    const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
+    p.block_k = cin <= 16 ? 16 : kBlockK;          // skinny inputs (padded images): 32-byte K rows, one MMA per filter tap
+    const int stage_bytes = (kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2 + 1023) & ~1023;
     // two CTAs per SM (<= ~110 KB each): one CTA's epilogue overlaps the other's MMA main loop
     int stages = (104 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
+    if (stages > 8) stages = 8;
     p.stages = stages;
-    CUtensorMap map_x, map_w;
-    if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
-    if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.block_n)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
+    CUtensorMap map_x, map_w, map_y;
+    // staged TMA-store epilogue when a whole 32-column group exists and the tile fits in the idle pipeline buffers
+    p.tma_store = (p.block_n >= 32 && (size_t)kBlockM * p.block_n * (out_f32 ? 4 : 2) <= (size_t)stages * stage_bytes) ? 1 : 0;
+    if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
+    if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn, p.block_k)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
+    if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.block_n, p.block_k))
+        return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
     const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -339,7 +429,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     if (tiles > 2147483647LL) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
     dim3 grid((unsigned)tiles, (cout + p.block_n - 1) / p.block_n);
-    conv_fwd_tc_kernel<0><<<grid, 192, smem, st>>>(map_x, map_w, bias, y, p);
+    conv_fwd_tc_kernel<0><<<grid, 192, smem, st>>>(map_x, map_w, map_y, bias, y, p);
     return check_launch("conv_fwd_tc");
 }
 

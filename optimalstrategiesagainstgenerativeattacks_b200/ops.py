@@ -115,8 +115,15 @@ def conv_profile_end():
     prof, _profile = _profile, None
     torch.cuda.synchronize()
     out = {}
+    shapes = {}
     for kind, recs in prof.items():
         out[kind] = {"flops": float(sum(r[0] for r in recs)), "ms": float(sum(r[1].elapsed_time(r[2]) for r in recs)), "launches": len(recs)}
+        for r in recs:
+            e = shapes.setdefault((kind,) + r[3], [0.0, 0.0, 0])
+            e[0] += r[0]
+            e[1] += r[1].elapsed_time(r[2])
+            e[2] += 1
+    out["_shapes"] = shapes
     return out
 
 
@@ -128,7 +135,7 @@ def _timed_call(kind, flops, name, *args):
     e0.record()
     C.call(name, *args)
     e1.record()
-    _profile.setdefault(kind, []).append((flops, e0, e1))
+    _profile.setdefault(kind, []).append((flops, e0, e1, tuple(args[4:10])))     # (n, h, w, ci, co, ks) for conv / wgrad calls
 
 
 def _conv_kind(n, h, w, ci, co, ks, x, wgrad):
