@@ -89,6 +89,11 @@ int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int d
 int gim_copy_cols(const void* src, int src_ld, int src_off, void* dst, int dst_ld, int dst_off,
                   long long rows, int c, int dtype, gim_stream_t stream);
 int gim_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, gim_stream_t stream);
+/* tap unrolling of skinny-channel tensors (c in {1,2,3,6}) so their convs become dense 1x1 tensor-core GEMMs:
+ * out[pix][t*c+ch] = x[pix + sign*offset(t)][ch] (zeros outside / for j >= k*k*c), rows of length kc */
+int gim_im2col(const void* x, void* out, int n, int h, int wd, int c, int ksize, int sign, int kc, int dtype, gim_stream_t stream);
+/* y[pix][ch] = bias[ch] + sum_t z[pix + offset(t)][t*c+ch]  (fp32; z rows of length ld) -- the adjoint gather */
+int gim_col2im(const float* z, const float* bias, float* y, int n, int h, int wd, int c, int ksize, int ld, gim_stream_t stream);
 
 /* ---- InstanceNorm2d / ada_in (model_blocks.py:611-630, 747-748; gim_img_models.py:126) ---- */
 /* per (n,c): mean and M2 = sum (x-mean)^2 over the hw pixels */

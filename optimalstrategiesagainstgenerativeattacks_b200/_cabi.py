@@ -39,6 +39,8 @@ PROTOTYPES = {
     "gim_nhwc_to_nchw": "ppiiiiip",
     "gim_copy_cols": "piipiiliip",
     "gim_cast": "pipilp",
+    "gim_im2col": "ppiiiiiiiip",
+    "gim_col2im": "pppiiiiiip",
     "gim_norm_stats": "pppiiiip",
     "gim_affine_act_fwd": "pppppiiifip",
     "gim_norm_bwd_reduce": "ppppppiiifip",

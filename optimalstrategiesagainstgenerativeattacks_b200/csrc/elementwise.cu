@@ -171,6 +171,53 @@ __global__ void __launch_bounds__(256) copy_cols_kernel(const T* __restrict__ sr
     }
 }
 
+// out[pix][t*c + ch] = x[pix + sign * tap_offset(t)][ch] (zero outside the image, zero for the padded tail j >= taps*c).
+// Skinny-channel tensors (images, last layers) are unrolled over the filter taps so that their convolutions become dense
+// 1x1 tensor-core GEMMs with K (or N) = taps * c.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int h, int w, int c, int ks, int sign, int kc) {
+    const int pad = (ks - 1) / 2, taps = ks * ks;
+    long long total = (long long)n * h * w * kc;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int j = (int)(i % kc);
+        long long pix = i / kc;
+        float v = 0.f;
+        if (j < taps * c) {
+            int t = j / c, ch = j - t * c;
+            int pw = (int)(pix % w);
+            long long r = pix / w;
+            int ph = (int)(r % h);
+            long long img = r / h;
+            int hh = ph + sign * (t / ks - pad), ww = pw + sign * (t % ks - pad);
+            if (hh >= 0 && hh < h && ww >= 0 && ww < w) v = to_f<T>(x[((img * h + hh) * (long long)w + ww) * c + ch]);
+        }
+        out[i] = from_f<T>(v);
+    }
+}
+
+// y[pix][ch] = bias[ch] + sum_t z[pix + tap_offset(t)][t*c + ch]   (adjoint of im2col with sign = +1); z rows have length ld
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ y, int n, int h,
+                                                     int w, int c, int ks, int ld) {
+    const int pad = (ks - 1) / 2, taps = ks * ks;
+    long long total = (long long)n * h * w * c;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % c);
+        long long pix = i / c;
+        int pw = (int)(pix % w);
+        long long r = pix / w;
+        int ph = (int)(r % h);
+        long long img = r / h;
+        float acc = bias ? bias[ch] : 0.f;
+        for (int t = 0; t < taps; ++t) {
+            int hh = ph + t / ks - pad, ww = pw + t % ks - pad;
+            if (hh >= 0 && hh < h && ww >= 0 && ww < w) acc += z[((img * h + hh) * (long long)w + ww) * ld + t * c + ch];
+        }
+        y[i] = acc;
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
     long long stride = (long long)gridDim.x * blockDim.x;
@@ -255,6 +302,20 @@ int gim_copy_cols(const void* src, int src_ld, int src_off, void* dst, int dst_l
     if (total <= 0) return GIM_OK;
     GIM_DISPATCH_DTYPE(dtype, (copy_cols_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)src, src_ld, src_off, (T*)dst, dst_ld, dst_off, rows, c)));
     return check_launch("copy_cols");
+}
+int gim_im2col(const void* x, void* out, int n, int h, int wd, int c, int ksize, int sign, int kc, int dtype, gim_stream_t s) {
+    long long total = (long long)n * h * wd * kc;
+    if (total <= 0) return GIM_OK;
+    GIM_REQUIRE(ksize >= 1 && (ksize & 1) && kc >= ksize * ksize * c && (sign == 1 || sign == -1), "im2col: bad arguments");
+    GIM_DISPATCH_DTYPE(dtype, (im2col_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)out, n, h, wd, c, ksize, sign, kc)));
+    return check_launch("im2col");
+}
+int gim_col2im(const float* z, const float* bias, float* y, int n, int h, int wd, int c, int ksize, int ld, gim_stream_t s) {
+    long long total = (long long)n * h * wd * c;
+    if (total <= 0) return GIM_OK;
+    GIM_REQUIRE(ksize >= 1 && (ksize & 1) && ld >= ksize * ksize * c, "col2im: bad arguments");
+    col2im_kernel<<<ew_grid(total, 256, 1), 256, 0, (cudaStream_t)s>>>(z, bias, y, n, h, wd, c, ksize, ld);
+    return check_launch("col2im");
 }
 int gim_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, gim_stream_t s) {
     if (n <= 0) return GIM_OK;

@@ -135,7 +135,8 @@ def _timed_call(kind, flops, name, *args):
     e0.record()
     C.call(name, *args)
     e1.record()
-    _profile.setdefault(kind, []).append((flops, e0, e1, tuple(args[4:10])))     # (n, h, w, ci, co, ks) for conv / wgrad calls
+    off = 3 if name == "gim_conv2d_wgrad" else 4
+    _profile.setdefault(kind, []).append((flops, e0, e1, tuple(args[off:off + 6])))     # (n, h, w, ci, co, ks)
 
 
 def _conv_kind(n, h, w, ci, co, ks, x, wgrad):
@@ -170,20 +171,34 @@ def _use_tc(x):
     return x.dtype == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT
 
 
+def _im2col(x, ks, sign, kc):
+    n, h, w, c = x.shape
+    out = torch.empty((n, h, w, kc), dtype=x.dtype, device=x.device)
+    C.call("gim_im2col", C.ptr(x), C.ptr(out), n, h, w, c, ks, sign, kc, C.dtype_code(x))
+    return out
+
+
 def _conv_raw(x, w_t, bias, ks):
-    """x [n,h,w,ci], w_t [taps,co,ci] (both operand dtype), bias fp32|None -> fp32 [n,h,w,co].  On the bf16 path skinny channel
-    counts (image / last layers: 1, 2, 3, 6) are zero-padded to 8 (inputs) / 16 (outputs) so every conv runs on tcgen05."""
+    """x [n,h,w,ci], w_t [taps,co,ci] (both operand dtype), bias fp32|None -> fp32 [n,h,w,co].
+    On the bf16 path layers with a skinny side (image / last layers: 1, 2, 3, 6 channels) are rewritten as dense 1x1 GEMMs so
+    that they, too, run on the tcgen05 kernel at full tile efficiency:
+      skinny input : unroll x over the taps (im2col of a few channels is cheap)  -> K = taps*ci
+      skinny output: z = x @ W^T with N = taps*co, then gather-sum the taps (col2im)."""
     n, h, w, ci = x.shape
-    co = w_t.shape[1]
-    if _use_tc(x) and (ci % 8 or co % 16):
-        cip, cop = _round_up(ci, 8), _round_up(co, 16)
-        wp = torch.zeros((w_t.shape[0], cop, cip), dtype=w_t.dtype, device=w_t.device)
-        wp[:, :co, :ci] = w_t
-        bp = None
-        if bias is not None:
-            bp = torch.zeros((cop,), dtype=torch.float32, device=x.device)
-            bp[:co] = bias
-        return _narrow_last(_conv_raw(_pad_last(x, cip), wp, bp, ks), co)
+    taps, co, _ = w_t.shape
+    if _use_tc(x) and ci % 8:
+        kc = _round_up(taps * ci, 8)
+        w2 = torch.zeros((1, co, kc), dtype=w_t.dtype, device=w_t.device)
+        w2[0, :, :taps * ci] = w_t.permute(1, 0, 2).reshape(co, taps * ci)
+        return _conv_raw(_im2col(x, ks, 1, kc), w2, bias, 1)
+    if _use_tc(x) and co % 16:
+        ld = _round_up(taps * co, 16)
+        w2 = torch.zeros((1, ld, ci), dtype=w_t.dtype, device=w_t.device)
+        w2[0, :taps * co] = w_t.reshape(taps * co, ci)
+        z = _conv_raw(x, w2, None, 1)
+        y = _empty((n, h, w, co), torch.float32, x)
+        C.call("gim_col2im", C.ptr(z), C.ptr(bias), C.ptr(y), n, h, w, co, ks, ld)
+        return y
     y = _empty((n, h, w, co), torch.float32, x)
     kind = _conv_kind(n, h, w, ci, co, ks, x, False) if _profile is not None else None
     _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_fwd", C.ptr(x), C.ptr(w_t), C.ptr(bias), C.ptr(y), n, h, w, ci, co, ks,
@@ -194,10 +209,16 @@ def _conv_raw(x, w_t, bias, ks):
 def _wgrad_raw(x, g, ks):
     n, h, w, ci = x.shape
     co = g.shape[3]
-    if _use_tc(x) and (ci % 8 or co % 8):
-        gwp = _wgrad_raw(_pad_last(x, _round_up(ci, 8)), _pad_last(g, _round_up(co, 8)), ks)
-        return gwp[:, :co, :ci].contiguous()
-    gw = _empty((ks * ks, co, ci), torch.float32, x)
+    taps = ks * ks
+    if _use_tc(x) and ci % 8:                       # gw[t][co][c] = sum_p g[p][co] * xcol[p][t*ci+c]
+        kc = _round_up(taps * ci, 8)
+        gw2 = _wgrad_raw(_im2col(x, ks, 1, kc), g, 1)
+        return gw2[0, :, :taps * ci].reshape(co, taps, ci).permute(1, 0, 2).contiguous()
+    if _use_tc(x) and co % 8:                       # gw[t][c][ci] = sum_q gcol[q][t*co+c] * x[q][ci],  gcol[q][t,c] = g[q - t][c]
+        ld = _round_up(taps * co, 8)
+        gw2 = _wgrad_raw(x, _im2col(g, ks, -1, ld), 1)
+        return gw2[0, :taps * co].reshape(taps, co, ci).contiguous()
+    gw = _empty((taps, co, ci), torch.float32, x)
     kind = _conv_kind(n, h, w, ci, co, ks, x, True) if _profile is not None else None
     _timed_call(kind, 2.0 * n * h * w * ci * co * ks * ks, "gim_conv2d_wgrad", C.ptr(x), C.ptr(g), C.ptr(gw), n, h, w, ci, co, ks,
                 C.dtype_code(x), _state["conv_algo"])
