@@ -85,6 +85,66 @@ __global__ void __launch_bounds__(256) dot_kernel(const T* __restrict__ x, const
 }
 
 // y[n,ho,wo,c] = scale * sum_{dy,dx in 2x2} (a + b)[n,2ho+dy,2wo+dx,c]
+// vector variants: one thread handles 16 bytes of adjacent channels (c % V == 0, 16-byte aligned bases)
+template <typename T>
+__global__ void __launch_bounds__(256) pool2_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
+                                                        int n, int h, int w, int c, float scale) {
+    constexpr int V = Vec16<T>::N;
+    int ho = h / 2, wo = w / 2, cv = c / V;
+    long long total = (long long)n * ho * wo * cv;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % cv) * V;
+        long long p = i / cv;
+        int x = (int)(p % wo); p /= wo;
+        int yy = (int)(p % ho);
+        long long img = p / ho;
+        long long base = ((img * h + 2 * yy) * w + 2 * x) * (long long)c + ch;
+        long long rs = (long long)w * c;
+        float acc[V], t[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        const long long offs[4] = {0, (long long)c, rs, rs + c};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ld16<T>(a + base + offs[q], t);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] += t[j];
+            if (b) {
+                ld16<T>(b + base + offs[q], t);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc[j] += t[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] *= scale;
+        st16<T>(y + (((img * ho + yy) * wo + x) * (long long)c + ch), acc);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) unpool2_vec_kernel(const T* __restrict__ gy, T* __restrict__ gx, int n, int h, int w, int c, float scale) {
+    constexpr int V = Vec16<T>::N;
+    int ho = h / 2, wo = w / 2, cv = c / V;
+    long long total = (long long)n * h * w * cv;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % cv) * V;
+        long long p = i / cv;
+        int x = (int)(p % w); p /= w;
+        int yy = (int)(p % h);
+        long long img = p / h;
+        float v[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = 0.f;
+        if ((yy >> 1) < ho && (x >> 1) < wo) {
+            ld16<T>(gy + ((img * ho + (yy >> 1)) * wo + (x >> 1)) * (long long)c + ch, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] *= scale;
+        }
+        st16<T>(gx + ((img * h + yy) * (long long)w + x) * c + ch, v);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
                                                     int n, int h, int w, int c, float scale) {
@@ -219,9 +279,18 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ z
 }
 
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n, bool vec) {
+    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = from_f<TO>(to_f<TI>(x[i]));
+    long long nv = vec ? n / 8 : 0;                     // 8 elements per thread: 32 B (fp32) / 16 B (bf16) accesses
+    for (long long i = tid; i < nv; i += stride) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 16 / (int)sizeof(TI)) ld16<TI>(x + i * 8 + j, *reinterpret_cast<float(*)[16 / sizeof(TI)]>(&f[j]));
+#pragma unroll
+        for (int j = 0; j < 8; j += 16 / (int)sizeof(TO)) st16<TO>(y + i * 8 + j, *reinterpret_cast<float(*)[16 / sizeof(TO)]>(&f[j]));
+    }
+    for (long long i = nv * 8 + tid; i < n; i += stride) y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
 
 }  // namespace gim
@@ -272,13 +341,25 @@ int gim_dot(const void* x, const void* y, float* out, long long n, int dtype, gi
 int gim_pool2_sum(const void* a, const void* b, void* y, int n, int h, int wd, int c, float scale, int dtype, gim_stream_t s) {
     long long total = (long long)n * (h / 2) * (wd / 2) * c;
     if (total <= 0) return GIM_OK;
-    GIM_DISPATCH_DTYPE(dtype, (pool2_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (T*)y, n, h, wd, c, scale)));
+    bool vec = aligned16(a) && aligned16(y) && (!b || aligned16(b));
+    if (dtype == GIM_F32 && vec && c % 4 == 0)
+        pool2_vec_kernel<float><<<ew_grid(total / 4, 256, 1), 256, 0, (cudaStream_t)s>>>((const float*)a, (const float*)b, (float*)y, n, h, wd, c, scale);
+    else if (dtype == GIM_BF16 && vec && c % 8 == 0)
+        pool2_vec_kernel<bf16><<<ew_grid(total / 8, 256, 1), 256, 0, (cudaStream_t)s>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n, h, wd, c, scale);
+    else
+        GIM_DISPATCH_DTYPE(dtype, (pool2_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (T*)y, n, h, wd, c, scale)));
     return check_launch("pool2_sum");
 }
 int gim_unpool2_bcast(const void* gy, void* gx, int n, int h, int wd, int c, float scale, int dtype, gim_stream_t s) {
     long long total = (long long)n * h * wd * c;
     if (total <= 0) return GIM_OK;
-    GIM_DISPATCH_DTYPE(dtype, (unpool2_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)gy, (T*)gx, n, h, wd, c, scale)));
+    bool vec = aligned16(gy) && aligned16(gx);
+    if (dtype == GIM_F32 && vec && c % 4 == 0)
+        unpool2_vec_kernel<float><<<ew_grid(total / 4, 256, 1), 256, 0, (cudaStream_t)s>>>((const float*)gy, (float*)gx, n, h, wd, c, scale);
+    else if (dtype == GIM_BF16 && vec && c % 8 == 0)
+        unpool2_vec_kernel<bf16><<<ew_grid(total / 8, 256, 1), 256, 0, (cudaStream_t)s>>>((const bf16*)gy, (bf16*)gx, n, h, wd, c, scale);
+    else
+        GIM_DISPATCH_DTYPE(dtype, (unpool2_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)gy, (T*)gx, n, h, wd, c, scale)));
     return check_launch("unpool2_bcast");
 }
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t s) {
@@ -319,12 +400,13 @@ int gim_col2im(const float* z, const float* bias, float* y, int n, int h, int wd
 }
 int gim_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, gim_stream_t s) {
     if (n <= 0) return GIM_OK;
-    int grid = ew_grid(n, 256);
+    int grid = ew_grid(n, 256, 16);
     cudaStream_t st = (cudaStream_t)s;
-    if (dtype_in == GIM_F32 && dtype_out == GIM_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, n);
-    else if (dtype_in == GIM_BF16 && dtype_out == GIM_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)y, n);
-    else if (dtype_in == GIM_F32 && dtype_out == GIM_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
-    else if (dtype_in == GIM_BF16 && dtype_out == GIM_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, n);
+    bool vec = aligned16(x) && aligned16(y);
+    if (dtype_in == GIM_F32 && dtype_out == GIM_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, n, vec);
+    else if (dtype_in == GIM_BF16 && dtype_out == GIM_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)y, n, vec);
+    else if (dtype_in == GIM_F32 && dtype_out == GIM_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n, vec);
+    else if (dtype_in == GIM_BF16 && dtype_out == GIM_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, n, vec);
     else return fail(GIM_E_ARG, "cast: bad dtype");
     return check_launch("cast");
 }

@@ -6,12 +6,23 @@
 namespace gim {
 
 // t[j] = sum_co W[co][j] * u[co]
-__global__ void __launch_bounds__(256) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, float* __restrict__ t, int cout, int J) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
+// grid (ceil(J/32), row_splits), block (32, 8): each CTA reduces a slab of rows for 32 columns; slabs combine with atomicAdd (t zeroed first)
+__global__ void __launch_bounds__(256) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, float* __restrict__ t, int cout, int J,
+                                                     int rows_per_split) {
+    __shared__ float sh[8][33];
+    int j = blockIdx.x * 32 + threadIdx.x;
+    int r0 = blockIdx.y * rows_per_split, r1 = min(cout, r0 + rows_per_split);
     float acc = 0.f;
-    for (int co = 0; co < cout; ++co) acc = fmaf(W[(long long)co * J + j], u[co], acc);
-    t[j] = acc;
+    if (j < J)
+        for (int co = r0 + threadIdx.y; co < r1; co += 8) acc = fmaf(W[(long long)co * J + j], u[co], acc);
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < J) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a += sh[q][threadIdx.x];
+        atomicAdd(&t[j], a);
+    }
 }
 
 // single CTA: v = t / max(||t||, eps) (power_iter) ; v_used = v
@@ -129,7 +140,13 @@ int gim_sn_forward(const float* weight_orig, float* u, float* v, int power_iter,
     float* sv = scratch + J;
     int rc;
     if (power_iter) {
-        sn_wtu_kernel<<<(J + 255) / 256, 256, 0, st>>>(weight_orig, u, t, cout, J);
+        if (cudaMemsetAsync(t, 0, sizeof(float) * (size_t)J, st) != cudaSuccess) return fail(GIM_E_CUDA, "sn_forward memset");
+        int col_blocks = (J + 31) / 32;
+        int splits = (2 * num_sms() + col_blocks - 1) / col_blocks;          // enough CTAs to cover the chip ~2x
+        if (splits > (cout + 31) / 32) splits = (cout + 31) / 32;
+        if (splits < 1) splits = 1;
+        int rows_per_split = (cout + splits - 1) / splits;
+        sn_wtu_kernel<<<dim3(col_blocks, (cout + rows_per_split - 1) / rows_per_split), dim3(32, 8), 0, st>>>(weight_orig, u, t, cout, J, rows_per_split);
         if ((rc = check_launch("sn_wtu")) != GIM_OK) return rc;
     }
     sn_vnorm_kernel<<<1, 1024, 0, st>>>(t, v, v_used, J, eps, power_iter);
