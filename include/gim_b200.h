@@ -89,6 +89,12 @@ int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int d
 int gim_copy_cols(const void* src, int src_ld, int src_off, void* dst, int dst_ld, int dst_off,
                   long long rows, int c, int dtype, gim_stream_t stream);
 int gim_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, gim_stream_t stream);
+/* conv-operand producer: out (dtype_out, NHWC) = f(x): mode 0 identity (cast), 1 LeakyReLU(slope), 2 nearest-upsample x2
+ * (out is [n,2h,2w,c]) -- fuses the activation / nn.Upsample in front of a conv (model_blocks.py:505-509, 761-766) with the
+ * single rounding to the operand dtype */
+int gim_operand_prepare(const void* x, int dtype_in, void* out, int dtype_out, int n, int h, int wd, int c, int mode, float slope, gim_stream_t stream);
+/* gx = g * (ref > 0 ? 1 : slope), mask from `ref` of dtype ref_dtype (the saved operand) */
+int gim_lrelu_bwd_ref(const float* g, const void* ref, int ref_dtype, float* gx, long long n, float slope, gim_stream_t stream);
 /* tap unrolling of skinny-channel tensors (c in {1,2,3,6}) so their convs become dense 1x1 tensor-core GEMMs:
  * out[pix][t*c+ch] = x[pix + sign*offset(t)][ch] (zeros outside / for j >= k*k*c), rows of length kc */
 int gim_im2col(const void* x, void* out, int n, int h, int wd, int c, int ksize, int sign, int kc, int dtype, gim_stream_t stream);

@@ -39,6 +39,8 @@ PROTOTYPES = {
     "gim_nhwc_to_nchw": "ppiiiiip",
     "gim_copy_cols": "piipiiliip",
     "gim_cast": "pipilp",
+    "gim_operand_prepare": "pipiiiiiifp",
+    "gim_lrelu_bwd_ref": "ppiplfp",
     "gim_im2col": "ppiiiiiiiip",
     "gim_col2im": "pppiiiiiip",
     "gim_norm_stats": "pppiiiip",

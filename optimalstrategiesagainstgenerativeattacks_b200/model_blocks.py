@@ -102,8 +102,9 @@ class SNConv2d(nn.Module):
         """Packed fp32 [k*k, cout, cin] weight W/sigma; runs the power iteration when self.training."""
         return ops.SpectralNormFn.apply(self.weight_orig, (self.weight_u, self.weight_v), self.training, SN_EPS)
 
-    def forward(self, x):
-        return ops.Conv2dFn.apply(x, self.effective_weight(), self.bias, self.kernel_size)
+    def forward(self, x, pre=ops.PRE_NONE, slope=0.2):
+        """`pre`: operator folded in front of the conv (ops.PRE_LRELU: LeakyReLU(slope); ops.PRE_UPSAMPLE: nearest x2)."""
+        return ops.Conv2dFn.apply(x, self.effective_weight(), self.bias, self.kernel_size, pre, slope)
 
 
 class InstanceNormAffine(nn.Module):
@@ -132,10 +133,8 @@ class ResBlockDown(nn.Module):
 
     def forward(self, x):
         out_res = self.conv_l1(x)
-        out = ops.lrelu(x)
-        out = self.conv_r1(out)
-        out = ops.lrelu(out)
-        out = self.conv_r2(out)
+        out = self.conv_r1(x, ops.PRE_LRELU)          # conv(lrelu(x)): the activation is fused into the operand producer
+        out = self.conv_r2(out, ops.PRE_LRELU)
         return ops.avg_pool2_add(out_res, out)
 
 
@@ -172,8 +171,8 @@ class ImgAttConvBlock(nn.Module):
         self.conv_r2 = SNConv2d(out_channels, out_channels, 3, padding=1)
 
     def forward(self, x):
-        out = self.conv_r1(ops.lrelu(x))
-        out = self.conv_r2(ops.lrelu(out))
+        out = self.conv_r1(x, ops.PRE_LRELU)
+        out = self.conv_r2(out, ops.PRE_LRELU)
         return ops.AddFn.apply(self.conv_l1(x), out)
 
 
@@ -213,8 +212,7 @@ class ResBlockUp(nn.Module):
     def forward(self, x):
         out_res = ops.upsample2(self.conv_l1(x))
         out = self.in1(x, 0.2)
-        out = ops.upsample2(out)
-        out = self.conv_r1(out)
+        out = self.conv_r1(out, ops.PRE_UPSAMPLE)     # conv(upsample(.)): the 4x larger tensor only exists as the bf16 operand
         out = self.in2(out, 0.2)
         out = self.conv_r2(out)
         return ops.AddFn.apply(out, out_res)
@@ -273,8 +271,7 @@ class AdaResBlockUp2(nn.Module):
         std_st2 = self.lin2_std(style)
         out_res = ops.upsample2(self.conv_l1(x))
         out = ops.ada_in(x, mean_st1, std_st1, 1e-5, 0.2)
-        out = ops.upsample2(out)
-        out = self.conv_r1(out)
+        out = self.conv_r1(out, ops.PRE_UPSAMPLE)
         out = ops.ada_in(out, mean_st2, std_st2, 1e-5, 0.2)
         out = self.conv_r2(out)
         return ops.AddFn.apply(out, out_res)

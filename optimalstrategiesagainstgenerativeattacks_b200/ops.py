@@ -225,31 +225,56 @@ def _wgrad_raw(x, g, ks):
     return gw
 
 
+PRE_NONE, PRE_LRELU, PRE_UPSAMPLE = 0, 1, 2
+
+
+def _prepare_operand(x, pre, slope):
+    """Operand of the active precision = prologue(x): identity / LeakyReLU / nearest-upsample x2, fused with the rounding."""
+    if pre == PRE_NONE:
+        return _operand(x)
+    n, h, w, c = x.shape
+    shape = (n, 2 * h, 2 * w, c) if pre == PRE_UPSAMPLE else (n, h, w, c)
+    out = torch.empty(shape, dtype=_state["operand_dtype"], device=x.device)
+    C.call("gim_operand_prepare", C.ptr(x), C.dtype_code(x), C.ptr(out), C.dtype_code(out), n, h, w, c, pre, slope)
+    return out
+
+
 class Conv2dFn(Function):
-    """y[n,h,w,co] = b[co] + sum x[n,h+r-p,w+s-p,ci] w[t,co,ci] -- nn.Conv2d(stride 1, 'same') of model_blocks.py:492-495."""
+    """y = conv(prologue(x), w) + b.  nn.Conv2d(stride 1, 'same') of model_blocks.py:492-495, optionally with the LeakyReLU
+    (model_blocks.py:505-509) or the nearest nn.Upsample(x2) (:761-766, 851-858) that precedes it folded into the operand producer."""
 
     @staticmethod
-    def forward(ctx, x, w32, bias, ks):
+    def forward(ctx, x, w32, bias, ks, pre=PRE_NONE, slope=LRELU_SLOPE):
         x = _c(x)
         w32 = _c(w32)
-        ctx.ks = ks
-        ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, w32)
-        return _conv_raw(_operand(x), _weight_as(w32, operand_dtype(), False), bias, ks)
+        xop = _prepare_operand(x, pre, slope)
+        ctx.cfg = (ks, pre, slope, bias is not None)
+        # with a prologue the (half-size) operand is what backward needs: weight-grad input and the LeakyReLU sign mask
+        ctx.save_for_backward(x if pre == PRE_NONE else xop, w32)
+        return _conv_raw(xop, _weight_as(w32, operand_dtype(), False), bias, ks)
 
     @staticmethod
     def backward(ctx, gy):
-        x, w32 = ctx.saved_tensors
+        xs, w32 = ctx.saved_tensors
+        ks, pre, slope, has_bias = ctx.cfg
         gy = _c(gy)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = ConvTransposeFn.apply(gy, w32, ctx.ks)
+            gx = ConvTransposeFn.apply(gy, w32, ks)
+            if pre == PRE_LRELU:
+                gx = LReluBwdFn.apply(gx, xs, slope)
+            elif pre == PRE_UPSAMPLE:
+                gx = Pool2Fn.apply(gx, None, 1.0)
         if not _state["input_grads_only"]:
             if ctx.needs_input_grad[1]:
-                gw = WgradFn.apply(x, gy, ctx.ks)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gw = WgradFn.apply(xs, gy, ks)
+            if has_bias and ctx.needs_input_grad[2]:
                 gb = ColSumFn.apply(gy)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None, None
+
+
+def conv2d(x, w32, bias, ks, pre=PRE_NONE, slope=LRELU_SLOPE):
+    return Conv2dFn.apply(x, w32, bias, ks, pre, slope)
 
 
 class ConvTransposeFn(Function):
@@ -269,7 +294,7 @@ class ConvTransposeFn(Function):
         gout = _c(gout)
         gg = gw = None
         if ctx.needs_input_grad[0]:
-            gg = Conv2dFn.apply(gout, w32, None, ctx.ks)
+            gg = conv2d(gout, w32, None, ctx.ks)
         if ctx.needs_input_grad[1]:
             gw = WgradFn.apply(gout, g, ctx.ks)
         return gg, gw, None
@@ -295,7 +320,7 @@ class WgradFn(Function):
         if ctx.needs_input_grad[0]:
             gx = ConvTransposeFn.apply(g, gout, ctx.ks)
         if ctx.needs_input_grad[1]:
-            gg = Conv2dFn.apply(x, gout, None, ctx.ks)
+            gg = conv2d(x, gout, None, ctx.ks)
         return gx, gg, None
 
 
@@ -384,13 +409,16 @@ class LReluFn(Function):
 
 
 class LReluBwdFn(Function):
-    """gx = g * (ref > 0 ? 1 : slope); piecewise linear => zero second derivative w.r.t. ref."""
+    """gx = g * (ref > 0 ? 1 : slope); piecewise linear => zero second derivative w.r.t. ref (ref may be the saved bf16 operand)."""
 
     @staticmethod
     def forward(ctx, g, ref, slope):
         g = _c(g)
         gx = torch.empty_like(g)
-        C.call("gim_lrelu_bwd", C.ptr(g), C.ptr(ref), C.ptr(gx), g.numel(), slope, C.dtype_code(g))
+        if g.dtype == torch.float32 and ref.dtype != g.dtype:
+            C.call("gim_lrelu_bwd_ref", C.ptr(g), C.ptr(ref), C.dtype_code(ref), C.ptr(gx), g.numel(), slope)
+        else:
+            C.call("gim_lrelu_bwd", C.ptr(g), C.ptr(ref), C.ptr(gx), g.numel(), slope, C.dtype_code(g))
         ctx.slope = slope
         ctx.save_for_backward(ref)
         return gx
@@ -735,7 +763,7 @@ def linear(x, weight, bias, slope=1.0):
     rows, k = x2.shape
     n = weight.shape[0]
     if _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and k % 8 == 0 and n % 16 == 0 and rows >= 16:
-        y = Conv2dFn.apply(x2.reshape(rows, 1, 1, k), weight.reshape(1, n, k), bias, 1).reshape(rows, n)
+        y = conv2d(x2.reshape(rows, 1, 1, k), weight.reshape(1, n, k), bias, 1).reshape(rows, n)
         if slope != 1.0:
             y = LReluFn.apply(y, slope)
     else:

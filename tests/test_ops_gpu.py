@@ -82,7 +82,7 @@ def test_conv_fwd_bwd_double_bwd(shape, prec, tol):
     wp = pack_w(w64.detach())
     b = b64.detach().to("cuda", torch.float32).requires_grad_()
     pr = probe.permute(0, 2, 3, 1).contiguous().to("cuda", dt)
-    y = ops.Conv2dFn.apply(x, wp, b, k)
+    y = ops.conv2d(x, wp, b, k)
     assert rel_err(nchw(y), y64) < tol
     s = ops.DotFn.apply(y, pr)
     (gx,) = torch.autograd.grad(s.sum(), x, create_graph=True)
@@ -337,10 +337,37 @@ def test_conv_tcgen05_matches_cuda_core(shape):
     for algo in ("simt", "tcgen05"):
         ops.set_conv_algo(algo)
         with torch.no_grad():
-            outs[algo] = ops.Conv2dFn.apply(x, wp, b, k).float()
+            outs[algo] = ops.conv2d(x, wp, b, k).float()
             wg[algo] = ops.WgradFn.apply(x, gy, k)
         torch.cuda.synchronize()
     assert rel_err(outs["tcgen05"], outs["simt"]) < 4e-3
     assert float((outs["tcgen05"] - outs["simt"]).abs().max()) < 0.05 * float(outs["simt"].abs().max())
     assert C.wgrad_tc_supported(n, h, w, ci, co, k, C.BF16)
     assert rel_err(wg["tcgen05"], wg["simt"]) < 1e-4          # same bf16 operands, fp32 accumulation in both
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_conv_with_fused_prologue(prec, tol):
+    """conv(lrelu(x)) and conv(upsample2(x)) with the prologue folded into the operand producer, first and second order."""
+    ops = ops_mod()
+    ops.set_precision(prec)
+    n, ci, co, k, h, w = 3, 64, 32, 3, 6, 10
+    x64 = rnd(n, ci, h, w, seed=1).requires_grad_()
+    w64 = (rnd(co, ci, k, k, seed=2) / np.sqrt(ci * k * k)).requires_grad_()
+    b64 = rnd(co, seed=3, scale=0.1).requires_grad_()
+    for pre, fn in ((ops.PRE_LRELU, lambda t: F.leaky_relu(t, 0.2)), (ops.PRE_UPSAMPLE, lambda t: F.interpolate(t, scale_factor=2, mode="nearest"))):
+        y64 = F.conv2d(fn(x64), w64, b64, padding=1)
+        probe = rnd(*y64.shape, seed=4)
+        (gx64,) = torch.autograd.grad((y64 * probe).sum(), x64, create_graph=True)
+        gX, gW, gB = torch.autograd.grad((y64 * probe).sum() + 0.5 * gx64.pow(2).sum(), (x64, w64, b64))
+        x = to_dev_nhwc(x64.detach(), torch.float32)
+        wp = pack_w(w64.detach())
+        b = b64.detach().to("cuda", torch.float32).requires_grad_()
+        pr = probe.permute(0, 2, 3, 1).contiguous().to("cuda", torch.float32)
+        y = ops.conv2d(x, wp, b, k, pre, 0.2)
+        assert rel_err(nchw(y), y64) < tol
+        s = ops.DotFn.apply(y, pr)
+        (gx,) = torch.autograd.grad(s.sum(), x, create_graph=True)
+        assert rel_err(nchw(gx), gx64) < tol
+        dX, dW, dB = torch.autograd.grad(s.sum() + 0.5 * ops.RowsSqSumFn.apply(gx.reshape(1, -1)).sum(), (x, wp, b))
+        assert rel_err(nchw(dX), gX) < tol and rel_err(unpack_w(dW, k), gW) < tol and rel_err(dB, gB) < tol
