@@ -292,8 +292,7 @@ def run_ours(args):
                   file=sys.stderr)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dev)
         return
     peaks = {}
     try:
@@ -325,13 +324,27 @@ def run_ours(args):
                      "other_conv_kernels_ms_per_step": {k: v["ms"] for k, v in prof.items() if k != "tcgen05"},
                      "all_conv_ms_per_step": total_conv_ms},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         torch.cuda.empty_cache()
         cb, _ = time_cpu(args.workload, args.cpu_batch, 2, 1)
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, dev)
+
+
+def _finish(world, dev):
+    """Leave a multi-rank run without tearing NCCL down: destroying a communicator that CUDA graphs still reference can block
+    forever, and nothing after the JSON line needs it.  Ranks meet at a last barrier, flush, and exit."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

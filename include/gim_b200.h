@@ -46,6 +46,15 @@ long long   gim_launch_count(int reset);
  * either way: bf16 operands with an fp32 result is the mixed-precision tensor-core path); bias fp32 or NULL */
 int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y,
                    int n, int h, int wd, int cin, int cout, int ksize, int dtype, int out_dtype, int algo, gim_stream_t stream);
+/* The tcgen05 convolution with a fused epilogue (bf16 operands only; the LeakyReLU of model_blocks.py:505-509 and its backward
+ * folded into the producing kernel):  v = conv(x, w) + bias;
+ *   epilogue & GIM_EPI_LRELU : v = LeakyReLU_slope(v)
+ *   epilogue & GIM_EPI_MASK  : v = v * (mask_ref[n,h,w,co] > 0 ? 1 : slope)   (mask_ref: bf16, same shape as y; cout % 32 == 0)
+ * y: out_dtype (fp32 or bf16). */
+#define GIM_EPI_LRELU 1
+#define GIM_EPI_MASK  2
+int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* y, const void* mask_ref,
+                         int n, int h, int wd, int cin, int cout, int ksize, int out_dtype, int epilogue, float slope, gim_stream_t stream);
 /* gw[t][co][ci] (fp32) = sum_{n,h,w} gy[n,h,w,co] * x[n,h+r-p,w+s-p,ci]  (overwrites gw) */
 int gim_conv2d_wgrad(const void* x, const void* gy, float* gw,
                      int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t stream);

@@ -12,6 +12,7 @@
 //
 //   weight-gradient:  dW[tap][co][ci] = sum_pix dY[pix][co] * X[pix + tap][ci]   (see the second half of this file)
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gim {
@@ -130,6 +131,9 @@ struct ConvTcParams {
     int out_f32;                                 // 1: y is fp32, 0: bf16
     int tma_store;                               // 1: epilogue stages the tile in smem (128B-swizzled) and writes it with TMA
     int block_k;                                 // K elements per stage: 64 (128-byte rows, SWIZZLE_128B) or 16 (32-byte rows, SWIZZLE_32B)
+    int epi;                                     // fused epilogue bits (persistent kernel): kEpiLrelu, kEpiMask
+    int m_sub;                                   // pixel tiles per macro tile (persistent kernel): 1 or 2
+    float slope;
 };
 
 template <int kDummy>
@@ -310,6 +314,245 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// persistent forward / input-gradient kernel (v2)
+//   One CTA per SM walks the output tiles (static round-robin).  The accumulator is double-buffered in tensor memory
+//   (2 x block_n columns), so the epilogue of tile i (TMEM -> registers -> swizzled smem -> TMA store, in 16 KB chunks through two
+//   rotating staging buffers) runs while the MMA warp already accumulates tile i+1; the TMA/MMA smem ring never drains between
+//   tiles.  Fused epilogues: + bias, LeakyReLU, LeakyReLU-backward mask taken from a saved bf16 operand, fp32 or bf16 output.
+// ----------------------------------------------------------------------------------------------------------------
+enum { kEpiLrelu = 1, kEpiMask = 2 };
+constexpr int kStagingBytes = 2 * kBlockM * 128;          // two 16 KB boxes (128 rows x 128 B)
+
+// A macro tile = m_sub (1 or 2) consecutive 128-pixel tiles x one block_n-wide channel tile.  With m_sub = 2 the two pixel tiles
+// share every weight box and their MMAs alternate between two independent accumulators (measured: a single dependent
+// accumulation chain of N=128 MMAs tops out near 1.0 PFLOP/s, two interleaved chains or N=256 reach 1.3).
+template <int kDummy>
+__global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                                                              const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias,
+                                                              const bf16* __restrict__ mask_ref, void* __restrict__ y, const ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = kBlockM * p.block_k * 2;
+    const int b_off = p.m_sub * a_bytes;
+    const int stage_bytes = (b_off + p.block_n * p.block_k * 2 + 1023) & ~1023;
+    uint8_t* staging = smem + p.stages * stage_bytes;
+    float* bias_sm = (float*)(staging + kStagingBytes);                       // 256 floats
+    uint64_t* full_bar = (uint64_t*)(bias_sm + 256);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tmem_full_bar = empty_bar + p.stages;                            // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;                              // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pad = (p.ks - 1) / 2;
+    const int kc_per_tap = (p.cin + p.block_k - 1) / p.block_k;
+    const int num_kb = p.ks * p.ks * kc_per_tap;
+    const int n_tiles = (p.cout + p.block_n - 1) / p.block_n;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int total_tiles = ((m_tiles + p.m_sub - 1) / p.m_sub) * n_tiles;
+    const uint32_t buf_cols = (uint32_t)(p.m_sub * p.block_n);
+    const uint32_t tmem_cols = 2u * buf_cols < 32u ? 32u : 2u * buf_cols;    // power of two by construction
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_y);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // two producers: A (warp 0), B (warp 6)
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 || warp == 6) {
+        // two TMA producers share the ring: warp 0 streams the activation boxes (A), warp 6 the weight boxes (B); each arms the
+        // full barrier with its own byte count
+        if (lane == 0) {
+            const bool is_a = warp == 0;
+            int s = 0;
+            uint32_t ph = 1;                                  // parity to wait for on empty[s]: the first pass over the ring is free
+            const uint32_t tx_bytes = is_a ? (uint32_t)b_off : (uint32_t)(p.block_n * p.block_k * 2);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles;
+                const int n0 = (tile - mt * n_tiles) * p.block_n;
+                int w0[2], h0[2], img0[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    int t = mt * p.m_sub + j;
+                    const int tw = t % p.tiles_w; t /= p.tiles_w;
+                    const int th = t % p.tiles_h; t /= p.tiles_h;
+                    w0[j] = tw * p.bw - pad; h0[j] = th * p.bh - pad; img0[j] = t * p.bn;      // beyond the last tile: img0 >= n, TMA zero-fills
+                }
+                int tap_row = n0, kc = 0, r = 0, q = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph);
+                    uint8_t* sa = smem + s * stage_bytes;
+                    mbar_expect_tx(&full_bar[s], tx_bytes);
+                    if (is_a) {
+                        tma_load_4d(sa, &map_x, &full_bar[s], kc, w0[0] + q, h0[0] + r, img0[0]);
+                        if (p.m_sub == 2) tma_load_4d(sa + a_bytes, &map_x, &full_bar[s], kc, w0[1] + q, h0[1] + r, img0[1]);
+                    } else {
+                        tma_load_2d(sa + b_off, &map_w, &full_bar[s], kc, tap_row);
+                    }
+                    kc += p.block_k;
+                    if (kc >= p.cin) { kc = 0; tap_row += p.cout; if (++q == p.ks) { q = 0; ++r; } }
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 0, 0);
+            // descriptors differ between stages only in the 14-bit start-address field: build them once
+            const bool k64 = p.block_k == 64;
+            const uint32_t s0 = smem_u32(smem);
+            const uint64_t desc_a0 = k64 ? make_desc_sw128(s0, 16, 1024) : make_desc(s0, 16, 256, 6);
+            const uint64_t desc_b0 = k64 ? make_desc_sw128(s0 + b_off, 16, 1024) : make_desc(s0 + b_off, 16, 256, 6);
+            const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), a_step = (uint64_t)(a_bytes >> 4);
+            const bool two = p.m_sub == 2;
+            int s = 0;
+            uint32_t ph = 0, i = 0;
+            uint64_t da = desc_a0, db = desc_b0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+                const uint32_t buf = i & 1;
+                mbar_wait(&tmem_empty_bar[buf], ((i >> 1) & 1) ^ 1);          // epilogue has drained this accumulator pair
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * buf_cols;
+                const uint32_t tmem_d1 = tmem_d + (uint32_t)p.block_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t acc = kb != 0 ? 1u : 0u;
+                    if (k64) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {                          // +32 B along K inside the 128-byte swizzle row
+                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                            if (two) umma_bf16(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                        }
+                    } else {
+                        umma_bf16(tmem_d, da, db, idesc, acc);
+                        if (two) umma_bf16(tmem_d1, da + a_step, db, idesc, acc);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    da += stage_step; db += stage_step;
+                    if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
+                }
+                umma_commit(&tmem_full_bar[buf]);
+            }
+        }
+    } else {
+        // ---- epilogue warps (128 threads): TMEM -> registers -> fused pointwise -> swizzled smem -> TMA store ----
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const int et = threadIdx.x - 64;                 // 0..127
+        const int lw = m % p.bw, lh = (m / p.bw) % p.bh, ln = m / (p.bw * p.bh);
+        const bool store_thread = (et == 0);
+        const int cols_per_chunk = p.out_f32 ? 32 : 64;
+        uint32_t i = 0, chunk = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+            const int mt = tile / n_tiles;
+            const int n0 = (tile - mt * n_tiles) * p.block_n;
+            const uint32_t buf = i & 1;
+            // bias tile -> smem (all readers of the previous tile's values are past their last chunk barrier)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int c = et; c < p.block_n; c += 128) bias_sm[c] = (bias && n0 + c < p.cout) ? __ldg(&bias[n0 + c]) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tmem_full_bar[buf], (i >> 1) & 1);
+            tc_fence_after();
+            for (int sub = 0; sub < p.m_sub; ++sub) {
+                int t = mt * p.m_sub + sub;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh, img0 = t * p.bn;
+                const int ww = w0 + lw, hh = h0 + lh, img = img0 + ln;
+                const bool valid = ww < p.w && hh < p.h && img < p.n;
+                const long long pix = ((long long)img * p.h + hh) * p.w + ww;
+                const uint32_t tmem_acc = tmem_base + buf * buf_cols + (uint32_t)(sub * p.block_n) + ((uint32_t)(quarter * 32) << 16);
+                const bool last_sub = sub == p.m_sub - 1;
+                for (int c0 = 0; c0 < p.block_n; c0 += cols_per_chunk, ++chunk) {
+                    uint8_t* box = staging + (chunk & 1) * (kBlockM * 128) + m * 128;
+#pragma unroll 1
+                    for (int h32 = 0; h32 < cols_per_chunk; h32 += 32) {
+                        const int cb = c0 + h32;
+                        float f[32];
+                        {
+                            uint32_t lo[16], hi[16];
+                            tmem_ld16(tmem_acc + (uint32_t)cb, lo);
+                            tmem_ld16(tmem_acc + (uint32_t)(cb + 16), hi);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) { f[j] = __uint_as_float(lo[j]); f[16 + j] = __uint_as_float(hi[j]); }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += bias_sm[cb + j];
+                        if (p.epi & kEpiLrelu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = lrelu_f(f[j], p.slope);
+                        }
+                        if (p.epi & kEpiMask) {
+                            if (valid && n0 + cb < p.cout) {         // cout % 32 == 0 is required for the mask epilogue
+                                const uint4* mr = reinterpret_cast<const uint4*>(mask_ref + pix * p.cout + n0 + cb);
+#pragma unroll
+                                for (int v4 = 0; v4 < 4; ++v4) {
+                                    const uint4 raw = __ldg(mr + v4);
+                                    const bf16* e = reinterpret_cast<const bf16*>(&raw);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        if (!(__bfloat162float(e[j]) > 0.f)) f[8 * v4 + j] *= p.slope;
+                                }
+                            }
+                        }
+                        if (p.out_f32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(box + ((j ^ (m & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+                            const int jb = h32 / 8;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 o;
+                                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+                                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                                o.x = *reinterpret_cast<uint32_t*>(&b0);
+                                o.y = *reinterpret_cast<uint32_t*>(&b1);
+                                o.z = *reinterpret_cast<uint32_t*>(&b2);
+                                o.w = *reinterpret_cast<uint32_t*>(&b3);
+                                *reinterpret_cast<uint4*>(box + (((jb + j) ^ (m & 7)) << 4)) = o;
+                            }
+                        }
+                        if (cb + 32 >= p.block_n) break;             // block_n == 32 with bf16 output: half a box
+                    }
+                    if (last_sub && c0 + cols_per_chunk >= p.block_n) {      // all TMEM reads of this macro tile are done: hand the buffer back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[buf])) : "memory");
+                    }
+                    fence_proxy_async();
+                    if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // previous box has left smem
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (store_thread) {
+                        if (n0 + c0 < p.cout) tma_store_4d(&map_y, staging + (chunk & 1) * (kBlockM * 128), n0 + c0, w0, h0, img0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+        }
+        if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // host side: TMA descriptors
 // ----------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -396,29 +639,77 @@ bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtyp
     return n > 0 && h > 0 && wd > 0;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// N tile of the persistent kernel: 256 halves the A-operand traffic per FLOP, 128 quantises better on small layers
+static int pick_block_n2(int cout, long long m_tiles) {
+    static const int forced = env_int("GIM_CONV_BN", 0);
+    int base = pick_block_n(cout);
+    if (base < 128) return base;
+    if (forced == 128 || forced == 256) return (forced == 256 && cout % 256 != 0) ? 128 : forced;
+    (void)m_tiles;
+    return cout % 256 == 0 ? 256 : 128;
+}
+
 int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, int out_f32,
-                   cudaStream_t st) {
+                   int epi, float slope, const void* mask_ref, cudaStream_t st) {
+    static const int use_v1 = env_int("GIM_CONV_V1", 0);
     ConvTcParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
     pixel_box(h, wd, p.bw, p.bh, p.bn);
     p.tiles_w = (wd + p.bw - 1) / p.bw;
     p.tiles_h = (h + p.bh - 1) / p.bh;
     p.tiles_n = (n + p.bn - 1) / p.bn;
-    p.block_n = pick_block_n(cout);
     p.out_f32 = out_f32;
+    p.epi = epi;
+    p.slope = slope;
     p.block_k = cin <= 16 ? 16 : kBlockK;          // skinny inputs (padded images): 32-byte K rows, one MMA per filter tap
-    const int stage_bytes = (kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2 + 1023) & ~1023;
-    // two CTAs per SM (<= ~110 KB each): one CTA's epilogue overlaps the other's MMA main loop
-    int stages = (104 * 1024) / stage_bytes;
-    if (stages > 8) stages = 8;
-    p.stages = stages;
+    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    if (m_tiles > 2147483647LL / 64) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
+    if ((epi & kEpiMask) && (!mask_ref || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the mask epilogue needs a reference tensor and cout % 32 == 0");
     CUtensorMap map_x, map_w, map_y;
-    // staged TMA-store epilogue when a whole 32-column group exists and the tile fits in the idle pipeline buffers
-    p.tma_store = (p.block_n >= 32 && (size_t)kBlockM * p.block_n * (out_f32 ? 4 : 2) <= (size_t)stages * stage_bytes) ? 1 : 0;
+    static const int force_v2 = env_int("GIM_CONV_V2", 0);
+    // measured (tools/conv_bench.py): the persistent kernel wins whenever it can use the 256-wide N tile; with 128-wide tiles two
+    // co-resident non-persistent CTAs still issue MMAs faster than one persistent CTA
+    const bool tiny = m_tiles * ((cout + 127) / 128) <= num_sms() / 2 && epi == 0;      // e.g. Linear layers: launch latency only
+    const bool v2 = !use_v1 && pick_block_n(cout) >= 32 && (!tiny || force_v2);
+    if (!v2 && epi != 0) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: fused epilogues need cout >= 32");
+    p.block_n = v2 ? pick_block_n2(cout, m_tiles) : pick_block_n(cout);
+    static const int force_msub = env_int("GIM_CONV_MSUB", 0);
+    p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;
+    if (force_msub == 1 || (force_msub == 2 && v2 && p.block_n <= 128)) p.m_sub = force_msub;
+    const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2 + 1023) & ~1023;
     if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
     if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn, p.block_k)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
     if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.block_n, p.block_k))
         return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
+    if (v2) {
+        const int fixed = kStagingBytes + 256 * (int)sizeof(float) + 64 * (int)sizeof(uint64_t) + 1024;
+        int stages = (227 * 1024 - fixed) / stage_bytes;
+        if (stages > 8) stages = 8;
+        p.stages = stages;
+        p.tma_store = 1;
+        const size_t smem = (size_t)stages * stage_bytes + fixed;
+        static bool attr_set2 = false;
+        if (!attr_set2) {
+            if (cudaFuncSetAttribute(conv_fwd_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                return fail(GIM_E_CUDA, "conv_fwd_tc: cannot raise dynamic shared memory limit");
+            attr_set2 = true;
+        }
+        const long long total = ((m_tiles + p.m_sub - 1) / p.m_sub) * ((cout + p.block_n - 1) / p.block_n);
+        const int grid = (int)(total < num_sms() ? total : num_sms());
+        conv_fwd_tc2_kernel<0><<<grid, 224, smem, st>>>(map_x, map_w, map_y, bias, (const bf16*)mask_ref, y, p);
+        return check_launch("conv_fwd_tc2");
+    }
+    // two CTAs per SM (<= ~110 KB each): one CTA's epilogue overlaps the other's MMA main loop
+    int stages = (104 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+    // staged TMA-store epilogue when a whole 32-column group exists and the tile fits in the idle pipeline buffers
+    p.tma_store = (p.block_n >= 32 && (size_t)kBlockM * p.block_n * (out_f32 ? 4 : 2) <= (size_t)stages * stage_bytes) ? 1 : 0;
     const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -426,9 +717,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
             return fail(GIM_E_CUDA, "conv_fwd_tc: cannot raise dynamic shared memory limit");
         attr_set = true;
     }
-    long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
-    if (tiles > 2147483647LL) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
-    dim3 grid((unsigned)tiles, (cout + p.block_n - 1) / p.block_n);
+    dim3 grid((unsigned)m_tiles, (cout + p.block_n - 1) / p.block_n);
     conv_fwd_tc_kernel<0><<<grid, 192, smem, st>>>(map_x, map_w, map_y, bias, y, p);
     return check_launch("conv_fwd_tc");
 }

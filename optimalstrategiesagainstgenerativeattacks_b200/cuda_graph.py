@@ -55,9 +55,10 @@ class GraphedIteration:
     def __call__(self, leaked=None, real=None, si=None):
         """Run one iteration; new batches are copied into the static input buffers (pass None to reuse them).
         Returns (im_loss, au_loss, loss_on_real, loss_on_fake, reg, out_on_real, out_on_fake) as device scalars."""
-        for dst, src in zip(self.static_in, (leaked, real, si)):
-            if src is not None:
-                dst.copy_(src, non_blocking=True)
+        with torch.no_grad():                             # R1 marks the static `real` buffer requires_grad in place
+            for dst, src in zip(self.static_in, (leaked, real, si)):
+                if src is not None:
+                    dst.copy_(src, non_blocking=True)
         self._host_bookkeeping()
         self.graph.replay()
         for opt in (self.trainer.module.authenticator_opt, self.trainer.module.impersonator_opt):
