@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
     int tile_end = tile_begin + p.tiles_per_split;
     if (tile_end > p.total_tiles) tile_end = p.total_tiles;
     const int num_kb = tile_end - tile_begin;                          // >= 1 by construction of the grid
-    const uint32_t tmem_cols = (uint32_t)p.block_n;                    // 64 or 128: powers of two >= 32
+    const uint32_t tmem_cols = 2u * (uint32_t)p.block_n;               // two accumulation chains of 64 or 128 columns
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_gy);
@@ -784,40 +784,44 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 1;
+            int tw = tile_begin % p.tiles_w, th = (tile_begin / p.tiles_w) % p.tiles_h, tn = tile_begin / (p.tiles_w * p.tiles_h);
+            const int nb = p.block_n / 64;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t round = kb / p.stages;
-                mbar_wait(&empty_bar[s], (round & 1) ^ 1);
-                int tt = tile_begin + kb;
-                const int tw = tt % p.tiles_w; tt /= p.tiles_w;
-                const int th = tt % p.tiles_h; tt /= p.tiles_h;
-                const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tt * p.bn;
+                mbar_wait(&empty_bar[s], ph);
+                const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tn * p.bn;
                 uint8_t* sa = smem + s * stage_bytes;
                 uint8_t* sb = sa + a_bytes;
                 mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
                 tma_load_4d(sa, &map_gy, &full_bar[s], co0, w0, h0, img0);
                 tma_load_4d(sa + kATileBytes, &map_gy, &full_bar[s], co0 + 64, w0, h0, img0);
-                for (int j = 0; j < p.block_n / 64; ++j)
+                for (int j = 0; j < nb; ++j)
                     tma_load_4d(sb + j * kATileBytes, &map_x, &full_bar[s], ci0 + 64 * j, w0 + dq, h0 + dr, img0);
+                if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc((uint32_t)p.block_n, 1, 1);
+            const uint32_t s0 = smem_u32(smem);
+            const uint64_t desc_a0 = make_desc_sw128(s0, kATileBytes, 1024), desc_b0 = make_desc_sw128(s0 + a_bytes, kATileBytes, 1024);
+            const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
+            const uint32_t tmem_d1 = tmem_base + (uint32_t)p.block_n;       // second accumulation chain (odd K steps), summed in the epilogue
+            int s = 0;
+            uint32_t ph = 0;
+            uint64_t da = desc_a0, db = desc_b0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t round = kb / p.stages;
-                mbar_wait(&full_bar[s], round & 1);
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+                const uint32_t acc = kb != 0 ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < kBlockM / 16; ++k) {             // 128 pixels per stage = 8 MMAs of K = 16
-                    const uint64_t da = make_desc_sw128(sa + k * 2048, kATileBytes, 1024);
-                    const uint64_t db = make_desc_sw128(sb + k * 2048, kATileBytes, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                }
+                for (int k = 0; k < kBlockM / 16; ++k)                 // 128 pixels per stage = 8 MMAs of K = 16, 2 KB apart
+                    umma_bf16((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
                 umma_commit(&empty_bar[s]);
+                da += stage_step; db += stage_step;
+                if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
             }
             umma_commit(tmem_full_bar);
         }
@@ -828,13 +832,14 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
         const int co = co0 + quarter * 32 + lane;
         float* dst_row = gw + ((long long)tap * p.cout + co) * p.cin + ci0;
         for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-            uint32_t v[16];
+            uint32_t v[16], v1[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p.block_n + c0), v1);
             tmem_ld_wait();
             if (co < p.cout) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (ci0 + c0 + j < p.cin) atomicAdd(dst_row + c0 + j, __uint_as_float(v[j]));
+                    if (ci0 + c0 + j < p.cin) atomicAdd(dst_row + c0 + j, __uint_as_float(v[j]) + __uint_as_float(v1[j]));
             }
         }
     }
