@@ -27,10 +27,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (img_size, channels, reg_param, au_lr, im_lr, mapper_lr, algorithmic GFLOP/episode/iteration as executed by the
-    #        reference, description)
-    "O": (32, 1, 0.0, 1e-6, 1e-5, 1e-7, 305.83, "GIM Omniglot-shaped 1x32x32 m=n=k=5 reg=0 (BASELINE configs[1] at the reference's Omniglot resolution)"),
-    "V": (64, 3, 10.0, 1e-4, 1e-4, 1e-6, 529.05, "GIM VoxCeleb2-shaped 3x64x64 m=n=k=5 R1 reg=10 (BASELINE configs[2])"),
+    # name: (img_size, channels, reg_param, au_lr, im_lr, mapper_lr, algorithmic GFLOP/episode/iteration, description).
+    # The GFLOP figure is SURVEY.md section 8d's *reduced* one (281 O / 494 V-R1 instead of 305.83 / 529.05): the G-step does not compute
+    # the authenticator's weight gradients, which the reference computes and discards.
+    "O": (32, 1, 0.0, 1e-6, 1e-5, 1e-7, 281.0, "GIM Omniglot-shaped 1x32x32 m=n=k=5 reg=0 (BASELINE configs[1] at the reference's Omniglot resolution)"),
+    "V": (64, 3, 10.0, 1e-4, 1e-4, 1e-6, 494.0, "GIM VoxCeleb2-shaped 3x64x64 m=n=k=5 R1 reg=10 (BASELINE configs[2])"),
 }
 M_, N_, K_ = 5, 5, 5
 STYLE = 512
@@ -313,6 +314,7 @@ def run_ours(args):
         "config": {"workload": desc, "episodes_per_gpu_per_step": B, "m": M_, "n": N_, "k": K_, "style_dim": STYLE, "parallelism": "dp%d" % world, "cuda_graph": graphed is not None,
                    "cache": "working set (activations of %d images/step) >> 126 MB L2; %d rotating input batches" % (B * 45, n_pool),
                    "algorithmic_gflop_per_episode": gflop_ep,
+                   "executed_conv_gflop_per_episode": sum(v["flops"] for v in prof.values()) / 1e9 / B,
                    "whole_step_model_tflops": gflop_ep * 1e-3 * eps_total / world},
         "e2e": {"value": eps_e2e, "unit": "episodes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

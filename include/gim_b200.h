@@ -50,10 +50,12 @@ int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y,
  * folded into the producing kernel):  v = conv(x, w) + bias;
  *   epilogue & GIM_EPI_LRELU : v = LeakyReLU_slope(v)
  *   epilogue & GIM_EPI_MASK  : v = v * (mask_ref[n,h,w,co] > 0 ? 1 : slope)   (mask_ref: bf16, same shape as y; cout % 32 == 0)
+ *   epilogue & GIM_EPI_ADD   : v = v + addend[n,h,w,co]                       (addend: fp32, same shape as y, may alias y; cout % 32 == 0)
  * y: out_dtype (fp32 or bf16). */
 #define GIM_EPI_LRELU 1
 #define GIM_EPI_MASK  2
-int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* y, const void* mask_ref,
+#define GIM_EPI_ADD   4
+int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* y, const void* mask_ref, const float* addend,
                          int n, int h, int wd, int cin, int cout, int ksize, int out_dtype, int epilogue, float slope, gim_stream_t stream);
 /* gw[t][co][ci] (fp32) = sum_{n,h,w} gy[n,h,w,co] * x[n,h+r-p,w+s-p,ci]  (overwrites gw) */
 int gim_conv2d_wgrad(const void* x, const void* gy, float* gw,
@@ -92,6 +94,11 @@ int gim_pool2_sum(const void* a, const void* b, void* y, int n, int h, int wd, i
 /* gx[n,h,w,c] = scale * gy[n,h/2,w/2,c] (0 where h/2>=ho or w/2>=wo) -- nearest Upsample x2 / AvgPool backward */
 int gim_unpool2_bcast(const void* gy, void* gx, int n, int h, int wd, int c, float scale, int dtype, gim_stream_t stream);
 /* layout + dtype conversion at the module boundary: NCHW fp32 <-> NHWC dtype */
+/* fused ResBlockDown tail (model_blocks.py:510-514): y = scale * 2x2-sum(a [+ b]) written as any of fp32 y, bf16(y), bf16(LeakyReLU(y))
+ * (NULL = skip); and the AvgPool backward emitted directly as the bf16 conv operand: gx = bf16(scale * gy[h/2, w/2]) */
+int gim_pool2_multi(const float* a, const float* b, float* y32, void* y_bf16, void* y_lrelu_bf16,
+                    int n, int h, int wd, int c, float scale, float slope, gim_stream_t stream);
+int gim_unpool2_cast(const float* gy, void* gx_bf16, int n, int h, int wd, int c, float scale, gim_stream_t stream);
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
 int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
 /* dst[row][dst_off + j] = src[row][src_off + j], j<c  (channel concat / split, gim_img_models.py:385) */

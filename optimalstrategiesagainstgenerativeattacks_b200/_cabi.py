@@ -20,7 +20,9 @@ _CODES = {"p": _P, "i": _I, "l": _L, "f": _F}
 # name -> argument codes (must match include/gim_b200.h; tests/test_cabi_symbols.py checks the symbol list)
 PROTOTYPES = {
     "gim_conv2d_fwd": "ppppiiiiiiiiip",
-    "gim_conv2d_fwd_fused": "pppppiiiiiiiifp",
+    "gim_conv2d_fwd_fused": "ppppppiiiiiiiifp",
+    "gim_pool2_multi": "pppppiiiiffp",
+    "gim_unpool2_cast": "ppiiiifp",
     "gim_conv2d_wgrad": "pppiiiiiiiip",
     "gim_weight_cast": "ppiiiip",
     "gim_weight_flip": "ppiiiip",

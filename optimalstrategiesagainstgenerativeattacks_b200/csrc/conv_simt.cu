@@ -268,7 +268,7 @@ static int conv_wgrad_simt(const void* x, const void* gy, float* gw, int n, int 
 
 // implemented in conv_tc.cu
 int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, int out_f32,
-                   int epi, float slope, const void* mask_ref, cudaStream_t st);
+                   int epi, float slope, const void* mask_ref, const float* addend, cudaStream_t st);
 int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st);
 bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
 bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
@@ -297,21 +297,21 @@ int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y, int
     if (algo == GIM_ALGO_TCGEN05 && !tc_ok) return fail(GIM_E_UNSUPPORTED, "conv2d_fwd: shape/dtype not supported by the tcgen05 path");
     GIM_REQUIRE(out_dtype == GIM_F32 || out_dtype == dtype, "conv2d_fwd: output must be fp32 or the operand dtype");
     if ((algo == GIM_ALGO_TCGEN05) || (algo == GIM_ALGO_AUTO && tc_ok))
-        return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ksize, out_dtype == GIM_F32 ? 1 : 0, 0, 0.f, nullptr, st);
+        return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ksize, out_dtype == GIM_F32 ? 1 : 0, 0, 0.f, nullptr, nullptr, st);
     if (dtype == GIM_F32) return conv_fwd_simt<float, float>(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
     if (dtype == GIM_BF16 && out_dtype == GIM_F32) return conv_fwd_simt<bf16, float>(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
     if (dtype == GIM_BF16) return conv_fwd_simt<bf16, bf16>(x, w, bias, y, n, h, wd, cin, cout, ksize, st);
     return fail(GIM_E_ARG, "conv2d_fwd: bad dtype");
 }
 
-int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* y, const void* mask_ref, int n, int h, int wd, int cin, int cout,
-                         int ksize, int out_dtype, int epilogue, float slope, gim_stream_t s) {
+int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* y, const void* mask_ref, const float* addend, int n, int h, int wd,
+                         int cin, int cout, int ksize, int out_dtype, int epilogue, float slope, gim_stream_t s) {
     GIM_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv2d_fwd_fused: empty shape");
     GIM_REQUIRE(ksize >= 1 && (ksize & 1), "conv2d_fwd_fused: kernel size must be odd ('same' padding)");
     GIM_REQUIRE(out_dtype == GIM_F32 || out_dtype == GIM_BF16, "conv2d_fwd_fused: bad output dtype");
-    GIM_REQUIRE((epilogue & ~3) == 0, "conv2d_fwd_fused: unknown epilogue bits");
+    GIM_REQUIRE((epilogue & ~7) == 0, "conv2d_fwd_fused: unknown epilogue bits");
     if (!conv_tc_supported(n, h, wd, cin, cout, ksize, GIM_BF16)) return fail(GIM_E_UNSUPPORTED, "conv2d_fwd_fused: shape not supported by the tcgen05 path");
-    return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ksize, out_dtype == GIM_F32 ? 1 : 0, epilogue, slope, mask_ref, (cudaStream_t)s);
+    return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ksize, out_dtype == GIM_F32 ? 1 : 0, epilogue, slope, mask_ref, addend, (cudaStream_t)s);
 }
 
 int gim_conv2d_wgrad(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ksize, int dtype, int algo, gim_stream_t s) {

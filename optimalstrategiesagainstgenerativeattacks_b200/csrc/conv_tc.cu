@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
 //   rotating staging buffers) runs while the MMA warp already accumulates tile i+1; the TMA/MMA smem ring never drains between
 //   tiles.  Fused epilogues: + bias, LeakyReLU, LeakyReLU-backward mask taken from a saved bf16 operand, fp32 or bf16 output.
 // ----------------------------------------------------------------------------------------------------------------
-enum { kEpiLrelu = 1, kEpiMask = 2 };
+enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4 };
 constexpr int kStagingBytes = 2 * kBlockM * 128;          // two 16 KB boxes (128 rows x 128 B)
 
 // A macro tile = m_sub (1 or 2) consecutive 128-pixel tiles x one block_n-wide channel tile.  With m_sub = 2 the two pixel tiles
@@ -329,7 +329,8 @@ constexpr int kStagingBytes = 2 * kBlockM * 128;          // two 16 KB boxes (12
 template <int kDummy>
 __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                                               const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias,
-                                                              const bf16* __restrict__ mask_ref, void* __restrict__ y, const ConvTcParams p) {
+                                                              const bf16* __restrict__ mask_ref, const float* addend, void* __restrict__ y,
+                                                              const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = kBlockM * p.block_k * 2;
@@ -505,6 +506,16 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
                                 }
                             }
                         }
+                        if (p.epi & kEpiAdd) {
+                            if (valid && n0 + cb < p.cout) {
+                                const float4* ad = reinterpret_cast<const float4*>(addend + pix * p.cout + n0 + cb);
+#pragma unroll
+                                for (int v4 = 0; v4 < 8; ++v4) {
+                                    const float4 t4 = ad[v4];          // plain load: the addend may alias the output of this launch
+                                    f[4 * v4] += t4.x; f[4 * v4 + 1] += t4.y; f[4 * v4 + 2] += t4.z; f[4 * v4 + 3] += t4.w;
+                                }
+                            }
+                        }
                         if (p.out_f32) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
@@ -655,7 +666,7 @@ static int pick_block_n2(int cout, long long m_tiles) {
 }
 
 int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, int out_f32,
-                   int epi, float slope, const void* mask_ref, cudaStream_t st) {
+                   int epi, float slope, const void* mask_ref, const float* addend, cudaStream_t st) {
     static const int use_v1 = env_int("GIM_CONV_V1", 0);
     ConvTcParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
@@ -670,6 +681,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     if (m_tiles > 2147483647LL / 64) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
     if ((epi & kEpiMask) && (!mask_ref || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the mask epilogue needs a reference tensor and cout % 32 == 0");
+    if ((epi & kEpiAdd) && (!addend || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the add epilogue needs an addend tensor and cout % 32 == 0");
     CUtensorMap map_x, map_w, map_y;
     static const int force_v2 = env_int("GIM_CONV_V2", 0);
     // measured (tools/conv_bench.py): the persistent kernel wins whenever it can use the 256-wide N tile; with 128-wide tiles two
@@ -701,7 +713,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
         }
         const long long total = ((m_tiles + p.m_sub - 1) / p.m_sub) * ((cout + p.block_n - 1) / p.block_n);
         const int grid = (int)(total < num_sms() ? total : num_sms());
-        conv_fwd_tc2_kernel<0><<<grid, 224, smem, st>>>(map_x, map_w, map_y, bias, (const bf16*)mask_ref, y, p);
+        conv_fwd_tc2_kernel<0><<<grid, 224, smem, st>>>(map_x, map_w, map_y, bias, (const bf16*)mask_ref, addend, y, p);
         return check_launch("conv_fwd_tc2");
     }
     // two CTAs per SM (<= ~110 KB each): one CTA's epilogue overlaps the other's MMA main loop

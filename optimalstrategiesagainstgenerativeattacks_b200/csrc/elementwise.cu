@@ -145,6 +145,77 @@ __global__ void __launch_bounds__(256) unpool2_vec_kernel(const T* __restrict__ 
     }
 }
 
+
+// AvgPool2d(2) of (a + b) with up to three outputs from one pass: fp32 y, bf16(y) and bf16(LeakyReLU(y)) -- the operands the next
+// ResBlockDown's 1x1 and 3x3 convolutions consume, so no separate cast / activation kernels touch HBM.  c % 4 == 0.
+__global__ void __launch_bounds__(256) pool2_multi_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y32,
+                                                          bf16* __restrict__ yb, bf16* __restrict__ yl, int n, int h, int w, int c, float scale,
+                                                          float slope) {
+    int ho = h / 2, wo = w / 2, cv = c / 4;
+    long long total = (long long)n * ho * wo * cv;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % cv) * 4;
+        long long p = i / cv;
+        int x = (int)(p % wo); p /= wo;
+        int yy = (int)(p % ho);
+        long long img = p / ho;
+        long long base = ((img * h + 2 * yy) * w + 2 * x) * (long long)c + ch;
+        long long rs = (long long)w * c;
+        const long long offs[4] = {0, (long long)c, rs, rs + c};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 t = *reinterpret_cast<const float4*>(a + base + offs[q]);
+            acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+            if (b) {
+                float4 u = *reinterpret_cast<const float4*>(b + base + offs[q]);
+                acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] *= scale;
+        long long o = ((img * ho + yy) * wo + x) * (long long)c + ch;
+        if (y32) *reinterpret_cast<float4*>(y32 + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (yb) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+            uint2 r; r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(yb + o) = r;
+        }
+        if (yl) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(lrelu_f(acc[0], slope), lrelu_f(acc[1], slope));
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(lrelu_f(acc[2], slope), lrelu_f(acc[3], slope));
+            uint2 r; r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(yl + o) = r;
+        }
+    }
+}
+
+// out[n,h,w,c] (bf16) = scale * g[n,h/2,w/2,c] (0 outside for odd h/w): the AvgPool backward written directly as the bf16 operand
+// of the input- and weight-gradient convolutions.  c % 8 == 0.
+__global__ void __launch_bounds__(256) unpool2_cast_kernel(const float* __restrict__ g, bf16* __restrict__ out, int n, int h, int w, int c, float scale) {
+    int ho = h / 2, wo = w / 2, cv = c / 8;
+    long long total = (long long)n * h * w * cv;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int ch = (int)(i % cv) * 8;
+        long long p = i / cv;
+        int x = (int)(p % w); p /= w;
+        int yy = (int)(p % h);
+        long long img = p / h;
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if ((yy >> 1) < ho && (x >> 1) < wo) {
+            const float* src = g + ((img * ho + (yy >> 1)) * wo + (x >> 1)) * (long long)c + ch;
+            float4 t0 = *reinterpret_cast<const float4*>(src), t1 = *reinterpret_cast<const float4*>(src + 4);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(scale * t0.x, scale * t0.y), p1 = __floats2bfloat162_rn(scale * t0.z, scale * t0.w);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(scale * t1.x, scale * t1.y), p3 = __floats2bfloat162_rn(scale * t1.z, scale * t1.w);
+            r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+            r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+        }
+        *reinterpret_cast<uint4*>(out + ((img * h + yy) * (long long)w + x) * c + ch) = r;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
                                                     int n, int h, int w, int c, float scale) {
@@ -409,6 +480,22 @@ int gim_unpool2_bcast(const void* gy, void* gx, int n, int h, int wd, int c, flo
     else
         GIM_DISPATCH_DTYPE(dtype, (unpool2_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)gy, (T*)gx, n, h, wd, c, scale)));
     return check_launch("unpool2_bcast");
+}
+int gim_pool2_multi(const float* a, const float* b, float* y32, void* y_bf16, void* y_lrelu_bf16, int n, int h, int wd, int c, float scale, float slope,
+                    gim_stream_t s) {
+    long long total = (long long)n * (h / 2) * (wd / 2) * c;
+    if (total <= 0) return GIM_OK;
+    GIM_REQUIRE(c % 4 == 0 && aligned16(a) && (!b || aligned16(b)) && (!y32 || aligned16(y32)) && (!y_bf16 || aligned16(y_bf16)) &&
+                    (!y_lrelu_bf16 || aligned16(y_lrelu_bf16)), "pool2_multi: needs c % 4 == 0 and 16-byte aligned tensors");
+    pool2_multi_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, (cudaStream_t)s>>>(a, b, y32, (bf16*)y_bf16, (bf16*)y_lrelu_bf16, n, h, wd, c, scale, slope);
+    return check_launch("pool2_multi");
+}
+int gim_unpool2_cast(const float* gy, void* gx_bf16, int n, int h, int wd, int c, float scale, gim_stream_t s) {
+    long long total = (long long)n * h * wd * c;
+    if (total <= 0) return GIM_OK;
+    GIM_REQUIRE(c % 8 == 0 && aligned16(gy) && aligned16(gx_bf16), "unpool2_cast: needs c % 8 == 0 and 16-byte aligned tensors");
+    unpool2_cast_kernel<<<ew_grid(total / 8, 256, 1), 256, 0, (cudaStream_t)s>>>(gy, (bf16*)gx_bf16, n, h, wd, c, scale);
+    return check_launch("unpool2_cast");
 }
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t s) {
     int hw = h * wd;

@@ -51,7 +51,9 @@ class Encoder(nn.Module):
         for i in range(self.n_down_blocks):
             if i == self.att_loc:
                 x = self.att(x)
-            x = self.down_blocks[i](x)
+            x = self.down_blocks[i](x, want_ops=i + 1 < self.n_down_blocks)       # the next consumer reads the bf16 operands
+        if isinstance(x, ops.Act):
+            x = x.t32
         x = ops.GlobalMaxFn.apply(x)
         if self.use_out_lrelu:
             x = ops.lrelu(x)
@@ -119,7 +121,7 @@ class Img2ImgDownModule(nn.Module):
             if i == self.att_loc:
                 x = self.att(x)
             x = self.down_blocks[i](x)
-            x = self.in_layers[i](x)
+            x = self.in_layers[i](x.t32 if isinstance(x, ops.Act) else x)
         return x
 
 

@@ -1,5 +1,6 @@
 """GIMImgTrainer -- same constructor, modes, return tuples, optimizer layout and checkpoint registration as the reference's
 training/gim_img_trainer.py; losses and optimizers run on libgim_b200 kernels."""
+import contextlib
 import os
 
 import torch
@@ -10,6 +11,19 @@ from . import ops
 from .checkpoints import CheckpointIO
 from .fused_adam import FusedAdam
 from .utils import GlobalStep, compute_grad2, num_parameters
+
+
+@contextlib.contextmanager
+def _frozen(module):
+    """Inside, the module's parameters do not require grad (graphs recorded inside treat them as constants)."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    for p in params:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p in params:
+            p.requires_grad_(True)
 
 
 class GIMImgTrainer(nn.Module):
@@ -70,10 +84,12 @@ class GIMImgTrainer(nn.Module):
             real_sample.requires_grad_()
             si_sample.requires_grad_()
         au = self.authenticator
-        au_si_src = au.src_encode_sample(si_sample)
-        au_si_env = au.env_encode_sample(si_sample)
-        au_real_src = au.src_encode_sample(real_sample)
-        au_real_env = au.env_encode_sample(real_sample)
+        # the R1 penalty differentiates the real/si branch twice: run it with the elementary (twice differentiable) operators
+        with (ops.composite_mode() if (grad and self.reg_param > 0) else contextlib.nullcontext()):
+            au_si_src = au.src_encode_sample(si_sample)
+            au_si_env = au.env_encode_sample(si_sample)
+            au_real_src = au.src_encode_sample(real_sample)
+            au_real_env = au.env_encode_sample(real_sample)
         au_fake_src = au.src_encode_sample(fake_sample)
         au_fake_env = au.env_encode_sample(fake_sample)
 
@@ -97,7 +113,11 @@ class GIMImgTrainer(nn.Module):
 
     def impersonator_forward(self, leaked_sample, si_sample):
         fake_sample = self.impersonator(leaked_sample=leaked_sample, n=self.n, remove_noise_mean=self.remove_noise_mean)
-        auth_out = self.authenticator(test_sample=fake_sample, si_sample=si_sample)
+        # The reference lets this backward fill the authenticator's .grad and then discards it (authenticator_opt.zero_grad() at
+        # training/gim_img_training.py:172 precedes its only use): treat D's weights as constants here, so neither its weight
+        # gradients nor the whole backward of the si branch are computed.
+        with _frozen(self.authenticator):
+            auth_out = self.authenticator(test_sample=fake_sample, si_sample=si_sample)
         loss = self.gan_loss(dis_out=auth_out, target=1.)
         return loss, fake_sample, auth_out
 

@@ -131,7 +131,14 @@ class ResBlockDown(nn.Module):
         self.conv_r1 = SNConv2d(in_channel, out_channel, conv_size, padding=padding_size)
         self.conv_r2 = SNConv2d(out_channel, out_channel, conv_size, padding=padding_size)
 
-    def forward(self, x):
+    def forward(self, x, want_ops=False):
+        """x: fp32 NHWC tensor or ops.Act.  On the bf16 tensor-core path the whole block is one fused autograd node and the result is
+        an ops.Act (fp32 output + the bf16 operands of the next block when `want_ops`); otherwise a plain tensor."""
+        if ops.fused_blocks_enabled() and self.conv_r2.out_channels % 32 == 0:
+            return ops.res_block_down(x, self.conv_l1.effective_weight(), self.conv_l1.bias, self.conv_r1.effective_weight(), self.conv_r1.bias,
+                                      self.conv_r2.effective_weight(), self.conv_r2.bias, self.conv_r1.kernel_size, 0.2, want_ops)
+        if isinstance(x, ops.Act):
+            x = x.t32
         out_res = self.conv_l1(x)
         out = self.conv_r1(x, ops.PRE_LRELU)          # conv(lrelu(x)): the activation is fused into the operand producer
         out = self.conv_r2(out, ops.PRE_LRELU)
@@ -150,6 +157,9 @@ class SelfAttention(nn.Module):
         self.gamma = nn.Parameter(torch.zeros(1))
 
     def forward(self, x):
+        if isinstance(x, ops.Act):
+            ops.register_operand(x.t32, x.tb)             # the three 1x1 convs read the bf16 copy the pooling kernel already wrote
+            x = x.t32
         n, h, w, c = x.shape
         f = self.conv_f(x).reshape(n, h * w, -1)          # keys    [n, N, c/8]
         g = self.conv_g(x).reshape(n, h * w, -1)          # queries [n, N, c/8]

@@ -21,7 +21,7 @@ from torch.autograd.function import once_differentiable
 from . import _cabi as C
 
 LRELU_SLOPE = 0.2
-_state = {"operand_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False}
+_state = {"operand_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False, "composite": False}
 
 
 def set_precision(name):
@@ -62,6 +62,23 @@ def input_grads_only():
         _state["input_grads_only"] = old
 
 
+@contextlib.contextmanager
+def composite_mode():
+    """Inside, the block-level fused operators are bypassed and every block runs as a composition of the elementary operators,
+    whose backward is itself differentiable -- required wherever a second-order graph is built (the R1 pass, compute_grad2)."""
+    old = _state["composite"]
+    _state["composite"] = True
+    try:
+        yield
+    finally:
+        _state["composite"] = old
+
+
+def fused_blocks_enabled():
+    """Block-level fusion exists on the bf16 tensor-core path only; the fp32 path stays the plain rel-1e-4 parity path."""
+    return _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and not _state["composite"]
+
+
 def _empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
@@ -71,6 +88,14 @@ def _c(t):
 
 
 _cast_memo = {}     # id(tensor) -> (weakref, version, operand copy): conv_l1 / attention convs / dgrad+wgrad share one cast
+
+
+def register_operand(t, op):
+    """Tell the operand cache that `op` already is `t` rounded to the operand dtype (written by a fused producer kernel)."""
+    if op is not None and op.dtype == _state["operand_dtype"]:
+        if len(_cast_memo) >= 4:
+            _cast_memo.clear()
+        _cast_memo[id(t)] = (weakref.ref(t), t._version, op)
 
 
 def _operand(t):
@@ -135,7 +160,7 @@ def _timed_call(kind, flops, name, *args):
     e0.record()
     C.call(name, *args)
     e1.record()
-    off = 3 if name == "gim_conv2d_wgrad" else 4
+    off = {"gim_conv2d_wgrad": 3, "gim_conv2d_fwd_fused": 6}.get(name, 4)
     _profile.setdefault(kind, []).append((flops, e0, e1, tuple(args[off:off + 6])))     # (n, h, w, ci, co, ks)
 
 
@@ -351,6 +376,138 @@ class RowBroadcastFn(Function):
     @staticmethod
     def backward(ctx, g):
         return ColSumFn.apply(g), None, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# block-level fused operators (bf16 tensor-core path, first order)
+# ------------------------------------------------------------------------------------------------------------
+EPI_LRELU, EPI_MASK, EPI_ADD = 1, 2, 4
+
+
+class Act:
+    """An activation together with the bf16 conv operands derived from it: t32 (fp32 NHWC, what autograd tracks), tb = bf16(t32),
+    tl = bf16(LeakyReLU(t32)).  Produced by the fused pooling kernel so that the next block never re-reads t32."""
+    __slots__ = ("t32", "tb", "tl")
+
+    def __init__(self, t32, tb=None, tl=None):
+        self.t32, self.tb, self.tl = t32, tb, tl
+
+
+def _conv_tc_fused(x, w_op, bias, ks, out_dtype, epi=0, slope=LRELU_SLOPE, mask_ref=None, addend=None, out=None):
+    """tcgen05 conv with a fused epilogue.  x bf16 [n,h,w,ci] (ci % 8 == 0), w_op bf16 [taps,co,ci] (co % 16 == 0)."""
+    n, h, w, ci = x.shape
+    taps, co, _ = w_op.shape
+    y = out if out is not None else _empty((n, h, w, co), out_dtype, x)
+    _timed_call("tcgen05" if _profile is not None else None, 2.0 * n * h * w * ci * co * taps, "gim_conv2d_fwd_fused", C.ptr(x), C.ptr(w_op), C.ptr(bias),
+                C.ptr(y), C.ptr(mask_ref), C.ptr(addend), n, h, w, ci, co, ks, C.dtype_code(y), epi, slope)
+    return y
+
+
+def _skinny_in(xop, w_t, ks):
+    """A conv whose input has a few channels (images) as a dense 1x1 GEMM over the tap-unrolled input: -> (xcol, w2 [1,co,kc])."""
+    taps, co, ci = w_t.shape
+    kc = _round_up(taps * ci, 8)
+    w2 = torch.zeros((1, co, kc), dtype=w_t.dtype, device=w_t.device)
+    w2[0, :, :taps * ci] = w_t.permute(1, 0, 2).reshape(co, taps * ci)
+    return _im2col(xop, ks, 1, kc), w2
+
+
+def _unskinny_gw(gw2, taps, co, ci):
+    return gw2[0, :, :taps * ci].reshape(co, taps, ci).permute(1, 0, 2).contiguous()
+
+
+def _colsum(x):
+    c = x.shape[-1]
+    out = _empty((c,), torch.float32, x)
+    C.call("gim_colsum", C.ptr(x), C.ptr(out), x.numel() // c, c, C.dtype_code(x))
+    return out
+
+
+class ResBlockDownFn(Function):
+    """AvgPool2(conv1x1(x)) + AvgPool2(conv_k(lrelu(conv_k(lrelu(x)))))  (reference model_blocks.py:486-514) as ONE autograd node:
+    the activation between the two k x k convs only exists as the bf16 LeakyReLU'd operand written by the first conv's epilogue,
+    the pooled output is written once together with the operands of the next block, and in the backward the AvgPool gradient, the
+    LeakyReLU masks and the residual sum are folded into the producing kernels' epilogues.  First order only (see composite_mode)."""
+
+    @staticmethod
+    def forward(ctx, x32, xb, xl, wl, bl, w1, b1, w2, b2, ks, slope, want_ops):
+        od = torch.bfloat16
+        x32 = _c(x32)
+        if xb is None:
+            xb = _operand(x32)
+        if xl is None:
+            xl = _prepare_operand(x32, PRE_LRELU, slope)
+        n, h, w, ci = xb.shape
+        wl_t, w1_t, w2_t = _weight_as(_c(wl), od, False), _weight_as(_c(w1), od, False), _weight_as(_c(w2), od, False)
+        skinny = ci % 8 != 0
+        if skinny:
+            xa, wl_e = _skinny_in(xb, wl_t, 1)
+            xr, w1_e = _skinny_in(xl, w1_t, ks)
+            k1 = 1
+        else:
+            xa, wl_e, xr, w1_e, k1 = xb, wl_t, xl, w1_t, ks
+        res = _conv_tc_fused(xa, wl_e, bl, 1, torch.float32)
+        tl = _conv_tc_fused(xr, w1_e, b1, k1, od, EPI_LRELU, slope)
+        o = _conv_tc_fused(tl, w2_t, b2, ks, torch.float32)
+        co = o.shape[-1]
+        y32 = _empty((n, h // 2, w // 2, co), torch.float32, o)
+        yb = torch.empty_like(y32, dtype=od) if want_ops else None
+        yl = torch.empty_like(y32, dtype=od) if want_ops else None
+        C.call("gim_pool2_multi", C.ptr(res), C.ptr(o), C.ptr(y32), C.ptr(yb), C.ptr(yl), n, h, w, co, 0.25, slope)
+        ctx.cfg = (ks, slope, skinny, (n, h, w, ci, co), want_ops)
+        ctx.save_for_backward(xa, xr, xl, tl, wl, w1, w2)
+        if want_ops:
+            ctx.mark_non_differentiable(yb, yl)
+            return y32, yb, yl
+        return y32, None, None
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, _gb, _gl):
+        xa, xr, xl, tl, wl, w1, w2 = ctx.saved_tensors
+        ks, slope, skinny, (n, h, w, ci, co), _ = ctx.cfg
+        od = torch.bfloat16
+        taps = ks * ks
+        gy = _c(gy)
+        g = _empty((n, h, w, co), od, gy)                      # AvgPool backward, written once as the bf16 operand
+        C.call("gim_unpool2_cast", C.ptr(gy), C.ptr(g), n, h, w, co, 0.25)
+        gt = _conv_tc_fused(g, _weight_as(w2, od, True), None, ks, od, EPI_MASK, slope, mask_ref=tl)      # d/d(conv_r1 output), masked
+        gwl = gbl = gw1 = gb1 = gw2 = gb2 = None
+        want_w = not _state["input_grads_only"]
+        if want_w and ctx.needs_input_grad[3]:
+            gwl = _wgrad_raw(xa, g, 1)
+            if skinny:
+                gwl = _unskinny_gw(gwl, 1, co, ci)
+        if want_w and ctx.needs_input_grad[7]:
+            gw2 = _wgrad_raw(tl, g, ks)
+        if want_w and ctx.needs_input_grad[5]:
+            gw1 = _wgrad_raw(xr, gt, 1 if skinny else ks)
+            if skinny:
+                gw1 = _unskinny_gw(gw1, taps, co, ci)
+        if want_w and (ctx.needs_input_grad[4] or ctx.needs_input_grad[8]):
+            gbl = gb2 = _colsum(gy)                                # both biases see the same gradient; sum(unpool(gy)/4) == sum(gy), in fp32
+        if want_w and ctx.needs_input_grad[6]:
+            gb1 = _colsum(gt)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if not skinny and ci % 32 == 0:
+                gx = _conv_tc_fused(g, _weight_as(wl, od, True), None, 1, torch.float32)
+                _conv_tc_fused(gt, _weight_as(w1, od, True), None, ks, torch.float32, EPI_MASK | EPI_ADD, slope, mask_ref=xl, addend=gx, out=gx)
+            else:                                                  # image-side block: few channels, elementary kernels
+                gx = _conv_raw(g, _weight_as(wl, od, True), None, 1)
+                g2 = _conv_raw(gt, _weight_as(w1, od, True), None, ks)
+                gm = torch.empty_like(g2)
+                C.call("gim_lrelu_bwd_ref", C.ptr(g2), C.ptr(xl), C.dtype_code(xl), C.ptr(gm), g2.numel(), slope)
+                C.call("gim_axpby", C.ptr(gx), C.ptr(gm), C.ptr(gx), gx.numel(), 1.0, 1.0, C.F32)
+        return gx, None, None, gwl, gbl, gw1, gb1, gw2, gb2, None, None, None
+
+
+def res_block_down(x, wl, bl, w1, b1, w2, b2, ks, slope=LRELU_SLOPE, want_ops=True):
+    """x: Act or fp32 NHWC tensor -> Act."""
+    if not isinstance(x, Act):
+        x = Act(x)
+    y32, yb, yl = ResBlockDownFn.apply(x.t32, x.tb, x.tl, wl, bl, w1, b1, w2, b2, ks, slope, want_ops)
+    return Act(y32, yb, yl)
 
 
 # ------------------------------------------------------------------------------------------------------------

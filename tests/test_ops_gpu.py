@@ -371,3 +371,56 @@ def test_conv_with_fused_prologue(prec, tol):
         assert rel_err(nchw(gx), gx64) < tol
         dX, dW, dB = torch.autograd.grad(s.sum() + 0.5 * ops.RowsSqSumFn.apply(gx.reshape(1, -1)).sum(), (x, wp, b))
         assert rel_err(nchw(dX), gX) < tol and rel_err(unpack_w(dW, k), gW) < tol and rel_err(dB, gB) < tol
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 128, 3, 16, 16), (2, 1, 128, 3, 32, 32), (2, 2, 64, 9, 16, 16), (4, 256, 512, 3, 8, 8), (2, 32, 64, 3, 13, 9)])
+def test_res_block_down_fused(shape):
+    """The block-level fused ResBlockDown (bf16 path: epilogue-fused LeakyReLU / masks / residual add, multi-output pooling) against
+    the float64 statement of model_blocks.py:486-514, and against the composition of elementary operators it replaces."""
+    ops = ops_mod()
+    ops.set_precision("bf16")
+    n, ci, co, k, h, w = shape
+    x64 = rnd(n, ci, h, w, seed=1).requires_grad_()
+    ws = [(rnd(co, ci, 1, 1, seed=2) / np.sqrt(ci)), (rnd(co, ci, k, k, seed=3) / np.sqrt(ci * k * k)), (rnd(co, co, k, k, seed=4) / np.sqrt(co * k * k))]
+    bs = [rnd(co, seed=5 + i, scale=0.1) for i in range(3)]
+    for t in ws + bs:
+        t.requires_grad_()
+    pad = (k - 1) // 2
+    res = F.conv2d(x64, ws[0], bs[0])
+    out = F.conv2d(F.leaky_relu(F.conv2d(F.leaky_relu(x64, 0.2), ws[1], bs[1], padding=pad), 0.2), ws[2], bs[2], padding=pad)
+    y64 = F.avg_pool2d(res, 2) + F.avg_pool2d(out, 2)
+    probe = rnd(*y64.shape, seed=9)
+    ref = torch.autograd.grad((y64 * probe).sum(), [x64] + ws + bs)
+    pr = probe.permute(0, 2, 3, 1).contiguous().to("cuda", torch.float32)
+
+    def run(fused):
+        x = to_dev_nhwc(x64.detach(), torch.float32)
+        wp = [pack_w(t.detach()) for t in ws]
+        bp = [t.detach().to("cuda", torch.float32).requires_grad_() for t in bs]
+        if fused:
+            y = ops.res_block_down(x, wp[0], bp[0], wp[1], bp[1], wp[2], bp[2], k, 0.2, True)
+            assert y.tb.dtype == torch.bfloat16 and torch.equal(y.tb, y.t32.bfloat16())
+            assert torch.equal(y.tl, F.leaky_relu(y.t32, 0.2).bfloat16())
+            y = y.t32
+        else:
+            r = ops.conv2d(x, wp[0], bp[0], 1)
+            o = ops.conv2d(ops.conv2d(x, wp[1], bp[1], k, ops.PRE_LRELU, 0.2), wp[2], bp[2], k, ops.PRE_LRELU, 0.2)
+            y = ops.avg_pool2_add(r, o)
+        g = torch.autograd.grad(ops.DotFn.apply(y, pr).sum(), [x] + wp + bp)
+        return y, g
+
+    yf, gf = run(True)
+    yc, gc = run(False)
+    assert rel_err(nchw(yf), y64) < BF16_TOL
+    assert rel_err(yf, yc) < 1e-5                         # same operand roundings: the fused block is the same arithmetic
+    names = ["x", "w_l1", "w_r1", "w_r2", "b_l1", "b_r1", "b_r2"]
+    for i, nm in enumerate(names):
+        a, c, r = gf[i], gc[i], ref[i]
+        if nm == "x":
+            a, c = nchw(a), nchw(c)
+        elif nm.startswith("w"):
+            kk = 1 if nm == "w_l1" else k
+            a, c = unpack_w(a, kk), unpack_w(c, kk)
+        assert rel_err(a, c) < 5e-3, nm                   # fused vs composite differ only by where bf16 roundings of gradients fall
+        # gradients pass through two LeakyReLU masks decided on bf16-rounded activations: both bf16 evaluations sit ~1-2 % from float64
+        assert rel_err(a, r) < 2.5 * BF16_TOL, nm
