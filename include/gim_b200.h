@@ -143,6 +143,12 @@ int gim_gemm_strided(const void* A, int dtA, long long sAb, long long sAm, long 
                      void* C, int dtC, long long sCb, long long ldc,
                      int m, int n, int k, int batch, float alpha, float beta, gim_stream_t stream);
 /* y[row][j] = x[row][j] + bias[j] ; act LeakyReLU(slope) if slope!=1 */
+/* the same GEMM on the tensor cores: each operand split hi+lo into two bf16 numbers, product = hi*hi + lo*hi + hi*lo in fp32
+ * (~2^-16 relative: fp32-grade attention logits at tensor-core speed) */
+int gim_gemm_strided_bf16(const void* A, int dtA, long long sAb, long long sAm, long long sAk,
+                          const void* B, int dtB, long long sBb, long long sBk, long long sBn,
+                          void* C, int dtC, long long sCb, long long ldc,
+                          int m, int n, int k, int batch, float alpha, float beta, gim_stream_t stream);
 int gim_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int c, float slope, gim_stream_t stream);
 int gim_softmax_rows_fwd(const float* x, float* y, long long rows, int cols, gim_stream_t stream);
 int gim_softmax_rows_bwd(const float* gy, const float* y, float* gx, long long rows, int cols, gim_stream_t stream);

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "gim_norm_coeffs": "ippppppiiifp",
     "gim_norm_bwd_coeffs": "ippppppppp" + "iiifp",
     "gim_gemm_strided": "pilllpilllpilliiiiffp",
+    "gim_gemm_strided_bf16": "pilllpilllpilliiiiffp",
     "gim_bias_act_fwd": "ppplifp",
     "gim_softmax_rows_fwd": "pplip",
     "gim_softmax_rows_bwd": "ppplip",

@@ -70,6 +70,162 @@ __global__ void __launch_bounds__(256) gemm_strided_kernel(const void* __restric
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// The same strided batched GEMM on the tensor cores for the bf16 path (attention bmm pair and its gradients: thousands of small
+// matrices, N_tok <= 256).  The attention logits and their softmax gradients are cancellation-prone, so the operands are NOT simply
+// rounded: each fp32 value is split hi + lo into two bf16 numbers while it is staged in shared memory (k-contiguous rows, so every
+// transpose combination feeds ldmatrix the same way) and the product is a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation
+// (mma.sync.m16n8k16) -- ~2^-16 relative, i.e. fp32-grade results at tensor-core speed.  These GEMMs are HBM-bound at a few GFLOP
+// each, so the legacy warp-level MMA (x3) is ample; tcgen05 stays reserved for the convolutions.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int TBM = 64, TBN = 64, TBK = 32, TLD = TBK + 8;       // 80-byte rows: conflict-free ldmatrix
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const bf16* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+
+__device__ __forceinline__ void split_store(bf16* hi, bf16* lo, float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    *hi = h;
+    *lo = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// One ROWS x TBK operand tile -> smem [row][k] as hi + lo bf16.  fp32 operands whose unit-stride axis is 16-byte aligned are read
+// with float4 loads (along k, or along the row axis for transposed operands); anything else element by element.
+template <int ROWS>
+__device__ __forceinline__ void stage_split_tile(bf16 (*hi)[TLD], bf16 (*lo)[TLD], const void* __restrict__ P, int dt, long long off, long long s_row,
+                                                 long long s_k, int row0, int rows_total, int k0, int K, int tid) {
+    const bool k_fast = (s_k == 1);
+    const bool vec = dt == GIM_F32 && (((uintptr_t)P) & 15) == 0 && (off & 3) == 0 && (k_fast ? (s_row & 3) == 0 : (s_row == 1 && (s_k & 3) == 0));
+    if (vec) {
+        const float* p = (const float*)P + off;
+        if (k_fast) {
+            for (int e = tid; e < ROWS * (TBK / 4); e += 128) {
+                const int r = e / (TBK / 4), kq = (e % (TBK / 4)) * 4;
+                const int gr = row0 + r, gk = k0 + kq;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (gr < rows_total) {
+                    if (gk + 3 < K) {
+                        const float4 t = *reinterpret_cast<const float4*>(p + gr * s_row + gk);
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (gk + i < K) v[i] = p[gr * s_row + gk + i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_store(&hi[r][kq + i], &lo[r][kq + i], v[i]);
+            }
+        } else {
+            for (int e = tid; e < (ROWS / 4) * TBK; e += 128) {
+                const int kk = e / (ROWS / 4), rq = (e % (ROWS / 4)) * 4;
+                const int gr = row0 + rq, gk = k0 + kk;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (gk < K) {
+                    if (gr + 3 < rows_total) {
+                        const float4 t = *reinterpret_cast<const float4*>(p + gk * s_k + gr);
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (gr + i < rows_total) v[i] = p[gk * s_k + gr + i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_store(&hi[rq + i][kk], &lo[rq + i][kk], v[i]);
+            }
+        }
+        return;
+    }
+    for (int e = tid; e < ROWS * TBK; e += 128) {
+        int r, kk;
+        if (k_fast) { r = e / TBK; kk = e % TBK; } else { kk = e / ROWS; r = e % ROWS; }
+        const int gr = row0 + r, gk = k0 + kk;
+        split_store(&hi[r][kk], &lo[r][kk], (gr < rows_total && gk < K) ? ld_dt(P, off + gr * s_row + gk * s_k, dt) : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(128) gemm_strided_mma_kernel(const void* __restrict__ A, int dtA, long long sAb, long long sAm, long long sAk,
+                                                               const void* __restrict__ B, int dtB, long long sBb, long long sBk, long long sBn,
+                                                               void* __restrict__ C, int dtC, long long sCb, long long ldc, int M, int N, int K,
+                                                               float alpha, float beta) {
+    __shared__ __align__(16) bf16 As[TBM][TLD], Al[TBM][TLD];     // hi / lo parts
+    __shared__ __align__(16) bf16 Bs[TBN][TLD], Bl[TBN][TLD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
+    const long long b = blockIdx.z;
+    const long long a_off = b * sAb, b_off = b * sBb, c_off = b * sCb;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += TBK) {
+        // stage the two tiles as [row][k] hi/lo bf16, walking the unit-stride axis of each operand with consecutive threads
+        stage_split_tile<TBM>(As, Al, A, dtA, a_off, sAm, sAk, m0, M, k0, K, tid);
+        stage_split_tile<TBN>(Bs, Bl, B, dtB, b_off, sBn, sBk, n0, N, k0, K, tid);
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < TBK; ks += 16) {
+            uint32_t af[2][4], al[2][4], bfr[2][4], bl[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {     // A 16x16: matrices (rows 0-7,k 0-7) (rows 8-15,k 0-7) (rows 0-7,k 8-15) (rows 8-15,k 8-15)
+                ldmatrix_x4(af[i], &As[wm + i * 16 + (lane & 15)][ks + (lane >> 4) * 8]);
+                ldmatrix_x4(al[i], &Al[wm + i * 16 + (lane & 15)][ks + (lane >> 4) * 8]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {     // B, two n8 tiles per x4: (n 0-7,k 0-7) (n 0-7,k 8-15) (n 8-15,k 0-7) (n 8-15,k 8-15)
+                ldmatrix_x4(bfr[j], &Bs[wn + j * 16 + (lane & 7) + ((lane >> 4) << 3)][ks + ((lane >> 3) & 1) * 8]);
+                ldmatrix_x4(bl[j], &Bl[wn + j * 16 + (lane & 7) + ((lane >> 4) << 3)][ks + ((lane >> 3) & 1) * 8]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int jj = j >> 1, q = (j & 1) * 2;
+                    mma_bf16_16816(acc[i][j], al[i], bfr[jj][q], bfr[jj][q + 1]);      // small terms first
+                    mma_bf16_16816(acc[i][j], af[i], bl[jj][q], bl[jj][q + 1]);
+                    mma_bf16_16816(acc[i][j], af[i], bfr[jj][q], bfr[jj][q + 1]);
+                }
+        }
+        __syncthreads();
+    }
+    const bool c_vec = dtC == GIM_F32 && beta == 0.f && (((uintptr_t)C) & 7) == 0 && ((c_off | ldc) & 1) == 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int gm = m0 + wm + i * 16 + (lane >> 2) + hrow * 8;
+                const int gn = n0 + wn + j * 8 + (lane & 3) * 2;
+                if (gm >= M) continue;
+                const long long idx = c_off + gm * ldc + gn;
+                if (c_vec && gn + 1 < N) {
+                    *reinterpret_cast<float2*>((float*)C + idx) = make_float2(alpha * acc[i][j][hrow * 2], alpha * acc[i][j][hrow * 2 + 1]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (gn + q < N) {
+                            float v = alpha * acc[i][j][hrow * 2 + q];
+                            if (beta != 0.f) v += beta * ld_dt(C, idx + q, dtC);
+                            st_dt(C, idx + q, dtC, v);
+                        }
+                }
+            }
+}
+
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, long long total,
                                                        int c, float slope) {
     long long stride = (long long)gridDim.x * blockDim.x;
@@ -142,6 +298,16 @@ int gim_gemm_strided(const void* A, int dtA, long long sAb, long long sAm, long 
     dim3 grid((m + 63) / 64, (n + 63) / 64, batch);
     gemm_strided_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(A, dtA, sAb, sAm, sAk, B, dtB, sBb, sBk, sBn, C, dtC, sCb, ldc, m, n, k, alpha, beta);
     return check_launch("gemm_strided");
+}
+int gim_gemm_strided_bf16(const void* A, int dtA, long long sAb, long long sAm, long long sAk, const void* B, int dtB, long long sBb, long long sBk,
+                          long long sBn, void* C, int dtC, long long sCb, long long ldc, int m, int n, int k, int batch, float alpha, float beta,
+                          gim_stream_t s) {
+    if (m <= 0 || n <= 0 || batch <= 0) return GIM_OK;
+    GIM_REQUIRE(k >= 0 && batch <= 65535 && (n + TBN - 1) / TBN <= 65535, "gemm_bf16: bad shape");
+    GIM_REQUIRE((dtA == GIM_F32 || dtA == GIM_BF16) && (dtB == GIM_F32 || dtB == GIM_BF16) && (dtC == GIM_F32 || dtC == GIM_BF16), "gemm_bf16: bad dtype");
+    dim3 grid((m + TBM - 1) / TBM, (n + TBN - 1) / TBN, batch);
+    gemm_strided_mma_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(A, dtA, sAb, sAm, sAk, B, dtB, sBb, sBk, sBn, C, dtC, sCb, ldc, m, n, k, alpha, beta);
+    return check_launch("gemm_strided_mma");
 }
 int gim_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int c, float slope, gim_stream_t s) {
     long long total = rows * c;

@@ -853,7 +853,8 @@ def _mm_raw(a, b, ta, tb, out_dtype):
     lda, ldb = a3.shape[2], b3.shape[2]
     sam, sak = (1, lda) if ta else (lda, 1)
     sbk, sbn = (1, ldb) if tb else (ldb, 1)
-    C.call("gim_gemm_strided", C.ptr(a3), C.dtype_code(a3), a3.shape[1] * a3.shape[2], sam, sak,
+    tc = _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT
+    C.call("gim_gemm_strided_bf16" if tc else "gim_gemm_strided", C.ptr(a3), C.dtype_code(a3), a3.shape[1] * a3.shape[2], sam, sak,
            C.ptr(b3), C.dtype_code(b3), b3.shape[1] * b3.shape[2], sbk, sbn,
            C.ptr(out), C.dtype_code(out), m * n, n, m, n, k, bt, 1.0, 0.0)
     return out if batched else out[0]

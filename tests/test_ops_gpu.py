@@ -424,3 +424,25 @@ def test_res_block_down_fused(shape):
         assert rel_err(a, c) < 5e-3, nm                   # fused vs composite differ only by where bf16 roundings of gradients fall
         # gradients pass through two LeakyReLU masks decided on bf16-rounded activations: both bf16 evaluations sit ~1-2 % from float64
         assert rel_err(a, r) < 2.5 * BF16_TOL, nm
+
+
+def test_matmul_tensor_core_path():
+    """bf16 path: the strided batched GEMM on mma.sync with hi+lo split operands (fp32-grade) for every transpose combination and
+    ragged tile edges, including the attention shapes of the O / V nets."""
+    ops = ops_mod()
+    ops.set_precision("bf16")
+    r16 = lambda t: t.float().double()
+    for (bt, m, n, k) in ((3, 70, 33, 17), (2, 64, 64, 32), (5, 64, 256, 64), (2, 256, 16, 256), (1, 130, 100, 200)):
+        for ta in (False, True):
+            for tb in (False, True):
+                a64 = rnd(bt, *((k, m) if ta else (m, k)), seed=1)
+                b64 = rnd(bt, *((n, k) if tb else (k, n)), seed=2)
+                ref = torch.matmul(r16(a64).transpose(1, 2) if ta else r16(a64), r16(b64).transpose(1, 2) if tb else r16(b64))
+                a, b = a64.float().cuda().requires_grad_(), b64.float().cuda().requires_grad_()
+                got = ops.matmul(a, b, ta, tb)
+                assert rel_err(got, ref) < 3e-5, (bt, m, n, k, ta, tb)
+                probe = rnd(*ref.shape, seed=3)
+                gr = torch.autograd.grad((torch.matmul(a64.requires_grad_().transpose(1, 2) if ta else a64.requires_grad_(),
+                                                       b64.requires_grad_().transpose(1, 2) if tb else b64.requires_grad_()) * probe).sum(), (a64, b64))
+                gg = torch.autograd.grad((got * probe.float().cuda()).sum(), (a, b))
+                assert rel_err(gg[0], gr[0]) < 3e-5 and rel_err(gg[1], gr[1]) < 3e-5
