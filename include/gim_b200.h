@@ -77,6 +77,23 @@ int gim_sn_forward(const float* weight_orig, float* u, float* v, int power_iter,
 int gim_sn_backward(const float* g_w_sn, const float* weight_orig, const float* u_used, const float* v_used,
                     const float* sigma, float* g_weight_orig, float* scratch,
                     int cout, int cin, int ksize, gim_stream_t stream);
+/* The same forward for a whole list of convolutions with one launch per phase (<= 16 layers per launch group).  Per layer:
+ * w [co][ci][k][k] weight_orig; u [co], v [ci*k*k] (updated in place when power_iter); w_sn fp32 [k*k][co][ci];
+ * w_op / w_flip: optional bf16 copies of w_sn and of its flipped+transposed pack [k*k][ci][co] (the conv / dgrad operands), NULL to
+ * skip; aux fp32 [co + ci*k*k + 1] = u_used | v_used | sigma; scratch fp32 [ci*k*k + co].  `layers` is a HOST array (copied into
+ * the launch parameters: CUDA-graph safe). */
+typedef struct {
+    const float* w;
+    float* u;
+    float* v;
+    float* w_sn;
+    void* w_op;
+    void* w_flip;
+    float* aux;
+    float* scratch;
+    int cout, cin, ksize, reserved;
+} gim_sn_layer;
+int gim_sn_forward_multi(const gim_sn_layer* layers, int n_layers, int power_iter, float eps, gim_stream_t stream);
 
 /* ---- pointwise / resampling (model_blocks.py:489-490, 740, 744; gim_img_models.py:215) ---- */
 int gim_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, gim_stream_t stream);

@@ -29,6 +29,7 @@ PROTOTYPES = {
     "gim_colsum": "pplii" + "p",
     "gim_sn_forward": "pppifpppppiiip",
     "gim_sn_backward": "pppppppiiip",
+    "gim_sn_forward_multi": "piifp",
     "gim_lrelu_fwd": "pplfip",
     "gim_lrelu_bwd": "ppplfip",
     "gim_tanh_fwd": "pplip",
@@ -72,6 +73,14 @@ PROTOTYPES = {
     "gim_adam_multi": "pilppfff" + "fp",
 }
 OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_launch_count")
+
+
+
+class SnLayer(ctypes.Structure):
+    """gim_sn_layer of include/gim_b200.h."""
+    _fields_ = [("w", _P), ("u", _P), ("v", _P), ("w_sn", _P), ("w_op", _P), ("w_flip", _P), ("aux", _P), ("scratch", _P),
+                ("cout", _I), ("cin", _I), ("ksize", _I), ("reserved", _I)]
+
 
 _lib = None
 

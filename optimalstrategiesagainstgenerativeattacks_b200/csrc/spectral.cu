@@ -125,6 +125,110 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restri
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Multi-layer variants: ONE launch per phase for up to kSnChunk convolutions (blockIdx.y = layer; the layer table travels as a
+// by-value kernel parameter, so the launches are CUDA-graph safe), instead of eight tiny launches per layer.  The last phase also
+// writes the bf16 conv operand and its flipped/transposed twin (the dgrad operand), replacing the per-call cast / flip kernels.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kSnChunk = 16;
+struct SnChunk {
+    gim_sn_layer l[kSnChunk];
+    int n;
+};
+
+// t[j] = sum_co W[co][j] * u[co]; one CTA per 32 columns walks all rows (no atomics, no memset)
+__global__ void __launch_bounds__(256) sn_wtu_multi_kernel(const __grid_constant__ SnChunk c) {
+    const gim_sn_layer& L = c.l[blockIdx.y];
+    const int J = L.cin * L.ksize * L.ksize;
+    if ((int)blockIdx.x * 32 >= J) return;
+    __shared__ float sh[8][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (j < J)
+        for (int co = threadIdx.y; co < L.cout; co += 8) acc = fmaf(L.w[(long long)co * J + j], L.u[co], acc);
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < J) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a += sh[q][threadIdx.x];
+        L.scratch[j] = a;
+    }
+}
+__global__ void __launch_bounds__(1024) sn_vnorm_multi_kernel(const __grid_constant__ SnChunk c, float eps, int power_iter) {
+    const gim_sn_layer& L = c.l[blockIdx.x];
+    const int J = L.cin * L.ksize * L.ksize;
+    __shared__ float sh[33];
+    float* v_used = L.aux + L.cout;
+    if (power_iter) {
+        const float* t = L.scratch;
+        float acc = 0.f;
+        for (int j = threadIdx.x; j < J; j += blockDim.x) acc += t[j] * t[j];
+        const float inv = 1.f / fmaxf(sqrtf(block_sum(acc, sh)), eps);
+        for (int j = threadIdx.x; j < J; j += blockDim.x) {
+            const float val = t[j] * inv;
+            L.v[j] = val;
+            v_used[j] = val;
+        }
+    } else {
+        for (int j = threadIdx.x; j < J; j += blockDim.x) v_used[j] = L.v[j];
+    }
+}
+__global__ void __launch_bounds__(128) sn_wv_multi_kernel(const __grid_constant__ SnChunk c) {
+    const gim_sn_layer& L = c.l[blockIdx.y];
+    if ((int)blockIdx.x >= L.cout) return;
+    const int J = L.cin * L.ksize * L.ksize;
+    __shared__ float sh[33];
+    const float* row = L.w + (long long)blockIdx.x * J;
+    const float* v = L.aux + L.cout;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) acc = fmaf(row[j], v[j], acc);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) L.scratch[J + blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(512) sn_unorm_multi_kernel(const __grid_constant__ SnChunk c, float eps, int power_iter) {
+    const gim_sn_layer& L = c.l[blockIdx.x];
+    const int J = L.cin * L.ksize * L.ksize;
+    __shared__ float sh[33];
+    const float* s = L.scratch + J;
+    float inv = 0.f;
+    if (power_iter) {
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < L.cout; i += blockDim.x) acc += s[i] * s[i];
+        inv = 1.f / fmaxf(sqrtf(block_sum(acc, sh)), eps);
+    }
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < L.cout; i += blockDim.x) {
+        const float ui = power_iter ? s[i] * inv : L.u[i];
+        if (power_iter) L.u[i] = ui;
+        L.aux[i] = ui;
+        dot += ui * s[i];
+    }
+    dot = block_sum(dot, sh);
+    if (threadIdx.x == 0) L.aux[L.cout + J] = dot;
+}
+// w_sn[t][co][ci] = W[co][ci][t] / sigma (fp32), the same as bf16, and the flipped/transposed bf16 pack [T-1-t][ci][co]
+__global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constant__ SnChunk c) {
+    const gim_sn_layer& L = c.l[blockIdx.y];
+    const int taps = L.ksize * L.ksize, J = L.cin * taps;
+    const float inv = 1.f / L.aux[L.cout + J];
+    const long long total = (long long)taps * L.cout * L.cin;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    bf16* wop = (bf16*)L.w_op;
+    bf16* wfl = (bf16*)L.w_flip;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int ci = (int)(i % L.cin);
+        const long long r = i / L.cin;
+        const int co = (int)(r % L.cout);
+        const int t = (int)(r / L.cout);
+        const float v = L.w[((long long)co * L.cin + ci) * taps + t] * inv;
+        L.w_sn[i] = v;
+        if (wop) wop[i] = __float2bfloat16_rn(v);
+        if (wfl) wfl[((long long)(taps - 1 - t) * L.cin + ci) * L.cout + co] = __float2bfloat16_rn(v);
+    }
+}
+
 }  // namespace gim
 
 using namespace gim;
@@ -173,6 +277,39 @@ int gim_sn_backward(const float* g_w_sn, const float* weight_orig, const float* 
     if (rc != GIM_OK) return rc;
     sn_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, st>>>(g_w_sn, u_used, v_used, sigma, scratch, g_weight_orig, cout, cin, taps);
     return check_launch("sn_bwd_apply");
+}
+
+int gim_sn_forward_multi(const gim_sn_layer* layers, int n_layers, int power_iter, float eps, gim_stream_t s) {
+    GIM_REQUIRE(n_layers >= 0 && (n_layers == 0 || layers), "sn_forward_multi: bad arguments");
+    cudaStream_t st = (cudaStream_t)s;
+    for (int base = 0; base < n_layers; base += kSnChunk) {
+        SnChunk c;
+        c.n = n_layers - base < kSnChunk ? n_layers - base : kSnChunk;
+        int max_j = 0, max_co = 0;
+        for (int i = 0; i < c.n; ++i) {
+            c.l[i] = layers[base + i];
+            GIM_REQUIRE(c.l[i].cout > 0 && c.l[i].cin > 0 && c.l[i].ksize > 0 && c.l[i].w && c.l[i].u && c.l[i].v && c.l[i].w_sn && c.l[i].aux && c.l[i].scratch,
+                        "sn_forward_multi: bad layer");
+            int j = c.l[i].cin * c.l[i].ksize * c.l[i].ksize;
+            if (j > max_j) max_j = j;
+            if (c.l[i].cout > max_co) max_co = c.l[i].cout;
+        }
+        for (int i = c.n; i < kSnChunk; ++i) c.l[i] = c.l[0];
+        int rc;
+        if (power_iter) {
+            sn_wtu_multi_kernel<<<dim3((max_j + 31) / 32, c.n), dim3(32, 8), 0, st>>>(c);
+            if ((rc = check_launch("sn_wtu_multi")) != GIM_OK) return rc;
+        }
+        sn_vnorm_multi_kernel<<<c.n, 1024, 0, st>>>(c, eps, power_iter);
+        if ((rc = check_launch("sn_vnorm_multi")) != GIM_OK) return rc;
+        sn_wv_multi_kernel<<<dim3(max_co, c.n), 128, 0, st>>>(c);
+        if ((rc = check_launch("sn_wv_multi")) != GIM_OK) return rc;
+        sn_unorm_multi_kernel<<<c.n, 512, 0, st>>>(c, eps, power_iter);
+        if ((rc = check_launch("sn_unorm_multi")) != GIM_OK) return rc;
+        sn_pack_multi_kernel<<<dim3(2 * num_sms() / c.n + 1, c.n), 256, 0, st>>>(c);
+        if ((rc = check_launch("sn_pack_multi")) != GIM_OK) return rc;
+    }
+    return GIM_OK;
 }
 
 }  // extern "C"

@@ -48,6 +48,7 @@ class Encoder(nn.Module):
 
     def forward(self, x):
         x = _as_nhwc(x)
+        mb.sn_prepare_module(self, skip=() if self.att_loc < self.n_down_blocks else (self.att,))
         for i in range(self.n_down_blocks):
             if i == self.att_loc:
                 x = self.att(x)
@@ -85,6 +86,7 @@ class EnvDecoder(nn.Module):
         x = x.reshape(n, 1, 1, c)
         if x.dtype != ops.act_dtype():
             x = ops.to_nhwc(x.reshape(n, c, 1, 1))
+        mb.sn_prepare_module(self, skip=() if self.att_loc < self.n_up_blocks else (self.att,))
         for i in range(self.n_up_blocks):
             if i == self.att_loc:
                 x = self.att(x)
@@ -191,6 +193,8 @@ class AdaInImage2Image(nn.Module):
 
     def forward(self, x, style):
         x = _as_nhwc(x)
+        skip = [m.att for m in (self.down_block, self.adain_up_block) if not m.att_loc < len(getattr(m, 'down_blocks', getattr(m, 'up_blocks', ())))]
+        mb.sn_prepare_module(self, skip=skip)
         x = self.down_block(x)
         x = self.adain_res_block(x=x, style=style)
         x = self.adain_up_block(x=x, style=style)

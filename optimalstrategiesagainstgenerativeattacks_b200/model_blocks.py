@@ -97,14 +97,31 @@ class SNConv2d(nn.Module):
         v = F.normalize(w.new_empty(width).normal_(0, 1), dim=0, eps=SN_EPS)
         self.register_buffer('weight_u', u)
         self.register_buffer('weight_v', v)
+        self._prepared = None
 
     def effective_weight(self):
-        """Packed fp32 [k*k, cout, cin] weight W/sigma; runs the power iteration when self.training."""
+        """Packed fp32 [k*k, cout, cin] weight W/sigma; runs the power iteration when self.training (unless sn_prepare_module already
+        did it for this call as part of a batched pass)."""
+        prep, self._prepared = self._prepared, None
+        if prep is not None and prep[4] == self.weight_orig._version:       # (a result left over from an aborted forward is dropped)
+            return ops.sn_prepared_weight(self.weight_orig, prep)
         return ops.SpectralNormFn.apply(self.weight_orig, (self.weight_u, self.weight_v), self.training, SN_EPS)
 
     def forward(self, x, pre=ops.PRE_NONE, slope=0.2):
         """`pre`: operator folded in front of the conv (ops.PRE_LRELU: LeakyReLU(slope); ops.PRE_UPSAMPLE: nearest x2)."""
         return ops.Conv2dFn.apply(x, self.effective_weight(), self.bias, self.kernel_size, pre, slope)
+
+
+def sn_prepare_module(module, skip=()):
+    """Batched spectral norm for every SNConv2d under `module` that its forward is about to call exactly once (reference semantics:
+    one power iteration per forward call of each conv, torch.nn.utils.spectral_norm).  `skip`: sub-modules whose convs do not run."""
+    skipped = set()
+    for sm in skip:
+        skipped.update(id(m) for m in sm.modules())
+    convs = [m for m in module.modules() if isinstance(m, SNConv2d) and id(m) not in skipped]
+    if convs:
+        ops.sn_prepare(convs, module.training, SN_EPS)
+
 
 
 class InstanceNormAffine(nn.Module):

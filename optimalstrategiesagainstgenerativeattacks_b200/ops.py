@@ -117,10 +117,17 @@ def _operand(t):
 # ------------------------------------------------------------------------------------------------------------
 # convolution triple
 # ------------------------------------------------------------------------------------------------------------
+_wops = {}          # id(packed fp32 weight) -> (weakref, bf16 copy, flipped bf16 copy) written by the batched spectral-norm pass
+
+
 def _weight_as(w32, dtype, flip):
     taps, co, ci = w32.shape
     if not flip and dtype == torch.float32:
         return w32
+    if dtype == torch.bfloat16:
+        hit = _wops.get(id(w32))
+        if hit is not None and hit[0]() is w32:
+            return hit[2] if flip else hit[1]
     out = _empty((taps, ci, co) if flip else (taps, co, ci), dtype, w32)
     C.call("gim_weight_flip" if flip else "gim_weight_cast", C.ptr(w32), C.ptr(out), taps, co, ci, C.dtype_code(out))
     return out
@@ -544,6 +551,74 @@ class SpectralNormFn(Function):
         C.call("gim_sn_backward", C.ptr(g), C.ptr(w), aux[:co].data_ptr(), aux[co:co + j].data_ptr(), aux[co + j:].data_ptr(),
                C.ptr(gw), C.ptr(scratch), co, ci, k)
         return gw, None, None, None
+
+
+def sn_prepare(convs, training, eps):
+    """Spectral normalisation of a whole list of SNConv2d modules with one launch per phase (gim_sn_forward_multi) instead of eight
+    launches per convolution: power iteration on (u, v) in place when training, W/sigma packed [k*k, co, ci] in fp32 plus -- on the
+    bf16 path -- the bf16 operand and its flipped/transposed twin for the input-gradient convolution.  Each module keeps its result
+    until its next effective_weight() call, which wraps it in the per-layer autograd node."""
+    if not convs:
+        return
+    dev = convs[0].weight_orig.device
+    bf = _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT
+    n32 = nbf = 0
+    plan = []
+    for m in convs:
+        co, ci, k = m.out_channels, m.in_channels, m.kernel_size
+        tot, j = co * ci * k * k, ci * k * k
+        o_sn, o_aux, o_scr = n32, n32 + _round_up(tot, 4), n32 + _round_up(tot, 4) + _round_up(co + j + 1, 4)
+        n32 = o_scr + _round_up(j + co, 4)
+        o_op, o_fl = nbf, nbf + _round_up(tot, 8)
+        nbf = o_fl + _round_up(tot, 8)
+        plan.append((m, co, ci, k, tot, j, o_sn, o_aux, o_scr, o_op, o_fl))
+    f32 = torch.empty(n32, dtype=torch.float32, device=dev)
+    b16 = torch.empty(nbf, dtype=torch.bfloat16, device=dev) if bf else None
+    table = (C.SnLayer * len(plan))()
+    for i, (m, co, ci, k, tot, j, o_sn, o_aux, o_scr, o_op, o_fl) in enumerate(plan):
+        w = m.weight_orig
+        if not w.is_contiguous():
+            raise RuntimeError("sn_prepare: weight_orig must be contiguous")
+        w_sn = f32[o_sn:o_sn + tot].view(k * k, co, ci)
+        aux = f32[o_aux:o_aux + co + j + 1]
+        w_op = b16[o_op:o_op + tot].view(k * k, co, ci) if bf else None
+        w_fl = b16[o_fl:o_fl + tot].view(k * k, ci, co) if bf else None
+        e = table[i]
+        e.w, e.u, e.v = w.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr()
+        e.w_sn, e.aux, e.scratch = w_sn.data_ptr(), aux.data_ptr(), f32[o_scr:].data_ptr()
+        e.w_op = w_op.data_ptr() if bf else None
+        e.w_flip = w_fl.data_ptr() if bf else None
+        e.cout, e.cin, e.ksize, e.reserved = co, ci, k, 0
+        m._prepared = (w_sn, aux, w_op, w_fl, w._version)
+    import ctypes
+    C.call("gim_sn_forward_multi", ctypes.cast(table, ctypes.c_void_p), len(plan), 1 if training else 0, eps)
+
+
+class SpectralNormPreparedFn(Function):
+    """The per-layer autograd node over a weight that sn_prepare already normalised (same backward as SpectralNormFn)."""
+
+    @staticmethod
+    def forward(ctx, weight_orig, prepared):
+        w_sn, aux = prepared[0], prepared[1]
+        co, ci, k, _ = weight_orig.shape
+        ctx.save_for_backward(weight_orig, aux)
+        ctx.dims = (co, ci, k)
+        return w_sn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return SpectralNormFn.backward(ctx, g)[0], None
+
+
+def sn_prepared_weight(weight_orig, prepared):
+    w = SpectralNormPreparedFn.apply(weight_orig, prepared)
+    if prepared[2] is not None:
+        if len(_wops) > 256:
+            for key in [k for k, v in _wops.items() if v[0]() is None]:
+                del _wops[key]
+        _wops[id(w)] = (weakref.ref(w), prepared[2], prepared[3])
+    return w
 
 
 # ------------------------------------------------------------------------------------------------------------
