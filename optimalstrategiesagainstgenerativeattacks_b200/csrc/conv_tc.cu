@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
 //   rotating staging buffers) runs while the MMA warp already accumulates tile i+1; the TMA/MMA smem ring never drains between
 //   tiles.  Fused epilogues: + bias, LeakyReLU, LeakyReLU-backward mask taken from a saved bf16 operand, fp32 or bf16 output.
 // ----------------------------------------------------------------------------------------------------------------
-enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4 };
+enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4, kEpiPool = 8 };
 constexpr int kStagingBytes = 2 * kBlockM * 128;          // two 16 KB boxes (128 rows x 128 B)
 
 // A macro tile = m_sub (1 or 2) consecutive 128-pixel tiles x one block_n-wide channel tile.  With m_sub = 2 the two pixel tiles
@@ -487,6 +487,35 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
 #pragma unroll
                             for (int j = 0; j < 16; ++j) { f[j] = __uint_as_float(lo[j]); f[16 + j] = __uint_as_float(hi[j]); }
                         }
+                        if (p.epi & kEpiPool) {
+                            // AvgPool2d(2) inside the epilogue: the pixel box is at most 16 wide, so the 2x2 window of a pixel lives in
+                            // lanes m^1 (w) and m^bw (h) of the same warp.  After the two butterflies each of the four lanes of a window
+                            // holds the window sum of all 32 columns and writes its own quarter (8 columns) of the pooled row.
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                f[j] += __shfl_xor_sync(0xffffffffu, f[j], 1);
+                                f[j] += __shfl_xor_sync(0xffffffffu, f[j], p.bw);
+                            }
+                            const int sub4 = (lw & 1) | ((lh & 1) << 1);
+                            float o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float v01 = (sub4 & 1) ? f[8 + e] : f[e], v23 = (sub4 & 1) ? f[24 + e] : f[16 + e];
+                                o[e] = 0.25f * ((sub4 & 2) ? v23 : v01) + bias_sm[cb + 8 * sub4 + e];
+                            }
+                            if ((p.epi & kEpiAdd) && valid && n0 + cb < p.cout) {
+                                const long long ppix = ((long long)img * (p.h >> 1) + (hh >> 1)) * (p.w >> 1) + (ww >> 1);
+                                const float4* ad = reinterpret_cast<const float4*>(addend + ppix * p.cout + n0 + cb + 8 * sub4);
+                                const float4 t0 = ad[0], t1 = ad[1];
+                                o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w;
+                                o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
+                            }
+                            const int pm = ((ln * (p.bh >> 1) + (lh >> 1)) * (p.bw >> 1)) + (lw >> 1);       // pooled row inside the box: 0..31
+                            uint8_t* prow = staging + (chunk & 1) * (kBlockM * 128) + pm * 128;
+                            *reinterpret_cast<float4*>(prow + (((2 * sub4) ^ (pm & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(prow + (((2 * sub4 + 1) ^ (pm & 7)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
+                            break;                                   // fp32 output: one 32-column group per chunk
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] += bias_sm[cb + j];
                         if (p.epi & kEpiLrelu) {
@@ -547,7 +576,10 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
                     if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // previous box has left smem
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (store_thread) {
-                        if (n0 + c0 < p.cout) tma_store_4d(&map_y, staging + (chunk & 1) * (kBlockM * 128), n0 + c0, w0, h0, img0);
+                        if (n0 + c0 < p.cout) {
+                            if (p.epi & kEpiPool) tma_store_4d(&map_y, staging + (chunk & 1) * (kBlockM * 128), n0 + c0, w0 >> 1, h0 >> 1, img0);
+                            else tma_store_4d(&map_y, staging + (chunk & 1) * (kBlockM * 128), n0 + c0, w0, h0, img0);
+                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -671,6 +703,13 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     ConvTcParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
     pixel_box(h, wd, p.bw, p.bh, p.bn);
+    if (epi & kEpiPool) {
+        if ((h & 1) || (wd & 1) || !out_f32 || (epi & (kEpiLrelu | kEpiMask)) || cout % 32 != 0)
+            return fail(GIM_E_ARG, "conv_fwd_tc: the pooling epilogue needs even h and w, fp32 output, cout % 32 == 0 and no activation epilogue");
+        p.bw = next_pow2(wd) < 16 ? next_pow2(wd) : 16;            // both pooling partners inside one warp
+        p.bh = next_pow2(h) < kBlockM / p.bw ? next_pow2(h) : kBlockM / p.bw;
+        p.bn = kBlockM / (p.bw * p.bh);
+    }
     p.tiles_w = (wd + p.bw - 1) / p.bw;
     p.tiles_h = (h + p.bh - 1) / p.bh;
     p.tiles_n = (n + p.bn - 1) / p.bn;
@@ -694,7 +733,9 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;
     if (force_msub == 1 || (force_msub == 2 && v2 && p.block_n <= 128)) p.m_sub = force_msub;
     const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2 + 1023) & ~1023;
-    if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
+    if (epi & kEpiPool) {
+        if (!make_out_map(&map_y, y, n, h / 2, wd / 2, cout, p.bw / 2, p.bh / 2, p.bn, 1)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(pooled y) failed");
+    } else if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
     if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn, p.block_k)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
     if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.block_n, p.block_k))
         return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");

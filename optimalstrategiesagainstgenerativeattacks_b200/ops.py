@@ -388,7 +388,7 @@ class RowBroadcastFn(Function):
 # ------------------------------------------------------------------------------------------------------------
 # block-level fused operators (bf16 tensor-core path, first order)
 # ------------------------------------------------------------------------------------------------------------
-EPI_LRELU, EPI_MASK, EPI_ADD = 1, 2, 4
+EPI_LRELU, EPI_MASK, EPI_ADD, EPI_POOL = 1, 2, 4, 8
 
 
 class Act:
@@ -453,14 +453,27 @@ class ResBlockDownFn(Function):
             k1 = 1
         else:
             xa, wl_e, xr, w1_e, k1 = xb, wl_t, xl, w1_t, ks
-        res = _conv_tc_fused(xa, wl_e, bl, 1, torch.float32)
-        tl = _conv_tc_fused(xr, w1_e, b1, k1, od, EPI_LRELU, slope)
-        o = _conv_tc_fused(tl, w2_t, b2, ks, torch.float32)
-        co = o.shape[-1]
-        y32 = _empty((n, h // 2, w // 2, co), torch.float32, o)
-        yb = torch.empty_like(y32, dtype=od) if want_ops else None
-        yl = torch.empty_like(y32, dtype=od) if want_ops else None
-        C.call("gim_pool2_multi", C.ptr(res), C.ptr(o), C.ptr(y32), C.ptr(yb), C.ptr(yl), n, h, w, co, 0.25, slope)
+        co = w2_t.shape[1]
+        od_out = (n, h // 2, w // 2, co)
+        if h % 2 == 0 and w % 2 == 0:
+            # AvgPool inside the conv epilogues: neither full-resolution fp32 tensor reaches HBM
+            y32 = _conv_tc_fused(xa, wl_e, bl, 1, torch.float32, EPI_POOL, out=_empty(od_out, torch.float32, xa))
+            tl = _conv_tc_fused(xr, w1_e, b1, k1, od, EPI_LRELU, slope)
+            _conv_tc_fused(tl, w2_t, b2, ks, torch.float32, EPI_POOL | EPI_ADD, addend=y32, out=y32)
+            yb = yl = None
+            if want_ops:
+                yb = torch.empty_like(y32, dtype=od)
+                yl = torch.empty_like(y32, dtype=od)
+                C.call("gim_cast", C.ptr(y32), C.F32, C.ptr(yb), C.BF16, y32.numel())
+                C.call("gim_operand_prepare", C.ptr(y32), C.F32, C.ptr(yl), C.BF16, n, h // 2, w // 2, co, PRE_LRELU, slope)
+        else:
+            res = _conv_tc_fused(xa, wl_e, bl, 1, torch.float32)
+            tl = _conv_tc_fused(xr, w1_e, b1, k1, od, EPI_LRELU, slope)
+            o = _conv_tc_fused(tl, w2_t, b2, ks, torch.float32)
+            y32 = _empty(od_out, torch.float32, o)
+            yb = torch.empty_like(y32, dtype=od) if want_ops else None
+            yl = torch.empty_like(y32, dtype=od) if want_ops else None
+            C.call("gim_pool2_multi", C.ptr(res), C.ptr(o), C.ptr(y32), C.ptr(yb), C.ptr(yl), n, h, w, co, 0.25, slope)
         ctx.cfg = (ks, slope, skinny, (n, h, w, ci, co), want_ops)
         ctx.save_for_backward(xa, xr, xl, tl, wl, w1, w2)
         if want_ops:
