@@ -133,6 +133,8 @@ struct ConvTcParams {
     int block_k;                                 // K elements per stage: 64 (128-byte rows, SWIZZLE_128B) or 16 (32-byte rows, SWIZZLE_32B)
     int epi;                                     // fused epilogue bits (persistent kernel): kEpiLrelu, kEpiMask
     int m_sub;                                   // pixel tiles per macro tile (persistent kernel): 1 or 2
+    int n_staging;                               // output staging boxes of the epilogue ring (persistent kernel): 2..4
+    int debug;                                   // GIM_CONV_DEBUG bits (profiling experiments only): 1 no TMA store, 2 no proxy fence, 4 no smem staging
     float slope;
 };
 
@@ -321,13 +323,13 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
 //   tiles.  Fused epilogues: + bias, LeakyReLU, LeakyReLU-backward mask taken from a saved bf16 operand, fp32 or bf16 output.
 // ----------------------------------------------------------------------------------------------------------------
 enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4, kEpiPool = 8 };
-constexpr int kStagingBytes = 2 * kBlockM * 128;          // two 16 KB boxes (128 rows x 128 B)
+constexpr int kBoxBytes = kBlockM * 128;                   // one staged output box: 128 rows x 128 B
 
 // A macro tile = m_sub (1 or 2) consecutive 128-pixel tiles x one block_n-wide channel tile.  With m_sub = 2 the two pixel tiles
 // share every weight box and their MMAs alternate between two independent accumulators (measured: a single dependent
 // accumulation chain of N=128 MMAs tops out near 1.0 PFLOP/s, two interleaved chains or N=256 reach 1.3).
 template <int kDummy>
-__global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+__global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                                               const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias,
                                                               const bf16* __restrict__ mask_ref, const float* addend, void* __restrict__ y,
                                                               const ConvTcParams p) {
@@ -337,8 +339,8 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
     const int b_off = p.m_sub * a_bytes;
     const int stage_bytes = (b_off + p.block_n * p.block_k * 2 + 1023) & ~1023;
     uint8_t* staging = smem + p.stages * stage_bytes;
-    float* bias_sm = (float*)(staging + kStagingBytes);                       // 256 floats
-    uint64_t* full_bar = (uint64_t*)(bias_sm + 256);
+    float* bias_all = (float*)(staging + 2 * p.n_staging * kBoxBytes);        // 256 floats per epilogue group
+    uint64_t* full_bar = (uint64_t*)(bias_all + 512);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* tmem_full_bar = empty_bar + p.stages;                            // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;                              // [2]
@@ -358,8 +360,8 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_y);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // two producers: A (warp 0), B (warp 6)
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // two producers: A (warp 0), B (warp 2)
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -368,8 +370,8 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 || warp == 6) {
-        // two TMA producers share the ring: warp 0 streams the activation boxes (A), warp 6 the weight boxes (B); each arms the
+    if (warp == 0 || warp == 2) {
+        // two TMA producers share the ring: warp 0 streams the activation boxes (A), warp 2 the weight boxes (B); each arms the
         // full barrier with its own byte count
         if (lane == 0) {
             const bool is_a = warp == 0;
@@ -444,23 +446,34 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
                 umma_commit(&tmem_full_bar[buf]);
             }
         }
-    } else {
-        // ---- epilogue warps (128 threads): TMEM -> registers -> fused pointwise -> swizzled smem -> TMA store ----
+    } else if (warp >= 4) {
+        // ---- epilogue: two groups of four warps (warps 4-7 and 8-11; warp & 3 = TMEM lane quarter) take alternate 16 KB chunks of
+        // every tile: TMEM -> registers -> fused pointwise -> swizzled smem -> TMA store.  A lone warp per scheduler is latency bound
+        // (tcgen05.ld, barrier, dependent ALU chains); the second group doubles the drain rate of the accumulators.
         const int quarter = warp & 3;
+        const int grp = (warp - 4) >> 2;
         const int m = quarter * 32 + lane;
-        const int et = threadIdx.x - 64;                 // 0..127
+        const int et = threadIdx.x - 128 - grp * 128;    // 0..127 inside the group
+        float* bias_sm = bias_all + grp * 256;
+        staging += grp * p.n_staging * kBoxBytes;
+        const int bar_id = 1 + grp;
+        uint32_t chunk_ctr = 0;                          // running chunk index (identical in both groups): parity selects the owner
+        int bias_n0 = -1;
         const int lw = m % p.bw, lh = (m / p.bw) % p.bh, ln = m / (p.bw * p.bh);
         const bool store_thread = (et == 0);
         const int cols_per_chunk = p.out_f32 ? 32 : 64;
-        uint32_t i = 0, chunk = 0;
+        uint32_t i = 0;
+        int sbuf = 0;                                    // staging box of the current chunk (ring of p.n_staging)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
             const int mt = tile / n_tiles;
             const int n0 = (tile - mt * n_tiles) * p.block_n;
             const uint32_t buf = i & 1;
-            // bias tile -> smem (all readers of the previous tile's values are past their last chunk barrier)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int c = et; c < p.block_n; c += 128) bias_sm[c] = (bias && n0 + c < p.cout) ? __ldg(&bias[n0 + c]) : 0.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (n0 != bias_n0) {                         // bias tile -> smem, only when the channel tile changes
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                for (int c = et; c < p.block_n; c += 128) bias_sm[c] = (bias && n0 + c < p.cout) ? __ldg(&bias[n0 + c]) : 0.f;
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                bias_n0 = n0;
+            }
             mbar_wait(&tmem_full_bar[buf], (i >> 1) & 1);
             tc_fence_after();
             for (int sub = 0; sub < p.m_sub; ++sub) {
@@ -472,9 +485,9 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
                 const bool valid = ww < p.w && hh < p.h && img < p.n;
                 const long long pix = ((long long)img * p.h + hh) * p.w + ww;
                 const uint32_t tmem_acc = tmem_base + buf * buf_cols + (uint32_t)(sub * p.block_n) + ((uint32_t)(quarter * 32) << 16);
-                const bool last_sub = sub == p.m_sub - 1;
-                for (int c0 = 0; c0 < p.block_n; c0 += cols_per_chunk, ++chunk) {
-                    uint8_t* box = staging + (chunk & 1) * (kBlockM * 128) + m * 128;
+                for (int c0 = 0; c0 < p.block_n; c0 += cols_per_chunk) {
+                    if (((chunk_ctr++) & 1) != (uint32_t)grp) continue;
+                    uint8_t* box = staging + sbuf * kBoxBytes + m * 128;
 #pragma unroll 1
                     for (int h32 = 0; h32 < cols_per_chunk; h32 += 32) {
                         const int cb = c0 + h32;
@@ -511,7 +524,7 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
                                 o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
                             }
                             const int pm = ((ln * (p.bh >> 1) + (lh >> 1)) * (p.bw >> 1)) + (lw >> 1);       // pooled row inside the box: 0..31
-                            uint8_t* prow = staging + (chunk & 1) * (kBlockM * 128) + pm * 128;
+                            uint8_t* prow = staging + sbuf * kBoxBytes + pm * 128;
                             *reinterpret_cast<float4*>(prow + (((2 * sub4) ^ (pm & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                             *reinterpret_cast<float4*>(prow + (((2 * sub4 + 1) ^ (pm & 7)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
                             break;                                   // fp32 output: one 32-column group per chunk
@@ -545,7 +558,9 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
                                 }
                             }
                         }
-                        if (p.out_f32) {
+                        if (p.debug & 4) {
+                            if (f[0] == 123.456f) box[0] = 1;
+                        } else if (p.out_f32) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 *reinterpret_cast<float4*>(box + ((j ^ (m & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -567,23 +582,29 @@ __global__ void __launch_bounds__(224, 1) conv_fwd_tc2_kernel(const __grid_const
                         }
                         if (cb + 32 >= p.block_n) break;             // block_n == 32 with bf16 output: half a box
                     }
-                    if (last_sub && c0 + cols_per_chunk >= p.block_n) {      // all TMEM reads of this macro tile are done: hand the buffer back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[buf])) : "memory");
-                    }
-                    fence_proxy_async();
-                    if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // previous box has left smem
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (!(p.debug & 2)) fence_proxy_async();
                     if (store_thread) {
+                        // With NB staging boxes the box written next was last read by the store issued NB-1 chunks ago: all but the
+                        // newest NB-2 stores must have left smem before anyone passes the barrier below.
+                        if (p.n_staging == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        else if (p.n_staging == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (store_thread && !(p.debug & 1)) {
                         if (n0 + c0 < p.cout) {
-                            if (p.epi & kEpiPool) tma_store_4d(&map_y, staging + (chunk & 1) * (kBlockM * 128), n0 + c0, w0 >> 1, h0 >> 1, img0);
-                            else tma_store_4d(&map_y, staging + (chunk & 1) * (kBlockM * 128), n0 + c0, w0, h0, img0);
+                            if (p.epi & kEpiPool) tma_store_4d(&map_y, staging + sbuf * kBoxBytes, n0 + c0, w0 >> 1, h0 >> 1, img0);
+                            else tma_store_4d(&map_y, staging + sbuf * kBoxBytes, n0 + c0, w0, h0, img0);
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    if (++sbuf == p.n_staging) sbuf = 0;
                 }
             }
+            // every TMEM read of this macro tile by this warp has completed (wait::ld): hand the accumulator buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[buf])) : "memory");
         }
         if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -740,9 +761,13 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.block_n, p.block_k))
         return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
     if (v2) {
-        const int fixed = kStagingBytes + 256 * (int)sizeof(float) + 64 * (int)sizeof(uint64_t) + 1024;
+        static const int env_nb = env_int("GIM_CONV_NSTAGING", 0), env_stages = env_int("GIM_CONV_STAGES", 0);
+        p.debug = env_int("GIM_CONV_DEBUG", 0);
+        p.n_staging = env_nb >= 2 && env_nb <= 4 ? env_nb : 2;
+        const int fixed = 2 * p.n_staging * kBoxBytes + 512 * (int)sizeof(float) + 64 * (int)sizeof(uint64_t) + 1024;
         int stages = (227 * 1024 - fixed) / stage_bytes;
         if (stages > 8) stages = 8;
+        if (env_stages >= 2 && env_stages < stages) stages = env_stages;
         p.stages = stages;
         p.tma_store = 1;
         const size_t smem = (size_t)stages * stage_bytes + fixed;
@@ -754,7 +779,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
         }
         const long long total = ((m_tiles + p.m_sub - 1) / p.m_sub) * ((cout + p.block_n - 1) / p.block_n);
         const int grid = (int)(total < num_sms() ? total : num_sms());
-        conv_fwd_tc2_kernel<0><<<grid, 224, smem, st>>>(map_x, map_w, map_y, bias, (const bf16*)mask_ref, addend, y, p);
+        conv_fwd_tc2_kernel<0><<<grid, 384, smem, st>>>(map_x, map_w, map_y, bias, (const bf16*)mask_ref, addend, y, p);
         return check_launch("conv_fwd_tc2");
     }
     // two CTAs per SM (<= ~110 KB each): one CTA's epilogue overlaps the other's MMA main loop

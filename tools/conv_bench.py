@@ -27,6 +27,8 @@ SHAPES = [
     (64, 64, 64, 64, 3),
     (16, 16, 128, 256, 1),
     (1, 1, 512, 512, 1),
+    (32, 32, 8, 128, 1),
+    (8, 8, 256, 256, 1),
 ]
 
 
@@ -87,7 +89,7 @@ def main():
             ref_t = torch.randn((n, h, w, co), device=dev).to(torch.bfloat16)
 
             def fused(i):
-                C.call("gim_conv2d_fwd_fused", C.ptr(xs[i % pool]), C.ptr(wt), C.ptr(bias), C.ptr(yb), None, n, h, w, ci, co, k, C.BF16, 1, 0.2)
+                C.call("gim_conv2d_fwd_fused", C.ptr(xs[i % pool]), C.ptr(wt), C.ptr(bias), C.ptr(yb), None, None, n, h, w, ci, co, k, C.BF16, 1, 0.2)
             for i in range(3):
                 fused(i)
             torch.cuda.synchronize()
@@ -105,10 +107,10 @@ def main():
                 fused(0)
                 want = torch.nn.functional.leaky_relu(ref, 0.2)
                 err = float((yb[:nn_].float() - want).norm() / want.norm())
-                C.call("gim_conv2d_fwd_fused", C.ptr(xs[0]), C.ptr(wt), None, C.ptr(yf), C.ptr(ref_t), n, h, w, ci, co, k, C.F32, 2, 0.2)
+                C.call("gim_conv2d_fwd_fused", C.ptr(xs[0]), C.ptr(wt), None, C.ptr(yf), C.ptr(ref_t), None, n, h, w, ci, co, k, C.F32, 2, 0.2)
                 want2 = (ref - bias) * torch.where(ref_t[:nn_].float() > 0, 1.0, 0.2)
                 err2 = float((yf[:nn_] - want2).norm() / want2.norm())
-                C.call("gim_conv2d_fwd_fused", C.ptr(xs[0]), C.ptr(wt), None, C.ptr(yb), C.ptr(ref_t), n, h, w, ci, co, k, C.BF16, 2, 0.2)
+                C.call("gim_conv2d_fwd_fused", C.ptr(xs[0]), C.ptr(wt), None, C.ptr(yb), C.ptr(ref_t), None, n, h, w, ci, co, k, C.BF16, 2, 0.2)
                 err3 = float((yb[:nn_].float() - want2).norm() / want2.norm())
                 line += " (rel %.1e mask %.1e %.1e)" % (err, err2, err3)
                 assert err < 1e-2 and err2 < 2e-3 and err3 < 1e-2, (err, err2, err3)
