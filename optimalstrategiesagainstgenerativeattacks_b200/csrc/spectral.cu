@@ -208,24 +208,54 @@ __global__ void __launch_bounds__(512) sn_unorm_multi_kernel(const __grid_consta
     dot = block_sum(dot, sh);
     if (threadIdx.x == 0) L.aux[L.cout + J] = dot;
 }
-// w_sn[t][co][ci] = W[co][ci][t] / sigma (fp32), the same as bf16, and the flipped/transposed bf16 pack [T-1-t][ci][co]
+// w_sn[t][co][ci] = W[co][ci][t] / sigma (fp32), the same as bf16, and the flipped/transposed bf16 pack [T-1-t][ci][co].
+// One CTA per 32(co) x 32(ci) tile: the [co][ci][taps] rows are read contiguously, transposed through shared memory in groups of
+// <= 9 taps, and all three outputs are written with ci- (resp. co-) contiguous rows.
+constexpr int kPackTaps = 9;
 __global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constant__ SnChunk c) {
     const gim_sn_layer& L = c.l[blockIdx.y];
     const int taps = L.ksize * L.ksize, J = L.cin * taps;
+    const int ci_tiles = (L.cin + 31) / 32, co_tiles = (L.cout + 31) / 32;
+    if ((int)blockIdx.x >= ci_tiles * co_tiles) return;
+    const int co0 = ((int)blockIdx.x / ci_tiles) * 32, ci0 = ((int)blockIdx.x % ci_tiles) * 32;
+    __shared__ float sh[kPackTaps][32][33];
     const float inv = 1.f / L.aux[L.cout + J];
-    const long long total = (long long)taps * L.cout * L.cin;
-    const long long stride = (long long)gridDim.x * blockDim.x;
     bf16* wop = (bf16*)L.w_op;
     bf16* wfl = (bf16*)L.w_flip;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int ci = (int)(i % L.cin);
-        const long long r = i / L.cin;
-        const int co = (int)(r % L.cout);
-        const int t = (int)(r / L.cout);
-        const float v = L.w[((long long)co * L.cin + ci) * taps + t] * inv;
-        L.w_sn[i] = v;
-        if (wop) wop[i] = __float2bfloat16_rn(v);
-        if (wfl) wfl[((long long)(taps - 1 - t) * L.cin + ci) * L.cout + co] = __float2bfloat16_rn(v);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int nci = min(32, L.cin - ci0);
+    for (int t0 = 0; t0 < taps; t0 += kPackTaps) {
+        const int nt = min(kPackTaps, taps - t0);
+        // read: for each co row, the segment [ci0 .. ci0+nci) x [t0 .. t0+nt) ; consecutive threads walk (ci, t) pairs
+        for (int r = ty; r < 32; r += 8) {
+            const int co = co0 + r;
+            if (co < L.cout) {
+                const float* row = L.w + ((long long)co * L.cin + ci0) * taps;
+                for (int e = tx; e < nci * nt; e += 32) {
+                    const int cil = e / nt, tl = e - cil * nt;
+                    sh[tl][r][cil] = row[cil * taps + t0 + tl] * inv;
+                }
+            }
+        }
+        __syncthreads();
+        for (int tl = 0; tl < nt; ++tl) {
+            const int t = t0 + tl;
+            for (int r = ty; r < 32; r += 8) {
+                // w_sn / w_op rows: fixed (t, co), ci contiguous
+                const int co = co0 + r;
+                if (co < L.cout && tx < nci) {
+                    const float v = sh[tl][r][tx];
+                    const long long o = ((long long)t * L.cout + co) * L.cin + ci0 + tx;
+                    L.w_sn[o] = v;
+                    if (wop) wop[o] = __float2bfloat16_rn(v);
+                }
+                // flipped rows: fixed (T-1-t, ci), co contiguous
+                const int ci = ci0 + r;
+                if (wfl && ci < L.cin && co0 + tx < L.cout)
+                    wfl[((long long)(taps - 1 - t) * L.cin + ci) * L.cout + co0 + tx] = __float2bfloat16_rn(sh[tl][tx][r]);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -306,7 +336,12 @@ int gim_sn_forward_multi(const gim_sn_layer* layers, int n_layers, int power_ite
         if ((rc = check_launch("sn_wv_multi")) != GIM_OK) return rc;
         sn_unorm_multi_kernel<<<c.n, 512, 0, st>>>(c, eps, power_iter);
         if ((rc = check_launch("sn_unorm_multi")) != GIM_OK) return rc;
-        sn_pack_multi_kernel<<<dim3(2 * num_sms() / c.n + 1, c.n), 256, 0, st>>>(c);
+        int max_tiles = 0;
+        for (int i = 0; i < c.n; ++i) {
+            int tl = ((c.l[i].cin + 31) / 32) * ((c.l[i].cout + 31) / 32);
+            if (tl > max_tiles) max_tiles = tl;
+        }
+        sn_pack_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c);
         if ((rc = check_launch("sn_pack_multi")) != GIM_OK) return rc;
     }
     return GIM_OK;
