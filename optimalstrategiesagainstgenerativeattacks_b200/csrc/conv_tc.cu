@@ -688,8 +688,9 @@ static bool make_mat_map(CUtensorMap* map, const void* m, long long rows, int co
 }
 
 static int pick_block_n(int cout) {
-    if (cout % 16 != 0) return 0;
-    if (cout >= 128) return 128;           // a ragged last N tile reads the next tap's rows; its columns are never stored
+    if (cout % 8 != 0) return 0;           // 16-byte rows of the packed weight / TMA-store strides
+    cout = (cout + 15) & ~15;              // a ragged last N tile reads rows beyond the tap (next tap's rows, or TMA zero fill past the
+    if (cout >= 128) return 128;           // end of the matrix); those columns are never stored (the output map clips them)
     if (cout > 64) return 128;
     if (cout > 32) return 64;
     return cout > 16 ? 32 : 16;
@@ -699,6 +700,7 @@ bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtyp
     if (dtype != GIM_BF16) return false;
     if (cin % 8 != 0) return false;        // TMA needs 16-byte global strides
     if (pick_block_n(cout) == 0) return false;
+    if (cout % 16 != 0 && cout < 24) return false;      // the narrow-tile kernel stores whole 16-column groups
     if (ks < 1 || !(ks & 1) || ks > 15) return false;
     return n > 0 && h > 0 && wd > 0;
 }

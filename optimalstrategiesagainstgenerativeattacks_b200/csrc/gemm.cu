@@ -155,14 +155,19 @@ __device__ __forceinline__ void stage_split_tile(bf16 (*hi)[TLD], bf16 (*lo)[TLD
 __global__ void __launch_bounds__(128) gemm_strided_mma_kernel(const void* __restrict__ A, int dtA, long long sAb, long long sAm, long long sAk,
                                                                const void* __restrict__ B, int dtB, long long sBb, long long sBk, long long sBn,
                                                                void* __restrict__ C, int dtC, long long sCb, long long ldc, int M, int N, int K,
-                                                               float alpha, float beta) {
+                                                               float alpha, float beta, int m_tiles, int k_per_split) {
     __shared__ __align__(16) bf16 As[TBM][TLD], Al[TBM][TLD];     // hi / lo parts
     __shared__ __align__(16) bf16 Bs[TBN][TLD], Bl[TBN][TLD];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
+    // blockIdx.x = m tile + m_tiles * k split: weight-gradient shapes (tiny M x N, K = tens of thousands of rows) are split along K
+    // over the chip and combined with fp32 atomics into a zeroed C
+    const int split = blockIdx.x / m_tiles;
+    const int m0 = (blockIdx.x - split * m_tiles) * TBM, n0 = blockIdx.y * TBN;
     const long long b = blockIdx.z;
     const long long a_off = b * sAb, b_off = b * sBb, c_off = b * sCb;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int k_begin = split * k_per_split, k_end = min(K, k_begin + k_per_split);
+    const bool atomic_out = k_per_split < K;
     float acc[2][4][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -171,10 +176,10 @@ __global__ void __launch_bounds__(128) gemm_strided_mma_kernel(const void* __res
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += TBK) {
+    for (int k0 = k_begin; k0 < k_end; k0 += TBK) {
         // stage the two tiles as [row][k] hi/lo bf16, walking the unit-stride axis of each operand with consecutive threads
-        stage_split_tile<TBM>(As, Al, A, dtA, a_off, sAm, sAk, m0, M, k0, K, tid);
-        stage_split_tile<TBN>(Bs, Bl, B, dtB, b_off, sBn, sBk, n0, N, k0, K, tid);
+        stage_split_tile<TBM>(As, Al, A, dtA, a_off, sAm, sAk, m0, M, k0, k_end, tid);
+        stage_split_tile<TBN>(Bs, Bl, B, dtB, b_off, sBn, sBk, n0, N, k0, k_end, tid);
         __syncthreads();
 #pragma unroll
         for (int ks = 0; ks < TBK; ks += 16) {
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(128) gemm_strided_mma_kernel(const void* __res
         }
         __syncthreads();
     }
-    const bool c_vec = dtC == GIM_F32 && beta == 0.f && (((uintptr_t)C) & 7) == 0 && ((c_off | ldc) & 1) == 0;
+    const bool c_vec = !atomic_out && dtC == GIM_F32 && beta == 0.f && (((uintptr_t)C) & 7) == 0 && ((c_off | ldc) & 1) == 0;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -219,11 +224,21 @@ __global__ void __launch_bounds__(128) gemm_strided_mma_kernel(const void* __res
                     for (int q = 0; q < 2; ++q)
                         if (gn + q < N) {
                             float v = alpha * acc[i][j][hrow * 2 + q];
+                            if (atomic_out) { atomicAdd((float*)C + idx + q, v); continue; }
                             if (beta != 0.f) v += beta * ld_dt(C, idx + q, dtC);
                             st_dt(C, idx + q, dtC, v);
                         }
                 }
             }
+}
+
+__global__ void __launch_bounds__(256) zero_strided_kernel(float* __restrict__ C, long long sCb, long long ldc, int M, int N, long long total) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int n = (int)(i % N);
+        const long long r = i / N;
+        C[(r / M) * sCb + (r % M) * ldc + n] = 0.f;
+    }
 }
 
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, long long total,
@@ -305,8 +320,28 @@ int gim_gemm_strided_bf16(const void* A, int dtA, long long sAb, long long sAm, 
     if (m <= 0 || n <= 0 || batch <= 0) return GIM_OK;
     GIM_REQUIRE(k >= 0 && batch <= 65535 && (n + TBN - 1) / TBN <= 65535, "gemm_bf16: bad shape");
     GIM_REQUIRE((dtA == GIM_F32 || dtA == GIM_BF16) && (dtB == GIM_F32 || dtB == GIM_BF16) && (dtC == GIM_F32 || dtC == GIM_BF16), "gemm_bf16: bad dtype");
-    dim3 grid((m + TBM - 1) / TBM, (n + TBN - 1) / TBN, batch);
-    gemm_strided_mma_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(A, dtA, sAb, sAm, sAk, B, dtB, sBb, sBk, sBn, C, dtC, sCb, ldc, m, n, k, alpha, beta);
+    const int m_tiles = (m + TBM - 1) / TBM, n_tiles = (n + TBN - 1) / TBN;
+    const long long ctas = (long long)m_tiles * n_tiles * batch;
+    int splits = 1;
+    if (dtC == GIM_F32 && beta == 0.f && k >= 8 * TBK && ctas < num_sms()) {       // few output tiles, long K: split K over the chip
+        long long want = (2LL * num_sms() + ctas - 1) / ctas, most = k / (4 * TBK);
+        splits = (int)(want < most ? want : most);
+        if (splits < 1) splits = 1;
+    }
+    int k_per_split = ((k + splits - 1) / splits + TBK - 1) / TBK * TBK;
+    if (k_per_split < TBK) k_per_split = TBK;
+    splits = k > 0 ? (k + k_per_split - 1) / k_per_split : 1;
+    if (splits > 1) {
+        const long long total = (long long)batch * m * n;
+        zero_strided_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((float*)C, sCb, ldc, m, n, total);
+        int rc = check_launch("gemm_zero");
+        if (rc != GIM_OK) return rc;
+    } else {
+        k_per_split = k > 0 ? k : 1;          // single pass over K (also covers k == 0: C = beta * C)
+    }
+    dim3 grid(m_tiles * splits, n_tiles, batch);
+    gemm_strided_mma_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(A, dtA, sAb, sAm, sAk, B, dtB, sBb, sBk, sBn, C, dtC, sCb, ldc, m, n, k, alpha, beta, m_tiles,
+                                                               k_per_split);
     return check_launch("gemm_strided_mma");
 }
 int gim_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int c, float slope, gim_stream_t s) {

@@ -223,7 +223,7 @@ def _conv_raw(x, w_t, bias, ks):
         w2 = torch.zeros((1, co, kc), dtype=w_t.dtype, device=w_t.device)
         w2[0, :, :taps * ci] = w_t.permute(1, 0, 2).reshape(co, taps * ci)
         return _conv_raw(_im2col(x, ks, 1, kc), w2, bias, 1)
-    if _use_tc(x) and co % 16:
+    if _use_tc(x) and (co % 8 or (co % 16 and co < 24)):
         ld = _round_up(taps * co, 16)
         w2 = torch.zeros((1, ld, ci), dtype=w_t.dtype, device=w_t.device)
         w2[0, :taps * co] = w_t.reshape(taps * co, ci)
@@ -1008,7 +1008,7 @@ def linear(x, weight, bias, slope=1.0):
     x2 = x.reshape(-1, shp[-1])
     rows, k = x2.shape
     n = weight.shape[0]
-    if _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and k % 8 == 0 and n % 16 == 0 and rows >= 16:
+    if _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and k % 8 == 0 and n % 8 == 0 and rows >= 16:
         y = conv2d(x2.reshape(rows, 1, 1, k), weight.reshape(1, n, k), bias, 1).reshape(rows, n)
         if slope != 1.0:
             y = LReluFn.apply(y, slope)

@@ -1,0 +1,73 @@
+"""CPU: host-side logic of the drop-in path that needs no kernel -- the episode index algebra and the device-resident episode source
+(reference data_handling/img_datasets.py:68-103, 153-187), the authentication-score arithmetic (authentication_eval/
+authentication_score.py:33-97) and the attackers' RNG consumption (agents.py:47-65)."""
+import random
+
+import numpy as np
+import torch
+
+from oracle import gim_oracle as O
+from optimalstrategiesagainstgenerativeattacks_b200 import authentication_eval as AE
+from optimalstrategiesagainstgenerativeattacks_b200 import img_datasets as D
+
+
+def test_episode_indices_match_oracle_bit_exact():
+    for seed in (0, 1, 7, 1234):
+        r1, r2 = random.Random(seed), random.Random(seed)
+        for index in (0, 3, 49, 50, 999, 12345):
+            for (per_cls, n_imgs, m, n, k) in ((50, 20, 5, 5, 5), (50, 20, 1, 5, 5), (7, 100, 5, 5, 10), (1, 15, 5, 5, 5)):
+                assert D.episode_indices(index, per_cls, n_imgs, m, n, k, r1) == O.episode_indices(index, per_cls, n_imgs, m, n, k, r2)
+
+
+def test_resident_dataset_gathers_the_drawn_images():
+    imgs = [torch.arange(c * 1 * 2 * 2, dtype=torch.float32).reshape(c, 1, 2, 2) + 1000 * i for i, c in enumerate((20, 14, 30, 16))]
+    ds = D.ResidentGIMDataSet(imgs, m=5, n=5, k=5, example_cnt_per_class=3, device="cpu", seed=11)
+    assert ds.n_classes == 3 and len(ds) == 9                  # the 14-image class cannot fill m+n+k = 15 slots (reference :60-63)
+    ref_rng = random.Random(11)
+    kept = [imgs[0], imgs[2], imgs[3]]
+    batch = ds.batch([4, 0, 8])
+    for row, index in enumerate((4, 0, 8)):
+        cls, leaked, real, si = O.episode_indices(index, 3, kept[index // 3].shape[0], 5, 5, 5, ref_rng)
+        assert int(batch["class"][row]) == cls
+        assert torch.equal(batch["leaked_sample"][row], kept[cls][leaked])
+        assert torch.equal(batch["real_sample"][row], kept[cls][real])
+        assert torch.equal(batch["si_sample"][row], kept[cls][si])
+    ex = ds[5]
+    assert ex["real_sample"].shape == (5, 1, 2, 2) and ex["class"] == 1 and ex["class_name"] == "2"
+    n_seen = sum(b["real_sample"].shape[0] for b in ds.iter_batches(4, shuffle=True, generator=torch.Generator().manual_seed(0)))
+    assert n_seen == len(ds)
+    # global-`random` mode: the same stream the reference's datasets consume
+    ds2 = D.ResidentGIMDataSet(imgs, m=5, n=5, k=5, example_cnt_per_class=3, device="cpu")
+    random.seed(5)
+    a = ds2[2]["si_sample"]
+    random.seed(5)
+    _, _, _, si = O.episode_indices(2, 3, 20, 5, 5, 5, random)
+    assert torch.equal(a, imgs[0][si])
+
+
+def test_roc_auc_matches_sklearn_with_ties():
+    from sklearn.metrics import roc_auc_score as sk
+    g = np.random.default_rng(3)
+    for n in (10, 257, 4000):
+        y = g.integers(0, 2, n)
+        y[0], y[1] = 0, 1
+        s = np.round(g.normal(size=n) + 0.7 * y, 1)            # rounding creates many ties
+        assert abs(AE.roc_auc_score(y, s) - sk(y, s)) < 1e-12
+    assert AE.roc_auc_score([1, 1, 0, 0], [2.0, 3.0, 0.0, 1.0]) == 1.0 and AE.roc_auc_score([1, 0], [0.5, 0.5]) == 0.5
+
+
+def test_comp_acc_and_agents():
+    acc, acc_fake, acc_real = AE.comp_acc(torch.tensor([1, 1, 0, 1]), torch.tensor([0, 1, 0, 0]))
+    assert float(acc_real) == 0.75 and float(acc_fake) == 0.75 and float(acc) == 0.75
+    out, pred = AE.Authenticator(lambda test_sample, si_sample: test_sample.sum(1) - si_sample.sum(1), th=0.).act(
+        torch.tensor([[1., 2.], [0., 0.]]), torch.tensor([[1., 1.], [1., 0.]]))
+    assert pred.tolist() == [1, 0] and pred.dtype == torch.long
+    leaked = torch.arange(2 * 5 * 3, dtype=torch.float32).reshape(2, 5, 3)
+    random.seed(9)
+    got = AE.replay_impersonator(leaked, 4)
+    random.seed(9)
+    want = torch.cat([leaked[:, random.randrange(5)].unsqueeze(1) for _ in range(4)], dim=1)     # the reference expression (agents.py:50)
+    assert torch.equal(got, want)
+    ds = D.ResidentGIMDataSet(D.synthetic_classes(4, 16, 1, 4, seed=1), m=5, n=5, k=5, example_cnt_per_class=2, device="cpu", seed=2)
+    fake = AE.rand_source_impersonator(leaked, 5, ds)
+    assert fake.shape == (2, 5, 1, 4, 4)

@@ -57,7 +57,7 @@ def unpack_w(gw, k):
 
 CONV_SHAPES = [  # n, ci, co, k, h, w
     (2, 3, 64, 3, 16, 16), (3, 64, 64, 3, 8, 8), (2, 6, 64, 9, 16, 16), (2, 64, 3, 9, 16, 16), (2, 64, 16, 1, 7, 5),
-    (1, 1, 128, 3, 32, 32), (5, 128, 128, 3, 4, 4), (2, 64, 128, 3, 13, 13), (130, 32, 8, 1, 1, 1),
+    (1, 1, 128, 3, 32, 32), (5, 128, 128, 3, 4, 4), (2, 64, 128, 3, 13, 13), (130, 32, 8, 1, 1, 1), (3, 64, 40, 3, 9, 7), (200, 72, 1000, 1, 1, 1),
 ]
 
 
@@ -432,7 +432,7 @@ def test_matmul_tensor_core_path():
     ops = ops_mod()
     ops.set_precision("bf16")
     r16 = lambda t: t.float().double()
-    for (bt, m, n, k) in ((3, 70, 33, 17), (2, 64, 64, 32), (5, 64, 256, 64), (2, 256, 16, 256), (1, 130, 100, 200)):
+    for (bt, m, n, k) in ((3, 70, 33, 17), (2, 64, 64, 32), (5, 64, 256, 64), (2, 256, 16, 256), (1, 130, 100, 200), (1, 10, 40, 5000), (2, 20, 10, 3333)):
         for ta in (False, True):
             for tb in (False, True):
                 a64 = rnd(bt, *((k, m) if ta else (m, k)), seed=1)

@@ -326,3 +326,58 @@ def test_spectral_norm_call_counts_follow_reference_state_machine(schemas, tmp_p
         assert rel_err(au.state_dict()[key], pa[key]) < 1e-4, key
     for key in ("img2img.adain_res_block.res_blocks.2.conv1.weight_u", "env_decoder.up_blocks.0.conv_r1.weight_v"):
         assert rel_err(im.state_dict()[key], pi[key]) < 1e-4, key
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_authentication_eval_vs_oracle(schemas, prec):
+    """the authentication eval loop (reference authentication_eval/authentication_score.py:47-97 with the GIM agents
+    of eval_gim_on_authentication.py:25-81) on a device-resident episode source: per-batch logits equal the oracle's, which -- like
+    the reference -- leaves the networks in train mode (one power iteration per encoder call), and the aggregated scores follow."""
+    import random
+    g, M = pkg()[0], pkg()[1]
+    from optimalstrategiesagainstgenerativeattacks_b200 import authentication_eval as AE
+    from optimalstrategiesagainstgenerativeattacks_b200 import img_datasets as D
+    g.set_precision(prec)
+    tol = TOLS[prec]
+    s = schemas["s16"]
+    au = load(M.get_au(16, 3, 64), s["au"], 11)
+    im = load(M.get_im(16, 3, 64), s["im"], 12)
+    pa, pi = oracle_params(s["au"], 11), oracle_params(s["im"], 12)
+    classes = D.synthetic_classes(3, 8, 3, 16, seed=5) * 0.5
+    mk = lambda: D.ResidentGIMDataSet(classes, m=2, n=3, k=2, example_cnt_per_class=2, device="cuda", seed=21)
+    authenticator = AE.Authenticator(AE.get_au_function(au))
+    impersonator = AE.Impersonator(AE.get_im_function(im, {"remove_noise_mean": True}))
+    zs = [seeded((2, 3, 64), 30 + i) for i in range(3)]
+    ds = mk()
+    outs = []
+    with inject_randn([z.cuda() for z in zs]):
+        for b in ds.iter_batches(2, shuffle=False):
+            o_real, p_real = authenticator.act(test_sample=b["real_sample"], si_sample=b["si_sample"])
+            fake = impersonator.act(leaked_sample=b["leaked_sample"], n=3)
+            o_fake, p_fake = authenticator.act(test_sample=fake, si_sample=b["si_sample"])
+            outs.append((o_real, o_fake, fake, p_real, p_fake))
+    def o_au(test, si):                                                # eval_gim_on_authentication.py:28-41: si is encoded first
+        si_src, si_env = O.encode_sample(pa, "src_encoder", si), O.encode_sample(pa, "env_encoder", si)
+        t_src, t_env = O.encode_sample(pa, "src_encoder", test), O.encode_sample(pa, "env_encoder", test)
+        return O.face_dis(pa, "dis", t_src, t_env, si_src, si_env)
+
+    ds = mk()                                                          # same episode draws for the oracle
+    with torch.no_grad():
+        for i, b in enumerate(ds.iter_batches(2, shuffle=False)):
+            real, leaked, si = (b[k_].cpu() for k_ in ("real_sample", "leaked_sample", "si_sample"))
+            r_real = o_au(real, si)
+            r_fake_img = O.impersonator(pi, leaked, 3, zs[i])
+            r_fake = o_au(r_fake_img, si)
+            assert rel_err(outs[i][2], r_fake_img) < tol
+            assert rel_err(outs[i][0], r_real) < tol and rel_err(outs[i][1], r_fake) < tol
+            assert outs[i][3].dtype == torch.long and torch.equal(outs[i][3].cpu(), torch.ge(outs[i][0], 0).long().cpu())
+    # spectral-norm state advanced exactly as in the oracle: 2 encoder calls per act, 2 acts per batch, 3 batches
+    assert rel_err(au.src_encoder.down_blocks[0].conv_r1.weight_u, pa["src_encoder.down_blocks.0.conv_r1.weight_u"]) < 1e-4
+    # the aggregate entry point: same loop, scores in range and self-consistent
+    random.seed(3)
+    torch.manual_seed(3)
+    acc, acc_fake, acc_real, auc = AE.eval_authenticator_and_impersonator("cuda", mk(), 2, 0, authenticator, impersonator)
+    assert 0.0 <= auc <= 1.0 and abs(float(acc) - 0.5 * (float(acc_fake) + float(acc_real))) < 1e-6
+    res = AE.eval_dis_on_multiple_im("cuda", mk(), 2, 0, authenticator, {"replay": AE.Impersonator(AE.replay_impersonator),
+                                                                         "rnd_src": AE.Impersonator(lambda leaked_sample, n: AE.rand_source_impersonator(leaked_sample, n, mk()))})
+    assert set(res) == {"replay", "rnd_src"} and all(0.0 <= r["auc"] <= 1.0 for r in res.values())
