@@ -931,6 +931,186 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// weight gradient with the gradient tile shared between filter taps (k > 1).
+//   One CTA owns up to three taps of one filter row: per 64-pixel K block it fetches the dY tile ONCE and one tap-shifted X tile
+//   per tap, and issues the taps' MMAs into separate TMEM accumulators (independent chains interleave on the tensor pipe).  TMA
+//   traffic per FLOP drops from 2 boxes per tap to (1 + T)/T -- the kernels are bound by the ~13 TB/s of L2->SM traffic, not by HBM.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kWgPix = 64;                       // pixels per K block
+constexpr int kWgBox = kWgPix * 128;             // one {64 channels, 64 pixels} TMA box: 8 KB
+
+struct WgradTc3Params {
+    int n, h, w, cin, cout, ks;
+    int bw, bh, bn, tiles_w, tiles_h, tiles_n;   // 64-pixel box
+    int block_n;                                 // ci per CTA: 64 or 128
+    int co_tiles, ci_tiles;
+    int stages, tiles_per_split, total_tiles;
+    int tgroup, groups_per_row;                  // taps per CTA (<= 3), tap groups per filter row
+};
+
+template <int kDummy>
+__global__ void __launch_bounds__(192, 1) conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
+                                                                float* __restrict__ gw, const WgradTc3Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = 2 * kWgBox;                                    // 128 co = two 64-channel boxes
+    const int b_tap_bytes = (p.block_n / 64) * kWgBox;
+    const int stage_bytes = a_bytes + p.tgroup * b_tap_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tmem_full_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int groups = p.ks * p.groups_per_row;
+    int t = blockIdx.x;
+    const int g = t % groups; t /= groups;
+    const int co_t = t % p.co_tiles;
+    const int ci_t = t / p.co_tiles;
+    const int co0 = co_t * 128, ci0 = ci_t * p.block_n;
+    const int pad = (p.ks - 1) / 2;
+    const int r = g / p.groups_per_row, q0 = (g - r * p.groups_per_row) * p.tgroup;
+    const int nt = min(p.tgroup, p.ks - q0);                           // taps handled here: (r, q0 .. q0+nt-1)
+    const int tile_begin = blockIdx.y * p.tiles_per_split;
+    const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_split);
+    const int num_kb = tile_end - tile_begin;                          // >= 1 by construction of the grid
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(p.tgroup * p.block_n)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_gy);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 1;
+            int tw = tile_begin % p.tiles_w, th = (tile_begin / p.tiles_w) % p.tiles_h, tn = tile_begin / (p.tiles_w * p.tiles_h);
+            const int nb = p.block_n / 64;
+            const uint32_t tx = (uint32_t)(a_bytes + nt * b_tap_bytes);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[s], ph);
+                const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tn * p.bn;
+                uint8_t* sa = smem + s * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                mbar_expect_tx(&full_bar[s], tx);
+                tma_load_4d(sa, &map_gy, &full_bar[s], co0, w0, h0, img0);
+                tma_load_4d(sa + kWgBox, &map_gy, &full_bar[s], co0 + 64, w0, h0, img0);
+                for (int tp = 0; tp < nt; ++tp)
+                    for (int j = 0; j < nb; ++j)
+                        tma_load_4d(sb + tp * b_tap_bytes + j * kWgBox, &map_x, &full_bar[s], ci0 + 64 * j, w0 + q0 + tp - pad, h0 + r - pad, img0);
+                if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 1, 1);
+            const uint32_t s0 = smem_u32(smem);
+            const uint64_t desc_a0 = make_desc_sw128(s0, kWgBox, 1024), desc_b0 = make_desc_sw128(s0 + a_bytes, kWgBox, 1024);
+            const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), tap_step = (uint64_t)(b_tap_bytes >> 4);
+            int s = 0;
+            uint32_t ph = 0;
+            uint64_t da = desc_a0, db = desc_b0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t acc = kb != 0 ? 1u : 0u;
+#pragma unroll
+                for (int k = 0; k < kWgPix / 16; ++k)                  // 64 pixels per stage = 4 K steps of 16, 2 KB apart
+                    for (int tp = 0; tp < nt; ++tp)
+                        umma_bf16(tmem_base + (uint32_t)(tp * p.block_n), da + (uint64_t)(k * 128), db + tp * tap_step + (uint64_t)(k * 128), idesc,
+                                  k ? 1u : acc);
+                umma_commit(&empty_bar[s]);
+                da += stage_step; db += stage_step;
+                if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int co = co0 + quarter * 32 + lane;
+        for (int tp = 0; tp < nt; ++tp) {
+            const int tap = r * p.ks + q0 + tp;
+            float* dst_row = gw + ((long long)tap * p.cout + co) * p.cin + ci0;
+            for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tp * p.block_n + c0), v);
+                tmem_ld_wait();
+                if (co < p.cout) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (ci0 + c0 + j < p.cin) atomicAdd(dst_row + c0 + j, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static int conv_wgrad_tc3(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
+    WgradTc3Params p;
+    p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
+    p.bw = next_pow2(wd) < kWgPix ? next_pow2(wd) : kWgPix;
+    p.bh = next_pow2(h) < kWgPix / p.bw ? next_pow2(h) : kWgPix / p.bw;
+    p.bn = kWgPix / (p.bw * p.bh);
+    p.tiles_w = (wd + p.bw - 1) / p.bw;
+    p.tiles_h = (h + p.bh - 1) / p.bh;
+    p.tiles_n = (n + p.bn - 1) / p.bn;
+    long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    if (total > 2147483647LL) return fail(GIM_E_ARG, "conv_wgrad_tc: too many tiles");
+    p.total_tiles = (int)total;
+    p.block_n = cin > 64 ? 128 : 64;
+    p.co_tiles = (cout + 127) / 128;
+    p.ci_tiles = (cin + p.block_n - 1) / p.block_n;
+    p.tgroup = 3;
+    p.groups_per_row = (ks + p.tgroup - 1) / p.tgroup;
+    const int stage_bytes = 2 * kWgBox + p.tgroup * (p.block_n / 64) * kWgBox;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    const long long out_tiles = (long long)ks * p.groups_per_row * p.co_tiles * p.ci_tiles;
+    long long want = ((long long)num_sms() * 2 + out_tiles - 1) / out_tiles;        // ~2 waves of CTAs over the chip
+    long long max_split = (total + 7) / 8;                                         // at least ~8 K blocks per CTA
+    if (max_split < 1) max_split = 1;
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    p.tiles_per_split = (int)((total + want - 1) / want);
+    const int splits = (int)((total + p.tiles_per_split - 1) / p.tiles_per_split);
+    CUtensorMap map_gy, map_x;
+    if (!make_act_map(&map_gy, gy, n, h, wd, cout, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(gy) failed");
+    if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed");
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_wgrad_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail(GIM_E_CUDA, "conv_wgrad_tc: cannot raise dynamic shared memory limit");
+        attr_set = true;
+    }
+    if (out_tiles > 2147483647LL) return fail(GIM_E_ARG, "conv_wgrad_tc: too many output tiles");
+    dim3 grid((unsigned)out_tiles, splits);
+    conv_wgrad_tc3_kernel<0><<<grid, 192, smem, st>>>(map_gy, map_x, gw, p);
+    return check_launch("conv_wgrad_tc3");
+}
+
 bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype) {
     if (dtype != GIM_BF16) return false;
     if (cin % 8 != 0 || cout % 8 != 0) return false;
@@ -939,6 +1119,11 @@ bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dty
 }
 
 int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
+    // Measured on B200 (tools/conv_bench.py, 640 images): sharing the dY tile between three taps is SLOWER than one tap per CTA with
+    // 128-pixel K blocks (664 vs 818, 612 vs 860, 632 vs 1050 TFLOP/s on the 128/256/512-channel 3x3 layers) although it moves a third
+    // less data: the weight-gradient kernel is not bound by L2->SM traffic.  Kept selectable for further experiments.
+    static const int tap_groups = env_int("GIM_WGRAD_TAPGROUP", 0);
+    if (ks > 1 && tap_groups) return conv_wgrad_tc3(x, gy, gw, n, h, wd, cin, cout, ks, st);
     WgradTcParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
     pixel_box(h, wd, p.bw, p.bh, p.bn);
