@@ -97,6 +97,20 @@ typedef struct {
     int cout, cin, ksize, reserved;
 } gim_sn_layer;
 int gim_sn_forward_multi(const gim_sn_layer* layers, int n_layers, int power_iter, float eps, gim_stream_t stream);
+/* Batched backward of the same: grad[co][ci][k][k] (+)= g[t][co][ci]/sigma - (sum(g.w)/sigma^2) u[co] v[ci*k*k+t].  g: gradient of the
+ * packed weight; u, v, sigma: the values the forward used (aux); scratch: one fp32 word per layer; accumulate != 0 adds into grad
+ * (the parameter's .grad), so no separate accumulation kernel runs.  `layers` is a HOST array. */
+typedef struct {
+    const float* g;
+    const float* w;
+    const float* u;
+    const float* v;
+    const float* sigma;
+    float* grad;
+    float* scratch;
+    int cout, cin, ksize, accumulate;
+} gim_sn_bwd_layer;
+int gim_sn_backward_multi(const gim_sn_bwd_layer* layers, int n_layers, gim_stream_t stream);
 
 /* ---- pointwise / resampling (model_blocks.py:489-490, 740, 744; gim_img_models.py:215) ---- */
 int gim_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, gim_stream_t stream);
@@ -211,6 +225,8 @@ typedef struct {
  * corrections use step+1); grad_scale multiplies g first (1/world_size after an allreduce(sum)). */
 int gim_adam_multi(const gim_adam_tensor* table, int n_tensors, long long max_numel, const float* lrs,
                    long long* step, float beta1, float beta2, float eps, float grad_scale, gim_stream_t stream);
+/* g = 0 for every tensor of the same table in one launch (optimizer.zero_grad() with the gradient buffers kept in place) */
+int gim_zero_grads_multi(const gim_adam_tensor* table, int n_tensors, long long max_numel, gim_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "gim_sn_forward": "pppifpppppiiip",
     "gim_sn_backward": "pppppppiiip",
     "gim_sn_forward_multi": "piifp",
+    "gim_sn_backward_multi": "pip",
     "gim_lrelu_fwd": "pplfip",
     "gim_lrelu_bwd": "ppplfip",
     "gim_tanh_fwd": "pplip",
@@ -71,6 +72,7 @@ PROTOTYPES = {
     "gim_rows_sqsum": "ppilip",
     "gim_rows_scale": "pppilfip",
     "gim_adam_multi": "pilppfff" + "fp",
+    "gim_zero_grads_multi": "pilp",
 }
 OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_launch_count")
 
@@ -80,6 +82,12 @@ class SnLayer(ctypes.Structure):
     """gim_sn_layer of include/gim_b200.h."""
     _fields_ = [("w", _P), ("u", _P), ("v", _P), ("w_sn", _P), ("w_op", _P), ("w_flip", _P), ("aux", _P), ("scratch", _P),
                 ("cout", _I), ("cin", _I), ("ksize", _I), ("reserved", _I)]
+
+
+class SnBwdLayer(ctypes.Structure):
+    """gim_sn_bwd_layer of include/gim_b200.h."""
+    _fields_ = [("g", _P), ("w", _P), ("u", _P), ("v", _P), ("sigma", _P), ("grad", _P), ("scratch", _P),
+                ("cout", _I), ("cin", _I), ("ksize", _I), ("accumulate", _I)]
 
 
 _lib = None

@@ -53,6 +53,18 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const gim_adam_tensor* 
 
 __global__ void adam_step_inc_kernel(long long* step) { *step += 1; }
 
+// zero every gradient of the optimizer in one launch (optimizer.zero_grad() with gradients kept in place)
+__global__ void __launch_bounds__(256) zero_grads_multi_kernel(const gim_adam_tensor* __restrict__ table) {
+    const gim_adam_tensor t = table[blockIdx.y];
+    if ((long long)blockIdx.x * blockDim.x >= t.numel) return;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float* g = const_cast<float*>(t.g);                  // the table is shared with the Adam kernel, which only reads gradients
+    const bool vec = (((uintptr_t)g & 15) == 0);
+    const long long nv = vec ? t.numel / 4 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.numel; i += stride) g[i] = 0.f;
+}
+
 }  // namespace gim
 
 using namespace gim;
@@ -70,4 +82,14 @@ extern "C" int gim_adam_multi(const gim_adam_tensor* table, int n_tensors, long 
     if (rc != GIM_OK) return rc;
     adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step);
     return check_launch("adam_step_inc");
+}
+
+extern "C" int gim_zero_grads_multi(const gim_adam_tensor* table, int n_tensors, long long max_numel, gim_stream_t s) {
+    if (n_tensors <= 0) return GIM_OK;
+    GIM_REQUIRE(n_tensors <= 65535, "zero_grads: too many tensors in one launch");
+    long long gx = (max_numel + 256 * 4 * 4 - 1) / (256 * 4 * 4);
+    if (gx < 1) gx = 1;
+    if (gx > 128) gx = 128;
+    zero_grads_multi_kernel<<<dim3((unsigned)gx, n_tensors), 256, 0, (cudaStream_t)s>>>(table);
+    return check_launch("zero_grads_multi");
 }

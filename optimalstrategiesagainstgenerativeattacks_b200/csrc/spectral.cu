@@ -259,6 +259,85 @@ __global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constan
     }
 }
 
+// ---- batched backward: gW[co][ci][t] (+)= G[t][co][ci]/sigma - (sum(G.W)/sigma^2) u[co] v[ci*taps+t] for up to kSnChunk layers ----
+struct SnBwdChunk {
+    gim_sn_bwd_layer l[kSnChunk];
+    int n;
+};
+
+// phase 1: c[layer] = sum G*W.  Same tiling as phase 2 (one CTA per 32(co) x 32(ci) tile, G transposed through shared memory so that
+// both G and W are read contiguously); per-CTA partial sums combine with one fp32 atomic into the layer's scratch word (zeroed by the caller)
+__global__ void __launch_bounds__(256) sn_bwd_dot_multi_kernel(const __grid_constant__ SnBwdChunk c) {
+    const gim_sn_bwd_layer& L = c.l[blockIdx.y];
+    const int taps = L.ksize * L.ksize;
+    const int ci_tiles = (L.cin + 31) / 32, co_tiles = (L.cout + 31) / 32;
+    if ((int)blockIdx.x >= ci_tiles * co_tiles) return;
+    const int co0 = ((int)blockIdx.x / ci_tiles) * 32, ci0 = ((int)blockIdx.x % ci_tiles) * 32;
+    __shared__ float sh[kPackTaps][32][33];
+    __shared__ float red[33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int nci = min(32, L.cin - ci0);
+    float acc = 0.f;
+    for (int t0 = 0; t0 < taps; t0 += kPackTaps) {
+        const int nt = min(kPackTaps, taps - t0);
+        for (int tl = 0; tl < nt; ++tl)
+            for (int r = ty; r < 32; r += 8) {
+                const int co = co0 + r;
+                if (co < L.cout && tx < nci) sh[tl][r][tx] = L.g[((long long)(t0 + tl) * L.cout + co) * L.cin + ci0 + tx];
+            }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int co = co0 + r;
+            if (co < L.cout) {
+                const float* row = L.w + ((long long)co * L.cin + ci0) * taps;
+                for (int e = tx; e < nci * nt; e += 32) {
+                    const int cil = e / nt, tl = e - cil * nt;
+                    acc = fmaf(sh[tl][r][cil], row[cil * taps + t0 + tl], acc);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0 && acc != 0.f) atomicAdd(L.scratch, acc);
+}
+// phase 2: one CTA per 32(co) x 32(ci) tile, G transposed through shared memory so that both G reads and gW writes are contiguous
+__global__ void __launch_bounds__(256) sn_bwd_apply_multi_kernel(const __grid_constant__ SnBwdChunk c) {
+    const gim_sn_bwd_layer& L = c.l[blockIdx.y];
+    const int taps = L.ksize * L.ksize;
+    const int ci_tiles = (L.cin + 31) / 32, co_tiles = (L.cout + 31) / 32;
+    if ((int)blockIdx.x >= ci_tiles * co_tiles) return;
+    const int co0 = ((int)blockIdx.x / ci_tiles) * 32, ci0 = ((int)blockIdx.x % ci_tiles) * 32;
+    __shared__ float sh[kPackTaps][32][33];
+    const float inv = 1.f / *L.sigma;
+    const float k = (*L.scratch) * inv * inv;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int nci = min(32, L.cin - ci0);
+    for (int t0 = 0; t0 < taps; t0 += kPackTaps) {
+        const int nt = min(kPackTaps, taps - t0);
+        for (int tl = 0; tl < nt; ++tl)
+            for (int r = ty; r < 32; r += 8) {
+                const int co = co0 + r;
+                if (co < L.cout && tx < nci) sh[tl][r][tx] = L.g[((long long)(t0 + tl) * L.cout + co) * L.cin + ci0 + tx];
+            }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int co = co0 + r;
+            if (co < L.cout) {
+                float* row = L.grad + ((long long)co * L.cin + ci0) * taps;
+                const float uco = L.u[co];
+                for (int e = tx; e < nci * nt; e += 32) {
+                    const int cil = e / nt, tl = e - cil * nt;
+                    const float val = sh[tl][r][cil] * inv - k * uco * L.v[(ci0 + cil) * taps + t0 + tl];
+                    float* dst = row + cil * taps + t0 + tl;
+                    *dst = L.accumulate ? *dst + val : val;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace gim
 
 using namespace gim;
@@ -343,6 +422,31 @@ int gim_sn_forward_multi(const gim_sn_layer* layers, int n_layers, int power_ite
         }
         sn_pack_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c);
         if ((rc = check_launch("sn_pack_multi")) != GIM_OK) return rc;
+    }
+    return GIM_OK;
+}
+
+int gim_sn_backward_multi(const gim_sn_bwd_layer* layers, int n_layers, gim_stream_t s) {
+    GIM_REQUIRE(n_layers >= 0 && (n_layers == 0 || layers), "sn_backward_multi: bad arguments");
+    cudaStream_t st = (cudaStream_t)s;
+    for (int base = 0; base < n_layers; base += kSnChunk) {
+        SnBwdChunk c;
+        c.n = n_layers - base < kSnChunk ? n_layers - base : kSnChunk;
+        int max_tiles = 0;
+        for (int i = 0; i < c.n; ++i) {
+            c.l[i] = layers[base + i];
+            const gim_sn_bwd_layer& L = c.l[i];
+            GIM_REQUIRE(L.cout > 0 && L.cin > 0 && L.ksize > 0 && L.g && L.w && L.u && L.v && L.sigma && L.grad && L.scratch, "sn_backward_multi: bad layer");
+            if (cudaMemsetAsync(L.scratch, 0, sizeof(float), st) != cudaSuccess) return fail(GIM_E_CUDA, "sn_backward_multi memset");
+            int tl = ((L.cin + 31) / 32) * ((L.cout + 31) / 32);
+            if (tl > max_tiles) max_tiles = tl;
+        }
+        for (int i = c.n; i < kSnChunk; ++i) c.l[i] = c.l[0];
+        sn_bwd_dot_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c);
+        int rc = check_launch("sn_bwd_dot_multi");
+        if (rc != GIM_OK) return rc;
+        sn_bwd_apply_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c);
+        if ((rc = check_launch("sn_bwd_apply_multi")) != GIM_OK) return rc;
     }
     return GIM_OK;
 }

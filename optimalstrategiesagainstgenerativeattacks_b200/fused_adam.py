@@ -111,4 +111,9 @@ class FusedAdam(torch.optim.Adam):
     def zero_grad(self, set_to_none=False):
         """Gradients are zeroed in place by default so their addresses (the fused kernel's pointer table, CUDA graphs,
         the data-parallel flat buckets) stay valid; parameters that never received a gradient keep grad None."""
+        if not set_to_none and self._table_key is not None:
+            active = [p for g in self.param_groups for p in g["params"] if p.grad is not None]
+            if tuple((p.data_ptr(), p.grad.data_ptr()) for p in active) == self._table_key:
+                C.call("gim_zero_grads_multi", self._table_dev.data_ptr(), self._n, self._max_numel)      # one launch for all gradients
+                return
         super().zero_grad(set_to_none=set_to_none)

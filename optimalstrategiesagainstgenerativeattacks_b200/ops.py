@@ -21,7 +21,7 @@ from torch.autograd.function import once_differentiable
 from . import _cabi as C
 
 LRELU_SLOPE = 0.2
-_state = {"operand_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False, "composite": False}
+_state = {"operand_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False, "composite": False, "defer_sn": False}
 
 
 def set_precision(name):
@@ -550,6 +550,7 @@ class SpectralNormFn(Function):
                u_used.data_ptr(), v_used.data_ptr(), C.ptr(scratch), co, ci, k)
         ctx.save_for_backward(w, aux)
         ctx.dims = (co, ci, k)
+        ctx.param = weight_orig
         return w_sn
 
     @staticmethod
@@ -558,12 +559,73 @@ class SpectralNormFn(Function):
         w, aux = ctx.saved_tensors
         co, ci, k = ctx.dims
         g = _c(g)
+        if _defer_sn_backward(ctx, g, w, aux):
+            return None, None, None, None
         gw = torch.empty_like(w)
         scratch = _empty((8,), torch.float32, w)
         j = ci * k * k
         C.call("gim_sn_backward", C.ptr(g), C.ptr(w), aux[:co].data_ptr(), aux[co:co + j].data_ptr(), aux[co + j:].data_ptr(),
                C.ptr(gw), C.ptr(scratch), co, ci, k)
         return gw, None, None, None
+
+
+# ---- deferred, batched spectral-norm backward ---------------------------------------------------------------------
+_sn_pending = []
+
+
+@contextlib.contextmanager
+def deferred_weight_grads():
+    """Wrap `loss.backward()`: inside, the spectral-norm backward of every convolution is not launched layer by layer (2 kernels + a
+    memset + an AccumulateGrad add each) but collected and, when the backward pass ends, run for all layers at once
+    (gim_sn_backward_multi), accumulating straight into `weight_orig.grad`.  Only valid for `.backward()` (which accumulates into
+    .grad); `torch.autograd.grad` w.r.t. a weight_orig must not be used inside."""
+    old = _state["defer_sn"]
+    _state["defer_sn"] = True
+    try:
+        yield
+    finally:
+        _state["defer_sn"] = old
+        _flush_sn_backward()
+
+
+def _defer_sn_backward(ctx, g, w, aux):
+    prm = getattr(ctx, "param", None)
+    if not _state["defer_sn"] or prm is None or not prm.is_leaf or not prm.requires_grad or not prm.is_contiguous():
+        return False
+    if not _sn_pending:
+        torch.autograd.Variable._execution_engine.queue_callback(_flush_sn_backward)
+    _sn_pending.append((prm, g, aux, ctx.dims))
+    return True
+
+
+def _flush_sn_backward():
+    import ctypes
+    pending, seen_round = list(_sn_pending), {}
+    del _sn_pending[:]
+    if not pending:
+        return
+    rounds = []                      # two gradients of the same parameter (D's encoders run three times per step) go to separate launches
+    for item in pending:
+        r = seen_round.get(id(item[0]), 0)
+        seen_round[id(item[0])] = r + 1
+        while len(rounds) <= r:
+            rounds.append([])
+        rounds[r].append(item)
+    with torch.no_grad():
+        for items in rounds:
+            scratch = torch.empty(len(items), dtype=torch.float32, device=items[0][1].device)
+            table = (C.SnBwdLayer * len(items))()
+            for i, (prm, g, aux, (co, ci, k)) in enumerate(items):
+                acc = 1
+                if prm.grad is None:
+                    prm.grad = torch.empty_like(prm)
+                    acc = 0
+                j = ci * k * k
+                e = table[i]
+                e.g, e.w, e.u, e.v, e.sigma = g.data_ptr(), prm.data_ptr(), aux.data_ptr(), aux[co:].data_ptr(), aux[co + j:].data_ptr()
+                e.grad, e.scratch = prm.grad.data_ptr(), scratch[i:].data_ptr()
+                e.cout, e.cin, e.ksize, e.accumulate = co, ci, k, acc
+            C.call("gim_sn_backward_multi", ctypes.cast(table, ctypes.c_void_p), len(items))
 
 
 def sn_prepare(convs, training, eps):
@@ -616,6 +678,7 @@ class SpectralNormPreparedFn(Function):
         co, ci, k, _ = weight_orig.shape
         ctx.save_for_backward(weight_orig, aux)
         ctx.dims = (co, ci, k)
+        ctx.param = weight_orig
         return w_sn
 
     @staticmethod

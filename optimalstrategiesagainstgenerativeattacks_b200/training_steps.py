@@ -2,13 +2,16 @@
 training/gim_gaussian_training.py:21-47), callable with either trainer."""
 import torch
 
+from . import ops
+
 
 def im_train_step(trainer, leaked_sample, si_sample):
     trainer.module.impersonator.train()
     trainer.module.impersonator_opt.zero_grad()
     loss, fake_sample, au_out = trainer.forward(mode='impersonator_forward', leaked_sample=leaked_sample, si_sample=si_sample)
     loss = loss.mean()
-    loss.backward()
+    with ops.deferred_weight_grads():          # one batched spectral-norm backward for all convolutions at the end of the pass
+        loss.backward()
     trainer.module.impersonator_opt.step()
     return loss.detach(), fake_sample.detach(), au_out.detach()
 
@@ -19,7 +22,8 @@ def au_train_step(trainer, real_sample, fake_sample, si_sample):
     (loss, loss_on_real, loss_on_fake, reg, out_on_real, out_on_fake, pred_on_real, pred_on_fake, fake_sample) = trainer.forward(
         mode='authenticator_forward', fake_sample=fake_sample, real_sample=real_sample, si_sample=si_sample)
     loss = loss.mean()
-    loss.backward()
+    with ops.deferred_weight_grads():
+        loss.backward()
     trainer.module.authenticator_opt.step()
     return (loss.detach(), loss_on_real.detach().mean(), loss_on_fake.detach().mean(), reg.detach().mean(),
             out_on_real.detach().mean(), out_on_fake.detach().mean(),
