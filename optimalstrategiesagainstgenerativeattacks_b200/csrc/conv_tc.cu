@@ -98,6 +98,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// 16-byte vector reduction into global memory (sm_90+): one instruction instead of four scalar atomics
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (sm_100 format, version 1), SWIZZLE_128B.
@@ -918,8 +922,10 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
             tmem_ld_wait();
             if (co < p.cout) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (ci0 + c0 + j < p.cin) atomicAdd(dst_row + c0 + j, __uint_as_float(v[j]) + __uint_as_float(v1[j]));
+                for (int j = 0; j < 16; j += 4)                      // cin % 8 == 0: whole 4-column groups are in or out
+                    if (ci0 + c0 + j < p.cin)
+                        red_add_v4(dst_row + c0 + j, __uint_as_float(v[j]) + __uint_as_float(v1[j]), __uint_as_float(v[j + 1]) + __uint_as_float(v1[j + 1]),
+                                   __uint_as_float(v[j + 2]) + __uint_as_float(v1[j + 2]), __uint_as_float(v[j + 3]) + __uint_as_float(v1[j + 3]));
             }
         }
     }
@@ -1052,8 +1058,9 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc3_kernel(const __grid_con
                 tmem_ld_wait();
                 if (co < p.cout) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (ci0 + c0 + j < p.cin) atomicAdd(dst_row + c0 + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 16; j += 4)
+                        if (ci0 + c0 + j < p.cin)
+                            red_add_v4(dst_row + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                 }
             }
         }
@@ -1119,9 +1126,10 @@ bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dty
 }
 
 int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
-    // Measured on B200 (tools/conv_bench.py, 640 images): sharing the dY tile between three taps is SLOWER than one tap per CTA with
-    // 128-pixel K blocks (664 vs 818, 612 vs 860, 632 vs 1050 TFLOP/s on the 128/256/512-channel 3x3 layers) although it moves a third
-    // less data: the weight-gradient kernel is not bound by L2->SM traffic.  Kept selectable for further experiments.
+    // Measured on B200 (tools/conv_bench.py, 640 images, both with vector reductions): sharing the dY tile between three taps only wins
+    // on the 128-channel 3x3 layer (997 vs 921 TFLOP/s) and loses elsewhere (785 vs 943, 821 vs 1197, 9x9: 838 vs 1055) although it moves
+    // a third less data: the weight-gradient kernel is not bound by L2->SM traffic (its epilogue atomics were the limiter: switching
+    // them to red.global.add.v4.f32 gave +10..45 %).  Kept selectable for further experiments.
     static const int tap_groups = env_int("GIM_WGRAD_TAPGROUP", 0);
     if (ks > 1 && tap_groups) return conv_wgrad_tc3(x, gy, gw, n, h, wd, cin, cout, ks, st);
     WgradTcParams p;
