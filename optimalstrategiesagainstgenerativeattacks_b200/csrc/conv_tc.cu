@@ -104,6 +104,58 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ---- cta_group::2 (two CTAs of a cluster share one MMA: M = 2 x 128 rows, each CTA holds its rows of A, half the rows of B and its
+// half of the accumulator).  Loads of either CTA signal the LEADER's (rank 0) barrier; commits are multicast to both CTAs. ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;           // clears the CTA-rank bit of a shared::cluster address -> same offset in CTA 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    __syncwarp();                                        // role loops leave the lanes of a warp apart; .aligned needs them together
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair when all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at this offset in the leader CTA (rank 0) of the cluster
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0u));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 // shared-memory matrix descriptor (sm_100 format, version 1), SWIZZLE_128B.
 //   K-major operand : rows of 128 B (64 bf16 along K); 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major operand: 64 MN elements contiguous (128 B) per K index, 8 K-rows = one 1024 B atom (SBO), next 64-wide MN block at LBO.
@@ -115,8 +167,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
     return make_desc(saddr, lbo_bytes, sbo_bytes, 2);      // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
 }
 // instruction descriptor, kind::f16: D fp32, A/B bf16, M=128, N=n; a_mn / b_mn = 1 for MN-major operands
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t n, uint32_t a_mn, uint32_t b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n, uint32_t a_mn, uint32_t b_mn, uint32_t m = 128u) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -138,6 +190,7 @@ struct ConvTcParams {
     int epi;                                     // fused epilogue bits (persistent kernel): kEpiLrelu, kEpiMask
     int m_sub;                                   // pixel tiles per macro tile (persistent kernel): 1 or 2
     int n_staging;                               // output staging boxes of the epilogue ring (persistent kernel): 2..4
+    int pair;                                    // 1: cta_group::2 kernel variant (two-CTA clusters)
     int debug;                                   // GIM_CONV_DEBUG bits (profiling experiments only): 1 no TMA store, 2 no proxy fence, 4 no smem staging
     float slope;
 };
@@ -332,16 +385,20 @@ constexpr int kBoxBytes = kBlockM * 128;                   // one staged output 
 // A macro tile = m_sub (1 or 2) consecutive 128-pixel tiles x one block_n-wide channel tile.  With m_sub = 2 the two pixel tiles
 // share every weight box and their MMAs alternate between two independent accumulators (measured: a single dependent
 // accumulation chain of N=128 MMAs tops out near 1.0 PFLOP/s, two interleaved chains or N=256 reach 1.3).
-template <int kDummy>
+template <int kPair>
 __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                                               const __grid_constant__ CUtensorMap map_y, const float* __restrict__ bias,
                                                               const bf16* __restrict__ mask_ref, const float* addend, void* __restrict__ y,
                                                               const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // kPair: the CTA pair computes (2 pixel tiles) x (block_n = 256 channels); this CTA stages its own pixel tile and 128 of the 256
+    // weight rows, and owns the accumulator rows of its pixel tile.
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const int b_rows = kPair ? p.block_n / 2 : p.block_n;        // weight rows staged by this CTA
     const int a_bytes = kBlockM * p.block_k * 2;
     const int b_off = p.m_sub * a_bytes;
-    const int stage_bytes = (b_off + p.block_n * p.block_k * 2 + 1023) & ~1023;
+    const int stage_bytes = (b_off + b_rows * p.block_k * 2 + 1023) & ~1023;
     uint8_t* staging = smem + p.stages * stage_bytes;
     float* bias_all = (float*)(staging + 2 * p.n_staging * kBoxBytes);        // 256 floats per epilogue group
     uint64_t* full_bar = (uint64_t*)(bias_all + 512);
@@ -356,7 +413,8 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
     const int num_kb = p.ks * p.ks * kc_per_tap;
     const int n_tiles = (p.cout + p.block_n - 1) / p.block_n;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int total_tiles = ((m_tiles + p.m_sub - 1) / p.m_sub) * n_tiles;
+    const int total_tiles = ((m_tiles + (kPair ? 2 : p.m_sub) - 1) / (kPair ? 2 : p.m_sub)) * n_tiles;
+    const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t buf_cols = (uint32_t)(p.m_sub * p.block_n);
     const uint32_t tmem_cols = 2u * buf_cols < 32u ? 32u : 2u * buf_cols;    // power of two by construction
 
@@ -365,12 +423,14 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_y);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // two producers: A (warp 0), B (warp 2)
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], kPair ? 16 : 8); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 1) {
+        if (kPair) tmem_alloc_2sm(tmem_slot, tmem_cols); else tmem_alloc(tmem_slot, tmem_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();      // the peer must not signal barriers that are not initialised yet
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -381,28 +441,35 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             const bool is_a = warp == 0;
             int s = 0;
             uint32_t ph = 1;                                  // parity to wait for on empty[s]: the first pass over the ring is free
-            const uint32_t tx_bytes = is_a ? (uint32_t)b_off : (uint32_t)(p.block_n * p.block_k * 2);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            // pair mode: the leader arms its barrier for both CTAs' bytes; the peer's loads complete on the leader's barrier
+            const uint32_t tx_bytes = (is_a ? (uint32_t)b_off : (uint32_t)(b_rows * p.block_k * 2)) * (kPair ? 2u : 1u);
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int mt = tile / n_tiles;
                 const int n0 = (tile - mt * n_tiles) * p.block_n;
                 int w0[2], h0[2], img0[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    int t = mt * p.m_sub + j;
+                    int t = kPair ? mt * 2 + (int)rank : mt * p.m_sub + j;
                     const int tw = t % p.tiles_w; t /= p.tiles_w;
                     const int th = t % p.tiles_h; t /= p.tiles_h;
                     w0[j] = tw * p.bw - pad; h0[j] = th * p.bh - pad; img0[j] = t * p.bn;      // beyond the last tile: img0 >= n, TMA zero-fills
                 }
-                int tap_row = n0, kc = 0, r = 0, q = 0;
+                int tap_row = n0 + (int)rank * b_rows, kc = 0, r = 0, q = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph);
                     uint8_t* sa = smem + s * stage_bytes;
-                    mbar_expect_tx(&full_bar[s], tx_bytes);
-                    if (is_a) {
-                        tma_load_4d(sa, &map_x, &full_bar[s], kc, w0[0] + q, h0[0] + r, img0[0]);
-                        if (p.m_sub == 2) tma_load_4d(sa + a_bytes, &map_x, &full_bar[s], kc, w0[1] + q, h0[1] + r, img0[1]);
+                    if (kPair) {
+                        if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
+                        if (is_a) tma_load_4d_2sm(sa, &map_x, &full_bar[s], kc, w0[0] + q, h0[0] + r, img0[0]);
+                        else tma_load_2d_2sm(sa + b_off, &map_w, &full_bar[s], kc, tap_row);
                     } else {
-                        tma_load_2d(sa + b_off, &map_w, &full_bar[s], kc, tap_row);
+                        mbar_expect_tx(&full_bar[s], tx_bytes);
+                        if (is_a) {
+                            tma_load_4d(sa, &map_x, &full_bar[s], kc, w0[0] + q, h0[0] + r, img0[0]);
+                            if (p.m_sub == 2) tma_load_4d(sa + a_bytes, &map_x, &full_bar[s], kc, w0[1] + q, h0[1] + r, img0[1]);
+                        } else {
+                            tma_load_2d(sa + b_off, &map_w, &full_bar[s], kc, tap_row);
+                        }
                     }
                     kc += p.block_k;
                     if (kc >= p.cin) { kc = 0; tap_row += p.cout; if (++q == p.ks) { q = 0; ++r; } }
@@ -411,8 +478,8 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 0, 0);
+        if (lane == 0 && rank == 0) {                    // pair mode: the leader CTA issues the MMAs of both CTAs
+            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 0, 0, kPair ? 256u : 128u);
             // descriptors differ between stages only in the 14-bit start-address field: build them once
             const bool k64 = p.block_k == 64;
             const uint32_t s0 = smem_u32(smem);
@@ -423,7 +490,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             int s = 0;
             uint32_t ph = 0, i = 0;
             uint64_t da = desc_a0, db = desc_b0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++i) {
                 const uint32_t buf = i & 1;
                 mbar_wait(&tmem_empty_bar[buf], ((i >> 1) & 1) ^ 1);          // epilogue has drained this accumulator pair
                 tc_fence_after();
@@ -433,21 +500,27 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t acc = kb != 0 ? 1u : 0u;
-                    if (k64) {
+                    if (kPair) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {                          // +32 B along K inside the 128-byte swizzle row
-                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
-                            if (two) umma_bf16(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
-                        }
+                        for (int k = 0; k < 4; ++k) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                        umma_commit_2sm(&empty_bar[s]);                        // frees this smem slot in both CTAs
                     } else {
-                        umma_bf16(tmem_d, da, db, idesc, acc);
-                        if (two) umma_bf16(tmem_d1, da + a_step, db, idesc, acc);
+                        if (k64) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {                      // +32 B along K inside the 128-byte swizzle row
+                                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                if (two) umma_bf16(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                            }
+                        } else {
+                            umma_bf16(tmem_d, da, db, idesc, acc);
+                            if (two) umma_bf16(tmem_d1, da + a_step, db, idesc, acc);
+                        }
+                        umma_commit(&empty_bar[s]);
                     }
-                    umma_commit(&empty_bar[s]);
                     da += stage_step; db += stage_step;
                     if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
                 }
-                umma_commit(&tmem_full_bar[buf]);
+                if (kPair) umma_commit_2sm(&tmem_full_bar[buf]); else umma_commit(&tmem_full_bar[buf]);
             }
         }
     } else if (warp >= 4) {
@@ -468,7 +541,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
         const int cols_per_chunk = p.out_f32 ? 32 : 64;
         uint32_t i = 0;
         int sbuf = 0;                                    // staging box of the current chunk (ring of p.n_staging)
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+        for (int tile = tile0; tile < total_tiles; tile += tile_step, ++i) {
             const int mt = tile / n_tiles;
             const int n0 = (tile - mt * n_tiles) * p.block_n;
             const uint32_t buf = i & 1;
@@ -481,7 +554,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             mbar_wait(&tmem_full_bar[buf], (i >> 1) & 1);
             tc_fence_after();
             for (int sub = 0; sub < p.m_sub; ++sub) {
-                int t = mt * p.m_sub + sub;
+                int t = kPair ? mt * 2 + (int)rank : mt * p.m_sub + sub;
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 const int w0 = tw * p.bw, h0 = th * p.bh, img0 = t * p.bn;
@@ -608,15 +681,18 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             // every TMEM read of this macro tile by this warp has completed (wait::ld): hand the accumulator buffer back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[buf])) : "memory");
+            if (lane == 0) {
+                if (kPair) mbar_arrive_leader(&tmem_empty_bar[buf]);
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[buf])) : "memory");
+            }
         }
         if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();      // nobody may still address the peer's barriers / TMEM / smem
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
+        if (kPair) tmem_dealloc_2sm(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -756,15 +832,17 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     const bool v2 = !use_v1 && pick_block_n(cout) >= 32 && (!tiny || force_v2);
     if (!v2 && epi != 0) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: fused epilogues need cout >= 32");
     p.block_n = v2 ? pick_block_n2(cout, m_tiles) : pick_block_n(cout);
-    static const int force_msub = env_int("GIM_CONV_MSUB", 0);
+    static const int force_msub = env_int("GIM_CONV_MSUB", 0), pair_mode = env_int("GIM_CONV_PAIR", 1);
     p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;
     if (force_msub == 1 || (force_msub == 2 && v2 && p.block_n <= 128)) p.m_sub = force_msub;
-    const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2 + 1023) & ~1023;
+    // cta_group::2: pairs of CTAs share one 256 x 256 MMA tile, each staging half of the weight tile
+    p.pair = (v2 && pair_mode && p.block_n == 256 && p.block_k == 64 && m_tiles >= 2) ? 1 : 0;
+    const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + (p.pair ? p.block_n / 2 : p.block_n) * p.block_k * 2 + 1023) & ~1023;
     if (epi & kEpiPool) {
         if (!make_out_map(&map_y, y, n, h / 2, wd / 2, cout, p.bw / 2, p.bh / 2, p.bn, 1)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(pooled y) failed");
     } else if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
     if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn, p.block_k)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
-    if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.block_n, p.block_k))
+    if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.pair ? p.block_n / 2 : p.block_n, p.block_k))
         return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
     if (v2) {
         static const int env_nb = env_int("GIM_CONV_NSTAGING", 0), env_stages = env_int("GIM_CONV_STAGES", 0);
@@ -782,6 +860,29 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
             if (cudaFuncSetAttribute(conv_fwd_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
                 return fail(GIM_E_CUDA, "conv_fwd_tc: cannot raise dynamic shared memory limit");
             attr_set2 = true;
+        }
+        if (p.pair) {
+            static bool attr_set3 = false;
+            if (!attr_set3) {
+                if (cudaFuncSetAttribute(conv_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                    return fail(GIM_E_CUDA, "conv_fwd_tc: cannot raise dynamic shared memory limit");
+                attr_set3 = true;
+            }
+            const long long pairs = ((m_tiles + 1) / 2) * (cout / p.block_n);
+            const long long max_pairs = num_sms() / 2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
+            cfg.blockDim = dim3(384);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, conv_fwd_tc2_kernel<1>, map_x, map_w, map_y, bias, (const bf16*)mask_ref, addend, y, p) != cudaSuccess)
+                return fail(GIM_E_CUDA, "conv_fwd_tc: cluster launch failed");
+            return check_launch("conv_fwd_tc2_pair");
         }
         const long long total = ((m_tiles + p.m_sub - 1) / p.m_sub) * ((cout + p.block_n - 1) / p.block_n);
         const int grid = (int)(total < num_sms() ? total : num_sms());
