@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
     const int num_kb = p.ks * p.ks * kc_per_tap;
     const int n_tiles = (p.cout + p.block_n - 1) / p.block_n;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int total_tiles = ((m_tiles + (kPair ? 2 : p.m_sub) - 1) / (kPair ? 2 : p.m_sub)) * n_tiles;
+    const int m_per_tile = (kPair ? 2 : 1) * p.m_sub;              // pixel tiles per (pair-)tile
+    const int total_tiles = ((m_tiles + m_per_tile - 1) / m_per_tile) * n_tiles;
     const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t buf_cols = (uint32_t)(p.m_sub * p.block_n);
     const uint32_t tmem_cols = 2u * buf_cols < 32u ? 32u : 2u * buf_cols;    // power of two by construction
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                 int w0[2], h0[2], img0[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    int t = kPair ? mt * 2 + (int)rank : mt * p.m_sub + j;
+                    int t = (kPair ? mt * 2 + (int)rank : mt) * p.m_sub + j;
                     const int tw = t % p.tiles_w; t /= p.tiles_w;
                     const int th = t % p.tiles_h; t /= p.tiles_h;
                     w0[j] = tw * p.bw - pad; h0[j] = th * p.bh - pad; img0[j] = t * p.bn;      // beyond the last tile: img0 >= n, TMA zero-fills
@@ -460,8 +461,12 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                     uint8_t* sa = smem + s * stage_bytes;
                     if (kPair) {
                         if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
-                        if (is_a) tma_load_4d_2sm(sa, &map_x, &full_bar[s], kc, w0[0] + q, h0[0] + r, img0[0]);
-                        else tma_load_2d_2sm(sa + b_off, &map_w, &full_bar[s], kc, tap_row);
+                        if (is_a) {
+                            tma_load_4d_2sm(sa, &map_x, &full_bar[s], kc, w0[0] + q, h0[0] + r, img0[0]);
+                            if (p.m_sub == 2) tma_load_4d_2sm(sa + a_bytes, &map_x, &full_bar[s], kc, w0[1] + q, h0[1] + r, img0[1]);
+                        } else {
+                            tma_load_2d_2sm(sa + b_off, &map_w, &full_bar[s], kc, tap_row);
+                        }
                     } else {
                         mbar_expect_tx(&full_bar[s], tx_bytes);
                         if (is_a) {
@@ -502,7 +507,10 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                     const uint32_t acc = kb != 0 ? 1u : 0u;
                     if (kPair) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                            if (two) umma_bf16_2sm(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                        }
                         umma_commit_2sm(&empty_bar[s]);                        // frees this smem slot in both CTAs
                     } else {
                         if (k64) {
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             mbar_wait(&tmem_full_bar[buf], (i >> 1) & 1);
             tc_fence_after();
             for (int sub = 0; sub < p.m_sub; ++sub) {
-                int t = kPair ? mt * 2 + (int)rank : mt * p.m_sub + sub;
+                int t = (kPair ? mt * 2 + (int)rank : mt) * p.m_sub + sub;
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 const int w0 = tw * p.bw, h0 = th * p.bh, img0 = t * p.bn;
@@ -836,7 +844,8 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;
     if (force_msub == 1 || (force_msub == 2 && v2 && p.block_n <= 128)) p.m_sub = force_msub;
     // cta_group::2: pairs of CTAs share one 256 x 256 MMA tile, each staging half of the weight tile
-    p.pair = (v2 && pair_mode && p.block_n == 256 && p.block_k == 64 && m_tiles >= 2) ? 1 : 0;
+    p.pair = (v2 && pair_mode && p.block_k == 64 && m_tiles >= 2 &&
+              (p.block_n == 256 || (p.block_n == 128 && p.m_sub == 2 && cout % 128 == 0 && pair_mode > 1))) ? 1 : 0;
     const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + (p.pair ? p.block_n / 2 : p.block_n) * p.block_k * 2 + 1023) & ~1023;
     if (epi & kEpiPool) {
         if (!make_out_map(&map_y, y, n, h / 2, wd / 2, cout, p.bw / 2, p.bh / 2, p.bn, 1)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(pooled y) failed");
@@ -868,7 +877,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
                     return fail(GIM_E_CUDA, "conv_fwd_tc: cannot raise dynamic shared memory limit");
                 attr_set3 = true;
             }
-            const long long pairs = ((m_tiles + 1) / 2) * (cout / p.block_n);
+            const long long pairs = ((m_tiles + 2 * p.m_sub - 1) / (2 * p.m_sub)) * (cout / p.block_n);
             const long long max_pairs = num_sms() / 2;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
