@@ -246,10 +246,10 @@ class GIMFaceAuthenticator(nn.Module, _EncodeMixin):
         self.dis = dis
 
     def forward(self, test_sample, si_sample):
-        test_src = self.src_encode_sample(test_sample)
-        si_src = self.src_encode_sample(si_sample)
-        test_env = self.env_encode_sample(test_sample)
-        si_env = self.env_encode_sample(si_sample)
+        # same call order per encoder as the reference (src: test, si; env: test, si); the two encoders are independent -> two streams
+        (test_src, si_src), (test_env, si_env) = ops.two_streams(
+            lambda: (self.src_encode_sample(test_sample), self.src_encode_sample(si_sample)),
+            lambda: (self.env_encode_sample(test_sample), self.env_encode_sample(si_sample)))
         return self.dis(test_src=test_src, test_env=test_env, si_src=si_src, si_env=si_env)
 
 
@@ -272,8 +272,8 @@ class GIMFaceImpersonator(nn.Module, _EncodeMixin):
         batch_size, m, img_channels, img_size, _ = leaked_sample.size()
         expanded_img = leaked_sample[:, 0].unsqueeze(1).expand(-1, n, -1, -1, -1)
 
-        src = ops.set_mean(self.src_encode_sample(leaked_sample))
-        env = ops.set_mean(self.env_encode_sample(leaked_sample))
+        src, env = ops.two_streams(lambda: ops.set_mean(self.src_encode_sample(leaked_sample)),
+                                   lambda: ops.set_mean(self.env_encode_sample(leaked_sample)))
 
         z = torch.randn((batch_size, n, self.style_dim), device=leaked_sample.device)
         w = self.env_noise_mapper(z)

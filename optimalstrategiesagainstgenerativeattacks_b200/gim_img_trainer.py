@@ -85,13 +85,14 @@ class GIMImgTrainer(nn.Module):
             si_sample.requires_grad_()
         au = self.authenticator
         # the R1 penalty differentiates the real/si branch twice: run it with the elementary (twice differentiable) operators
-        with (ops.composite_mode() if (grad and self.reg_param > 0) else contextlib.nullcontext()):
-            au_si_src = au.src_encode_sample(si_sample)
-            au_si_env = au.env_encode_sample(si_sample)
-            au_real_src = au.src_encode_sample(real_sample)
-            au_real_env = au.env_encode_sample(real_sample)
-        au_fake_src = au.src_encode_sample(fake_sample)
-        au_fake_env = au.env_encode_sample(fake_sample)
+        # (per encoder the call order is the reference's: si, real, fake; the src and env encoders are independent -> two streams)
+        def branch(encode):
+            with (ops.composite_mode() if (grad and self.reg_param > 0) else contextlib.nullcontext()):
+                e_si = encode(si_sample)
+                e_real = encode(real_sample)
+            return e_si, e_real, encode(fake_sample)
+        (au_si_src, au_real_src, au_fake_src), (au_si_env, au_real_env, au_fake_env) = ops.two_streams(
+            lambda: branch(au.src_encode_sample), lambda: branch(au.env_encode_sample))
 
         out_on_real = au.dis(test_src=au_real_src, test_env=au_real_env, si_src=au_si_src, si_env=au_si_env)
         loss_on_real = self.gan_loss(dis_out=out_on_real, target=1.)

@@ -79,6 +79,39 @@ def fused_blocks_enabled():
     return _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and not _state["composite"]
 
 
+# ---- two-branch stream parallelism ------------------------------------------------------------------------------------
+_side = {"stream": None, "enabled": True, "used": False}
+
+
+def set_stream_parallelism(flag):
+    _side["enabled"] = bool(flag)
+
+
+def two_streams(fn_main, fn_side):
+    """Run two independent branches (the src and env encoders see the same images) on two CUDA streams: -> (fn_main(), fn_side()).
+    Inside a captured CUDA graph the branches become parallel graph branches, so one branch's kernels fill the tail waves and launch
+    gaps of the other.  Autograd replays each branch's backward on the stream its forward ran on.  Results are identical to running
+    the branches one after the other (they share no state)."""
+    if not (_side["enabled"] and torch.cuda.is_available()):
+        return fn_main(), fn_side()
+    cur = torch.cuda.current_stream()
+    if _side["stream"] is None or _side["stream"].device != cur.device:
+        _side["stream"] = torch.cuda.Stream(device=cur.device)
+    side = _side["stream"]
+    if side == cur:                                       # nested use from inside the side branch
+        return fn_main(), fn_side()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        b = fn_side()
+    a = fn_main()
+    cur.wait_stream(side)
+    _side["used"] = True
+    for t in (b if isinstance(b, (tuple, list)) else (b,)):
+        if torch.is_tensor(t):
+            t.record_stream(cur)
+    return a, b
+
+
 def _empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
@@ -611,6 +644,13 @@ def _flush_sn_backward():
         while len(rounds) <= r:
             rounds.append([])
         rounds[r].append(item)
+    if _side["used"] and _side["stream"] is not None:
+        # gradients produced by the side branch's backward: order this stream after it, and keep their memory until the flush is done
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(_side["stream"])
+        for _, g, aux, _ in pending:
+            g.record_stream(cur)
+            aux.record_stream(cur)
     with torch.no_grad():
         for items in rounds:
             scratch = torch.empty(len(items), dtype=torch.float32, device=items[0][1].device)
