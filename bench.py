@@ -302,6 +302,18 @@ def run_ours(args):
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "bf16_tflops_sustained of MEASURED_PEAKS.json" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/, tools/ncu_summarize.py): per launch,
+    # for the layer shape that takes most of its time in this workload (128->128 3x3 @32x32 over B*5 = 640 images)
+    traffic, traffic_note = None, None
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_conv_shapes_r01.json")))
+        top = ncu["fwd_32x32_128_128_k3"]
+        if args.workload == "O" and B == 128:
+            traffic = top["dram_bytes_read"] + top["dram_bytes_write"]
+            traffic_note = ("per launch of the 128->128 3x3 @32x32 layer (640 images): algorithmic %.1f MB, ncu tensor-pipe active %.1f %%, "
+                            "%.0f us under ncu" % (top["algorithmic_bytes"] / 1e6, top["tensor_pipe_active_pct"], top["duration_us"]))
+    except Exception:
+        pass
     tc = prof.get("tcgen05", {"flops": 0.0, "ms": 0.0, "launches": 0})
     achieved = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
     total_conv_ms = sum(v["ms"] for v in prof.values())
@@ -319,8 +331,8 @@ def run_ours(args):
         "e2e": {"value": eps_e2e, "unit": "episodes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_fwd_tc_kernel (tcgen05 implicit GEMM: conv forward + input-gradient)",
-                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": "conv_fwd_tc2_kernel / conv_fwd_tc_kernel (tcgen05 implicit GEMM: conv forward + input-gradient)",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": peak_src, "launches_per_step": tc["launches"], "kernel_ms_per_step": tc["ms"],
                      "share_of_step": tc["ms"] / (ms_total / args.steps) if ms_total else None,
                      "other_conv_kernels_ms_per_step": {k: v["ms"] for k, v in prof.items() if k != "tcgen05"},
