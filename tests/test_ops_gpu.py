@@ -58,6 +58,7 @@ def unpack_w(gw, k):
 CONV_SHAPES = [  # n, ci, co, k, h, w
     (2, 3, 64, 3, 16, 16), (3, 64, 64, 3, 8, 8), (2, 6, 64, 9, 16, 16), (2, 64, 3, 9, 16, 16), (2, 64, 16, 1, 7, 5),
     (1, 1, 128, 3, 32, 32), (5, 128, 128, 3, 4, 4), (2, 64, 128, 3, 13, 13), (130, 32, 8, 1, 1, 1), (3, 64, 40, 3, 9, 7), (200, 72, 1000, 1, 1, 1),
+    (4, 64, 256, 3, 16, 16), (9, 128, 512, 1, 8, 8),          # 256-wide N tiles: the cta_group::2 (two-CTA cluster) kernel variant
 ]
 
 
