@@ -53,11 +53,14 @@ int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y,
  *   epilogue & GIM_EPI_ADD   : v = v + addend[n,h,w,co]                       (addend: fp32, same shape as y, may alias y; cout % 32 == 0)
  *   epilogue & GIM_EPI_POOL  : y[n,h/2,w/2,co] = AvgPool2d(2)(conv) + bias (+ addend[n,h/2,w/2,co] with GIM_EPI_ADD): the ResBlockDown tail
  *                              (model_blocks.py:510-514) without the full-resolution tensor ever reaching HBM; even h, w; fp32 y
+ *   epilogue & GIM_EPI_ADDUP : v = v + 0.25 * addend[n,h/2,w/2,co]  (fp32 half-resolution addend: the AvgPool backward of a gradient that was
+ *                              propagated at the pooled resolution -- a 1x1 convolution commutes with the pooling; even h, w; cout % 32 == 0)
  * y: out_dtype (fp32 or bf16). */
 #define GIM_EPI_LRELU 1
 #define GIM_EPI_MASK  2
 #define GIM_EPI_ADD   4
 #define GIM_EPI_POOL  8
+#define GIM_EPI_ADDUP 16
 int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* y, const void* mask_ref, const float* addend,
                          int n, int h, int wd, int cin, int cout, int ksize, int out_dtype, int epilogue, float slope, gim_stream_t stream);
 /* gw[t][co][ci] (fp32) = sum_{n,h,w} gy[n,h,w,co] * x[n,h+r-p,w+s-p,ci]  (overwrites gw) */

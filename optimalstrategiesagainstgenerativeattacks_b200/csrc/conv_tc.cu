@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
 //   rotating staging buffers) runs while the MMA warp already accumulates tile i+1; the TMA/MMA smem ring never drains between
 //   tiles.  Fused epilogues: + bias, LeakyReLU, LeakyReLU-backward mask taken from a saved bf16 operand, fp32 or bf16 output.
 // ----------------------------------------------------------------------------------------------------------------
-enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4, kEpiPool = 8 };
+enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4, kEpiPool = 8, kEpiAddUp = 16 };
 constexpr int kBoxBytes = kBlockM * 128;                   // one staged output box: 128 rows x 128 B
 
 // A macro tile = m_sub (1 or 2) consecutive 128-pixel tiles x one block_n-wide channel tile.  With m_sub = 2 the two pixel tiles
@@ -633,6 +633,17 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                                 }
                             }
                         }
+                        if (p.epi & kEpiAddUp) {                  // + 0.25 * addend[n, h/2, w/2, :]: the AvgPool backward of a half-resolution gradient
+                            if (valid && n0 + cb < p.cout) {
+                                const long long ppix = ((long long)img * (p.h >> 1) + (hh >> 1)) * (p.w >> 1) + (ww >> 1);
+                                const float4* ad = reinterpret_cast<const float4*>(addend + ppix * p.cout + n0 + cb);
+#pragma unroll
+                                for (int v4 = 0; v4 < 8; ++v4) {
+                                    const float4 t4 = __ldg(ad + v4);
+                                    f[4 * v4] += 0.25f * t4.x; f[4 * v4 + 1] += 0.25f * t4.y; f[4 * v4 + 2] += 0.25f * t4.z; f[4 * v4 + 3] += 0.25f * t4.w;
+                                }
+                            }
+                        }
                         if (p.epi & kEpiAdd) {
                             if (valid && n0 + cb < p.cout) {
                                 const float4* ad = reinterpret_cast<const float4*>(addend + pix * p.cout + n0 + cb);
@@ -831,7 +842,8 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     if (m_tiles > 2147483647LL / 64) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
     if ((epi & kEpiMask) && (!mask_ref || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the mask epilogue needs a reference tensor and cout % 32 == 0");
-    if ((epi & kEpiAdd) && (!addend || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the add epilogue needs an addend tensor and cout % 32 == 0");
+    if ((epi & (kEpiAdd | kEpiAddUp)) && (!addend || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the add epilogue needs an addend tensor and cout % 32 == 0");
+    if ((epi & kEpiAddUp) && ((epi & (kEpiAdd | kEpiPool)) || (h & 1) || (wd & 1))) return fail(GIM_E_ARG, "conv_fwd_tc: add-upsampled needs even h, w and excludes add / pool");
     CUtensorMap map_x, map_w, map_y;
     static const int force_v2 = env_int("GIM_CONV_V2", 0);
     // measured (tools/conv_bench.py): the persistent kernel wins whenever it can use the 256-wide N tile; with 128-wide tiles two

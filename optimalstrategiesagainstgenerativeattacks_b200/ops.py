@@ -421,7 +421,7 @@ class RowBroadcastFn(Function):
 # ------------------------------------------------------------------------------------------------------------
 # block-level fused operators (bf16 tensor-core path, first order)
 # ------------------------------------------------------------------------------------------------------------
-EPI_LRELU, EPI_MASK, EPI_ADD, EPI_POOL = 1, 2, 4, 8
+EPI_LRELU, EPI_MASK, EPI_ADD, EPI_POOL, EPI_ADDUP = 1, 2, 4, 8, 16
 
 
 class Act:
@@ -465,34 +465,44 @@ def _colsum(x):
 
 class ResBlockDownFn(Function):
     """AvgPool2(conv1x1(x)) + AvgPool2(conv_k(lrelu(conv_k(lrelu(x)))))  (reference model_blocks.py:486-514) as ONE autograd node:
-    the activation between the two k x k convs only exists as the bf16 LeakyReLU'd operand written by the first conv's epilogue,
-    the pooled output is written once together with the operands of the next block, and in the backward the AvgPool gradient, the
-    LeakyReLU masks and the residual sum are folded into the producing kernels' epilogues.  First order only (see composite_mode)."""
+    * the 1x1 residual convolution commutes with the pooling, AvgPool2(conv1x1(x)) == conv1x1(AvgPool2(x)), so it runs at the pooled
+      resolution on both passes (4x fewer FLOPs and bytes; the same identity the up-sampling blocks use);
+    * the activation between the two k x k convs only exists as the bf16 LeakyReLU'd operand written by the first conv's epilogue;
+    * AvgPool + residual add happen inside the second conv's epilogue, the pooled output is written once;
+    * in the backward the AvgPool gradient, the LeakyReLU masks and the residual-gradient sum are folded into the producing kernels'
+      epilogues.
+    First order only (see composite_mode).  Odd spatial sizes use the unfused pooling kernels."""
 
     @staticmethod
     def forward(ctx, x32, xb, xl, wl, bl, w1, b1, w2, b2, ks, slope, want_ops):
         od = torch.bfloat16
         x32 = _c(x32)
-        if xb is None:
-            xb = _operand(x32)
+        n, h, w, ci = x32.shape
         if xl is None:
             xl = _prepare_operand(x32, PRE_LRELU, slope)
-        n, h, w, ci = xb.shape
         wl_t, w1_t, w2_t = _weight_as(_c(wl), od, False), _weight_as(_c(w1), od, False), _weight_as(_c(w2), od, False)
+        co = w2_t.shape[1]
         skinny = ci % 8 != 0
+        even = h % 2 == 0 and w % 2 == 0
         if skinny:
-            xa, wl_e = _skinny_in(xb, wl_t, 1)
             xr, w1_e = _skinny_in(xl, w1_t, ks)
             k1 = 1
         else:
-            xa, wl_e, xr, w1_e, k1 = xb, wl_t, xl, w1_t, ks
-        co = w2_t.shape[1]
+            xr, w1_e, k1 = xl, w1_t, ks
         od_out = (n, h // 2, w // 2, co)
-        if h % 2 == 0 and w % 2 == 0:
-            # AvgPool inside the conv epilogues: neither full-resolution fp32 tensor reaches HBM
-            y32 = _conv_tc_fused(xa, wl_e, bl, 1, torch.float32, EPI_POOL, out=_empty(od_out, torch.float32, xa))
+        if even:
+            # residual branch at the pooled resolution: xp = bf16(AvgPool2(x))
+            if ci % 4 == 0:
+                xp = _empty((n, h // 2, w // 2, ci), od, x32)
+                C.call("gim_pool2_multi", C.ptr(x32), None, None, C.ptr(xp), None, n, h, w, ci, 0.25, slope)
+            else:
+                xp32 = _empty((n, h // 2, w // 2, ci), torch.float32, x32)
+                C.call("gim_pool2_sum", C.ptr(x32), None, C.ptr(xp32), n, h, w, ci, 0.25, C.F32)
+                xp = _operand(xp32)
+            xa, wl_e = _skinny_in(xp, wl_t, 1) if skinny else (xp, wl_t)
+            y32 = _conv_tc_fused(xa, wl_e, bl, 1, torch.float32)
             tl = _conv_tc_fused(xr, w1_e, b1, k1, od, EPI_LRELU, slope)
-            _conv_tc_fused(tl, w2_t, b2, ks, torch.float32, EPI_POOL | EPI_ADD, addend=y32, out=y32)
+            _conv_tc_fused(tl, w2_t, b2, ks, torch.float32, EPI_POOL | EPI_ADD, addend=y32, out=y32)      # AvgPool + residual in the epilogue
             yb = yl = None
             if want_ops:
                 yb = torch.empty_like(y32, dtype=od)
@@ -500,6 +510,9 @@ class ResBlockDownFn(Function):
                 C.call("gim_cast", C.ptr(y32), C.F32, C.ptr(yb), C.BF16, y32.numel())
                 C.call("gim_operand_prepare", C.ptr(y32), C.F32, C.ptr(yl), C.BF16, n, h // 2, w // 2, co, PRE_LRELU, slope)
         else:
+            if xb is None:
+                xb = _operand(x32)
+            xa, wl_e = _skinny_in(xb, wl_t, 1) if skinny else (xb, wl_t)
             res = _conv_tc_fused(xa, wl_e, bl, 1, torch.float32)
             tl = _conv_tc_fused(xr, w1_e, b1, k1, od, EPI_LRELU, slope)
             o = _conv_tc_fused(tl, w2_t, b2, ks, torch.float32)
@@ -507,8 +520,9 @@ class ResBlockDownFn(Function):
             yb = torch.empty_like(y32, dtype=od) if want_ops else None
             yl = torch.empty_like(y32, dtype=od) if want_ops else None
             C.call("gim_pool2_multi", C.ptr(res), C.ptr(o), C.ptr(y32), C.ptr(yb), C.ptr(yl), n, h, w, co, 0.25, slope)
-        ctx.cfg = (ks, slope, skinny, (n, h, w, ci, co), want_ops)
+        ctx.cfg = (ks, slope, skinny, even, (n, h, w, ci, co), want_ops)
         ctx.save_for_backward(xa, xr, xl, tl, wl, w1, w2)
+        ctx.biases = (bl, b1, b2)
         if want_ops:
             ctx.mark_non_differentiable(yb, yl)
             return y32, yb, yl
@@ -518,17 +532,18 @@ class ResBlockDownFn(Function):
     @once_differentiable
     def backward(ctx, gy, _gb, _gl):
         xa, xr, xl, tl, wl, w1, w2 = ctx.saved_tensors
-        ks, slope, skinny, (n, h, w, ci, co), _ = ctx.cfg
+        ks, slope, skinny, even, (n, h, w, ci, co), _ = ctx.cfg
         od = torch.bfloat16
         taps = ks * ks
         gy = _c(gy)
         g = _empty((n, h, w, co), od, gy)                      # AvgPool backward, written once as the bf16 operand
         C.call("gim_unpool2_cast", C.ptr(gy), C.ptr(g), n, h, w, co, 0.25)
+        gl = _operand(gy) if even else g                       # gradient of the residual branch: at the pooled resolution when it ran there
         gt = _conv_tc_fused(g, _weight_as(w2, od, True), None, ks, od, EPI_MASK, slope, mask_ref=tl)      # d/d(conv_r1 output), masked
         gwl = gbl = gw1 = gb1 = gw2 = gb2 = None
         want_w = not _state["input_grads_only"]
         if want_w and ctx.needs_input_grad[3]:
-            gwl = _wgrad_raw(xa, g, 1)
+            gwl = _wgrad_raw(xa, gl, 1)
             if skinny:
                 gwl = _unskinny_gw(gwl, 1, co, ci)
         if want_w and ctx.needs_input_grad[7]:
@@ -544,10 +559,17 @@ class ResBlockDownFn(Function):
         gx = None
         if ctx.needs_input_grad[0]:
             if not skinny and ci % 32 == 0:
-                gx = _conv_tc_fused(g, _weight_as(wl, od, True), None, 1, torch.float32)
-                _conv_tc_fused(gt, _weight_as(w1, od, True), None, ks, torch.float32, EPI_MASK | EPI_ADD, slope, mask_ref=xl, addend=gx, out=gx)
+                gx1 = _conv_tc_fused(gl, _weight_as(wl, od, True), None, 1, torch.float32)          # pooled resolution when `even`
+                if even:
+                    gx = _conv_tc_fused(gt, _weight_as(w1, od, True), None, ks, torch.float32, EPI_MASK | EPI_ADDUP, slope, mask_ref=xl, addend=gx1)
+                else:
+                    gx = _conv_tc_fused(gt, _weight_as(w1, od, True), None, ks, torch.float32, EPI_MASK | EPI_ADD, slope, mask_ref=xl, addend=gx1, out=gx1)
             else:                                                  # image-side block: few channels, elementary kernels
-                gx = _conv_raw(g, _weight_as(wl, od, True), None, 1)
+                gx = _conv_raw(gl, _weight_as(wl, od, True), None, 1)
+                if even:
+                    up = _empty((n, h, w, ci), torch.float32, gx)
+                    C.call("gim_unpool2_bcast", C.ptr(gx), C.ptr(up), n, h, w, ci, 0.25, C.F32)
+                    gx = up
                 g2 = _conv_raw(gt, _weight_as(w1, od, True), None, ks)
                 gm = torch.empty_like(g2)
                 C.call("gim_lrelu_bwd_ref", C.ptr(g2), C.ptr(xl), C.dtype_code(xl), C.ptr(gm), g2.numel(), slope)

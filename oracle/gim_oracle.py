@@ -171,7 +171,12 @@ def mlp(p, prefix, x, n_layers):
 def res_block_down(p, prefix, x, ksize=3, training=True):
     """ResBlockDown model_blocks.py:497-514."""
     pad = (ksize - 1) // 2
-    left = avg_pool2(sn_conv(p, prefix + ".conv_l1", x, 0, training))
+    if OPERAND_BF16 and x.shape[-1] % 2 == 0 and x.shape[-2] % 2 == 0:
+        # emulation of the build's bf16 numerics only: its fused block runs the 1x1 residual conv AFTER the pooling (the same value in
+        # exact arithmetic: a 1x1 convolution commutes with AvgPool), so the bf16 operand rounding falls on AvgPool(x) instead of x
+        left = sn_conv(p, prefix + ".conv_l1", avg_pool2(x), 0, training)
+    else:
+        left = avg_pool2(sn_conv(p, prefix + ".conv_l1", x, 0, training))
     out = sn_conv(p, prefix + ".conv_r1", lrelu(x), pad, training)
     out = sn_conv(p, prefix + ".conv_r2", lrelu(out), pad, training)
     return left + avg_pool2(out)

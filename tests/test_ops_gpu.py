@@ -413,7 +413,8 @@ def test_res_block_down_fused(shape):
     yf, gf = run(True)
     yc, gc = run(False)
     assert rel_err(nchw(yf), y64) < BF16_TOL
-    assert rel_err(yf, yc) < 1e-5                         # same operand roundings: the fused block is the same arithmetic
+    # same arithmetic except that the fused residual branch rounds AvgPool(x) instead of x to bf16 (the 1x1 conv runs after the pooling)
+    assert rel_err(yf, yc) < 3e-3
     names = ["x", "w_l1", "w_r1", "w_r2", "b_l1", "b_r1", "b_r2"]
     for i, nm in enumerate(names):
         a, c, r = gf[i], gc[i], ref[i]
