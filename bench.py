@@ -282,10 +282,12 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
 
     # dominant-kernel roofline: one extra iteration with CUDA events around every tensor-core conv launch
+    ops.set_stream_parallelism(False)             # one stream: a bracketed launch must not share the GPU with the other encoder branch
     ops.conv_profile_begin()
     iteration(*dev_pool[0])                       # eager, so that events can bracket each launch
     torch.cuda.synchronize()
     prof = ops.conv_profile_end()
+    ops.set_stream_parallelism(True)
     shapes = prof.pop("_shapes", {})
     if rank == 0 and os.environ.get("GIM_PROFILE_SHAPES"):
         for key, (fl, ms, cnt) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:40]:
