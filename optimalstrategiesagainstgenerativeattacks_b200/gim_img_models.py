@@ -138,9 +138,9 @@ class Img2ImgAdaInResModule(nn.Module):
         for i in range(self.n_blocks):
             self.res_blocks.append(mb.AdaResBlock2(channels=style_dim, style_dim=style_dim))
 
-    def forward(self, x, style):
+    def forward(self, x, style, styles=None):
         for i in range(self.n_blocks):
-            x = self.res_blocks[i](x=x, style=style)
+            x = self.res_blocks[i](x=x, style=style, styles=None if styles is None else styles[i])
         return x
 
 
@@ -166,11 +166,11 @@ class Img2ImgAdaInUpModule(nn.Module):
                 conv_size=9 if last else 3, padding_size=4 if last else 1))
         self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
 
-    def forward(self, x, style):
+    def forward(self, x, style, styles=None):
         for i in range(self.n_up_blocks):
             if i == self.att_loc:
                 x = self.att(x)
-            x = self.up_blocks[i](x=x, style=style)
+            x = self.up_blocks[i](x=x, style=style, styles=None if styles is None else styles[i])
         return ops.TanhFn.apply(x)
 
 
@@ -195,9 +195,13 @@ class AdaInImage2Image(nn.Module):
         x = _as_nhwc(x)
         skip = [m.att for m in (self.down_block, self.adain_up_block) if not m.att_loc < len(getattr(m, 'down_blocks', getattr(m, 'up_blocks', ())))]
         mb.sn_prepare_module(self, skip=skip)
+        # the 4 x (n_res + n_up) style Linears share their input: one GEMM over the concatenated weights
+        blocks = list(self.adain_res_block.res_blocks) + list(self.adain_up_block.up_blocks)
+        styles = mb.batched_style_projections(blocks, style)
+        n_res = len(self.adain_res_block.res_blocks)
         x = self.down_block(x)
-        x = self.adain_res_block(x=x, style=style)
-        x = self.adain_up_block(x=x, style=style)
+        x = self.adain_res_block(x=x, style=style, styles=styles[:n_res])
+        x = self.adain_up_block(x=x, style=style, styles=styles[n_res:])
         return ops.from_nhwc(x)
 
 

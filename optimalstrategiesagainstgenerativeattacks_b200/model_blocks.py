@@ -260,11 +260,12 @@ class AdaResBlock2(nn.Module):
         self.conv1 = SNConv2d(channels, channels, 3, padding=1)
         self.conv2 = SNConv2d(channels, channels, 3, padding=1)
 
-    def forward(self, x, style):
-        mean_st1 = self.lin1_mean(style)
-        std_st1 = self.lin1_std(style)
-        mean_st2 = self.lin2_mean(style)
-        std_st2 = self.lin2_std(style)
+    def style_linears(self):
+        return [self.lin1_mean, self.lin1_std, self.lin2_mean, self.lin2_std]
+
+    def forward(self, x, style, styles=None):
+        """`styles`: the four style projections if the caller already computed them (one batched GEMM for all blocks)."""
+        mean_st1, std_st1, mean_st2, std_st2 = styles if styles is not None else [lin(style) for lin in self.style_linears()]
         out = self.conv1(x)
         out = ops.ada_in(out, mean_st1, std_st1, 1e-5, 0.2)
         out = self.conv2(out)
@@ -291,14 +292,34 @@ class AdaResBlockUp2(nn.Module):
         self.conv_r1 = SNConv2d(in_channels, out_channels, conv_size, padding=padding_size)
         self.conv_r2 = SNConv2d(out_channels, out_channels, conv_size, padding=padding_size)
 
-    def forward(self, x, style):
-        mean_st1 = self.lin1_mean(style)
-        std_st1 = self.lin1_std(style)
-        mean_st2 = self.lin2_mean(style)
-        std_st2 = self.lin2_std(style)
+    def style_linears(self):
+        return [self.lin1_mean, self.lin1_std, self.lin2_mean, self.lin2_std]
+
+    def forward(self, x, style, styles=None):
+        mean_st1, std_st1, mean_st2, std_st2 = styles if styles is not None else [lin(style) for lin in self.style_linears()]
         out_res = ops.upsample2(self.conv_l1(x))
         out = ops.ada_in(x, mean_st1, std_st1, 1e-5, 0.2)
         out = self.conv_r1(out, ops.PRE_UPSAMPLE)
         out = ops.ada_in(out, mean_st2, std_st2, 1e-5, 0.2)
         out = self.conv_r2(out)
         return ops.AddFn.apply(out, out_res)
+
+
+def batched_style_projections(blocks, style):
+    """All `lin{1,2}_{mean,std}` projections of a list of AdaIN blocks (reference model_blocks.py:795-805, 836-846: four nn.Linear per
+    block, all applied to the same style vectors) as ONE GEMM over the concatenated weights instead of 4 x len(blocks) tiny ones; the
+    per-layer results (and, through autograd, the per-layer gradients) are slices of it.  -> list of 4-tuples, one per block."""
+    lins = [lin for b in blocks for lin in b.style_linears()]
+    sizes = [lin.out_features for lin in lins]
+    total = sum(sizes)
+    pad = (-total) % 8                                    # the tensor-core GEMM wants a multiple of 8 output features
+    ws, bs = [lin.weight for lin in lins], [lin.bias for lin in lins]
+    if pad:
+        ws.append(style.new_zeros((pad, style.shape[-1])))
+        bs.append(style.new_zeros((pad,)))
+    y = ops.linear(style, torch.cat(ws, dim=0), torch.cat(bs, dim=0))
+    outs, off = [], 0
+    for n in sizes:
+        outs.append(y[:, off:off + n])
+        off += n
+    return [tuple(outs[4 * i:4 * i + 4]) for i in range(len(blocks))]
