@@ -71,6 +71,8 @@ int gim_weight_cast(const float* w, void* out, int taps, int cout, int cin, int 
 int gim_weight_flip(const float* w, void* out, int taps, int cout, int cin, int dtype, gim_stream_t stream);
 /* out[c] (fp32) = sum_rows x[row][c]   (bias gradient; rows = n*h*w) */
 int gim_colsum(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t stream);
+/* out[c] += sum_rows x[row][c]: accumulates straight into a parameter's .grad (no memset, no separate accumulation kernel) */
+int gim_colsum_acc(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t stream);
 
 /* ---- spectral norm: torch.nn.utils.spectral_norm hook, 1 power iteration (model_blocks.py:492-495 etc.) ---- */
 /* weight_orig [cout][cin][k][k] fp32; u[cout], v[cin*k*k] updated in place when power_iter!=0;

@@ -337,9 +337,14 @@ int gim_weight_flip(const float* w, void* out, int taps, int cout, int cin, int 
     GIM_DISPATCH_DTYPE(dtype, (weight_flip_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(w, (T*)out, taps, cout, cin)));
     return check_launch("weight_flip");
 }
-int gim_colsum(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t s) {
+static int colsum_launch(const void* x, float* out, long long rows, int c, int dtype, bool accumulate, gim_stream_t s);
+
+int gim_colsum(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t s) { return colsum_launch(x, out, rows, c, dtype, false, s); }
+int gim_colsum_acc(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t s) { return colsum_launch(x, out, rows, c, dtype, true, s); }
+
+static int colsum_launch(const void* x, float* out, long long rows, int c, int dtype, bool accumulate, gim_stream_t s) {
     if (c <= 0) return GIM_OK;
-    if (cudaMemsetAsync(out, 0, sizeof(float) * (size_t)c, (cudaStream_t)s) != cudaSuccess) return fail(GIM_E_CUDA, "colsum memset");
+    if (!accumulate && cudaMemsetAsync(out, 0, sizeof(float) * (size_t)c, (cudaStream_t)s) != cudaSuccess) return fail(GIM_E_CUDA, "colsum memset");
     if (rows <= 0) return GIM_OK;
     int cchunks = (c + 31) / 32;
     long long want = ((long long)num_sms() * 4 + cchunks - 1) / cchunks;

@@ -314,6 +314,7 @@ class Conv2dFn(Function):
         w32 = _c(w32)
         xop = _prepare_operand(x, pre, slope)
         ctx.cfg = (ks, pre, slope, bias is not None)
+        ctx.bias_param = bias
         # with a prologue the (half-size) operand is what backward needs: weight-grad input and the LeakyReLU sign mask
         ctx.save_for_backward(x if pre == PRE_NONE else xop, w32)
         return _conv_raw(xop, _weight_as(w32, operand_dtype(), False), bias, ks)
@@ -334,7 +335,8 @@ class Conv2dFn(Function):
             if ctx.needs_input_grad[1]:
                 gw = WgradFn.apply(xs, gy, ks)
             if has_bias and ctx.needs_input_grad[2]:
-                gb = ColSumFn.apply(gy)
+                # first-order pass: straight into bias.grad; when a graph of the backward is being built, the differentiable operator
+                gb = ColSumFn.apply(gy) if torch.is_grad_enabled() else _bias_grad(gy, ctx.bias_param)
         return gx, gw, gb, None, None, None
 
 
@@ -456,6 +458,17 @@ def _unskinny_gw(gw2, taps, co, ci):
     return gw2[0, :, :taps * ci].reshape(co, taps, ci).permute(1, 0, 2).contiguous()
 
 
+def _bias_grad(x, param):
+    """Bias gradient sum_rows x.  Inside `deferred_weight_grads()` (i.e. under loss.backward()) it is accumulated straight into the
+    leaf's .grad -- no memset, no AccumulateGrad add -- and None is returned to autograd; otherwise the column sums are returned."""
+    if (_state["defer_sn"] and param is not None and param.is_leaf and param.requires_grad and param.dtype == torch.float32 and param.is_contiguous()
+            and param.grad is not None and param.grad.is_contiguous()):
+        c = x.shape[-1]
+        C.call("gim_colsum_acc", C.ptr(x), C.ptr(param.grad), x.numel() // c, c, C.dtype_code(x))
+        return None
+    return _colsum(x)
+
+
 def _colsum(x):
     c = x.shape[-1]
     out = _empty((c,), torch.float32, x)
@@ -552,10 +565,13 @@ class ResBlockDownFn(Function):
             gw1 = _wgrad_raw(xr, gt, 1 if skinny else ks)
             if skinny:
                 gw1 = _unskinny_gw(gw1, taps, co, ci)
-        if want_w and (ctx.needs_input_grad[4] or ctx.needs_input_grad[8]):
-            gbl = gb2 = _colsum(gy)                                # both biases see the same gradient; sum(unpool(gy)/4) == sum(gy), in fp32
+        bl_p, b1_p, b2_p = ctx.biases
+        if want_w and ctx.needs_input_grad[4]:
+            gbl = _bias_grad(gy, bl_p)                             # both biases see the same gradient; sum(unpool(gy)/4) == sum(gy), in fp32
+        if want_w and ctx.needs_input_grad[8]:
+            gb2 = _bias_grad(gy, b2_p)
         if want_w and ctx.needs_input_grad[6]:
-            gb1 = _colsum(gt)
+            gb1 = _bias_grad(gt, b1_p)
         gx = None
         if ctx.needs_input_grad[0]:
             if not skinny and ci % 32 == 0:
@@ -641,6 +657,9 @@ def deferred_weight_grads():
     finally:
         _state["defer_sn"] = old
         _flush_sn_backward()
+        if _side["used"] and _side["stream"] is not None:
+            # kernels of the side branch's backward wrote into .grad directly (bias sums): the optimizer on this stream must see them
+            torch.cuda.current_stream().wait_stream(_side["stream"])
 
 
 def _defer_sn_backward(ctx, g, w, aux):

@@ -48,15 +48,16 @@ def main():
         rows = load(rep)
         kind = "wgrad" if "wgrad" in rows[0]["name"] else "fwd"
         per_shape = len(rows) // len(SHAPES)
-        out_txt.append("%s   (%s; last of %d launches per shape)" % (rows[0]["name"].split("(")[0], os.path.basename(rep), per_shape))
+        out_txt.append("%s kernels   (%s; last of %d launches per shape; <1> = cta_group::2 two-CTA cluster variant)" % (kind, os.path.basename(rep), per_shape))
         out_txt.append("  shape (640 images)            grid        us    TFLOP/s  tensor-pipe%  DRAM rd / wr MB   algorithmic MB  DRAM%  L2%   TMA-load GB (L2->SM TB/s)  regs")
         for si, (h, w, ci, co, k) in enumerate(SHAPES):
             r = rows[(si + 1) * per_shape - 1]
             flops = 2.0 * N_IMG * h * w * ci * co * k * k
             alg = N_IMG * h * w * (ci * 2 + (co * 4 if kind == "fwd" else co * 2)) + k * k * ci * co * (2 if kind == "fwd" else 4)
-            out_txt.append("  %2dx%-2d %3d->%-3d k%d   %14s  %7.1f  %8.1f  %8.1f      %7.1f / %-7.1f   %8.1f     %5.1f  %5.1f   %6.2f (%.1f)            %d" % (
+            variant = r["name"].split("(")[0].split("::")[-1].replace("void ", "")
+            out_txt.append("  %2dx%-2d %3d->%-3d k%d   %14s  %7.1f  %8.1f  %8.1f      %7.1f / %-7.1f   %8.1f     %5.1f  %5.1f   %6.2f (%.1f)            %d   %s" % (
                 h, w, ci, co, k, r["grid"], r["dur"], flops / r["dur"] / 1e6, r["tensor"], r["rd"] / 1e6, r["wr"] / 1e6, alg / 1e6, r["dram"], r["lts"],
-                r["tma_ld"] / 1e9, r["tma_ld"] / r["dur"] / 1e6, int(r["regs"])))
+                r["tma_ld"] / 1e9, r["tma_ld"] / r["dur"] / 1e6, int(r["regs"]), variant))
             out_json["%s_%dx%d_%d_%d_k%d" % (kind, h, w, ci, co, k)] = {
                 "duration_us": r["dur"], "dram_bytes_read": r["rd"], "dram_bytes_write": r["wr"], "algorithmic_bytes": alg, "flops": flops,
                 "tensor_pipe_active_pct": r["tensor"], "tma_load_bytes": r["tma_ld"]}
