@@ -138,6 +138,12 @@ int gim_unpool2_bcast(const void* gy, void* gx, int n, int h, int wd, int c, flo
 int gim_pool2_multi(const float* a, const float* b, float* y32, void* y_bf16, void* y_lrelu_bf16,
                     int n, int h, int wd, int c, float scale, float slope, gim_stream_t stream);
 int gim_unpool2_cast(const float* gy, void* gx_bf16, int n, int h, int wd, int c, float scale, gim_stream_t stream);
+/* First ResBlockDown of an encoder (image input with a few channels, model_blocks.py:497-509): both input-side convolutions in one pass.
+ * x fp32 NHWC [n,h,w,c]; w_r1 fp32 packed [k*k][cout][c], w_l1 fp32 packed [1][cout][c] (spectral-normalised), biases fp32;
+ * t = bf16(LeakyReLU(conv_k(LeakyReLU(x)) + b_r1)) [n,h,w,cout];  res = conv_1x1(AvgPool2(x)) + b_l1 [n,h/2,w/2,cout] fp32.
+ * Operands rounded to bf16 like the tensor-core path.  c*k*k <= 64, cout % 8 == 0, even h and w. */
+int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, const float* w_l1, const float* b_l1, void* t_bf16, float* res_pooled,
+                        int n, int h, int wd, int c, int cout, int ksize, float slope, gim_stream_t stream);
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
 int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
 /* dst[row][dst_off + j] = src[row][src_off + j], j<c  (channel concat / split, gim_img_models.py:385) */

@@ -381,6 +381,196 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ z
     }
 }
 
+
+// First ResBlockDown of an encoder (image input: 1-4 channels): both input-side convolutions in one HBM-bound pass.
+//   t[pix][co]   = bf16(LeakyReLU(b_r1[co] + sum_{tap,c} bf16(LeakyReLU(x))[pix+tap][c] * bf16(w_r1[tap][co][c])))     (k x k, 'same')
+//   res[pp][co]  = b_l1[co] + sum_c bf16(AvgPool2(x))[pp][c] * bf16(w_l1[co][c])                                        (1x1 at the pooled resolution)
+// With K = taps*c <= 36 these are outer products, not GEMMs: the tensor-core route needs an im2col pass and runs at 3 % of peak, bound by
+// its epilogue; here the only traffic is the two outputs.  Operands are rounded to bf16 exactly as on the tensor-core path.
+// One thread = one pixel x 8 output channels (a 16-byte store); weights live in shared memory as [tap*c][co].
+__global__ void __launch_bounds__(256) first_block_kernel(const float* __restrict__ x, const float* __restrict__ w_r1, const float* __restrict__ b_r1,
+                                                          const float* __restrict__ w_l1, const float* __restrict__ b_l1, bf16* __restrict__ t_out,
+                                                          float* __restrict__ res_out, int n, int h, int w, int c, int co, int ks, float slope) {
+    extern __shared__ float wsm[];                 // [taps*c][co] (r1), then [c][co] (l1), then biases
+    const int taps = ks * ks, pad = (ks - 1) / 2, kk = taps * c;
+    float* w1s = wsm;
+    float* wls = w1s + kk * co;
+    float* b1s = wls + c * co;
+    float* bls = b1s + co;
+    // layout [tap*c + ch][half][group][4]: output channel o = group*8 + half*4 + j.  A warp's two 16-byte loads per (tap, ch) then touch
+    // consecutive 16-byte chunks (one per channel group): bank-conflict free, the second pixel of the warp is a broadcast
+    for (int i = threadIdx.x; i < kk * co; i += blockDim.x) {
+        const int k = i / co, o = i - k * co;       // k = tap*c + ch
+        const int tap = k / c, ch = k - tap * c;
+        const int grp = o >> 3, half = (o >> 2) & 1, j = o & 3;
+        w1s[(k * 2 + half) * (co / 2) + grp * 4 + j] = __bfloat162float(__float2bfloat16_rn(w_r1[((long long)tap * co + o) * c + ch]));
+    }
+    for (int i = threadIdx.x; i < c * co; i += blockDim.x) {
+        const int ch = i / co, o = i - ch * co;
+        wls[i] = __bfloat162float(__float2bfloat16_rn(w_l1[(long long)o * c + ch]));
+    }
+    for (int i = threadIdx.x; i < co; i += blockDim.x) { b1s[i] = b_r1[i]; bls[i] = b_l1[i]; }
+    __syncthreads();
+    const int cg = co / 8;                          // channel groups of 8
+    // 32-bit index arithmetic (the host checks n*h*w*co/8 < 2^31): 64-bit divisions per element would dominate this kernel
+    const unsigned total = (unsigned)n * h * w * cg;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int g = (int)(i % (unsigned)cg);
+        const unsigned pix = i / (unsigned)cg;
+        const int pw = (int)(pix % (unsigned)w);
+        const unsigned r = pix / (unsigned)w;
+        const int ph = (int)(r % (unsigned)h);
+        const unsigned img = r / (unsigned)h;
+        const float* xi = x + (size_t)img * h * w * c;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = b1s[g * 8 + j];
+        int tap = 0;
+        for (int dr = -pad; dr <= pad; ++dr) {
+            const int hh = ph + dr;
+            for (int dq = -pad; dq <= pad; ++dq, ++tap) {
+                const int ww = pw + dq;
+                if (hh < 0 || hh >= h || ww < 0 || ww >= w) continue;
+                const float* xq = xi + (hh * w + ww) * c;
+                for (int ch = 0; ch < c; ++ch) {
+                    const float xv = __bfloat162float(__float2bfloat16_rn(lrelu_f(__ldg(xq + ch), slope)));
+                    const float* wrow = w1s + (tap * c + ch) * co + g * 4;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wrow), w1v = *reinterpret_cast<const float4*>(wrow + co / 2);
+                    acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+                    acc[4] = fmaf(xv, w1v.x, acc[4]); acc[5] = fmaf(xv, w1v.y, acc[5]); acc[6] = fmaf(xv, w1v.z, acc[6]); acc[7] = fmaf(xv, w1v.w, acc[7]);
+                }
+            }
+        }
+        uint4 o;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(lrelu_f(acc[0], slope), lrelu_f(acc[1], slope));
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(lrelu_f(acc[2], slope), lrelu_f(acc[3], slope));
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(lrelu_f(acc[4], slope), lrelu_f(acc[5], slope));
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(lrelu_f(acc[6], slope), lrelu_f(acc[7], slope));
+        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(t_out + (size_t)pix * co + g * 8) = o;
+        // the thread of the top-left pixel of each 2x2 window also produces the pooled residual for its 8 channels
+        if (!(ph & 1) && !(pw & 1) && ph + 1 < h && pw + 1 < w) {
+            float rs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rs[j] = bls[g * 8 + j];
+            for (int ch = 0; ch < c; ++ch) {
+                const float* q = xi + (ph * w + pw) * c + ch;
+                const float xp = __bfloat162float(__float2bfloat16_rn(0.25f * (__ldg(q) + __ldg(q + c) + __ldg(q + w * c) + __ldg(q + w * c + c))));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rs[j] = fmaf(xp, wls[ch * co + g * 8 + j], rs[j]);
+            }
+            float* dst = res_out + (((size_t)img * (h / 2) + ph / 2) * (w / 2) + pw / 2) * co + g * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(rs[4], rs[5], rs[6], rs[7]);
+        }
+    }
+}
+
+// Specialised variant (compile-time channel count and filter size, w % 4 == 0): one thread = 4 consecutive pixels of a row x 8 output
+// channels.  The 3 x 6 input neighbourhood is loaded (and activated / rounded) once for the four pixels and every weight read from
+// shared memory feeds four FMAs, so the kernel stays below the issue limit and runs at the speed of its two output streams.
+template <int C, int KS>
+__global__ void __launch_bounds__(256) first_block_quad_kernel(const float* __restrict__ x, const float* __restrict__ w_r1, const float* __restrict__ b_r1,
+                                                               const float* __restrict__ w_l1, const float* __restrict__ b_l1, bf16* __restrict__ t_out,
+                                                               float* __restrict__ res_out, int n, int h, int w, int co, float slope) {
+    extern __shared__ float wsm[];
+    constexpr int TAPS = KS * KS, PAD = (KS - 1) / 2, KK = TAPS * C, PX = 4, NX = PX + KS - 1;
+    float* w1s = wsm;                               // [tap*C + ch][half][group][4]
+    float* wls = w1s + KK * co;                     // [ch][co]
+    float* b1s = wls + C * co;
+    float* bls = b1s + co;
+    for (int i = threadIdx.x; i < KK * co; i += blockDim.x) {
+        const int k = i / co, o = i - k * co;
+        const int tap = k / C, ch = k - tap * C;
+        const int grp = o >> 3, half = (o >> 2) & 1, j = o & 3;
+        w1s[(k * 2 + half) * (co / 2) + grp * 4 + j] = __bfloat162float(__float2bfloat16_rn(w_r1[((long long)tap * co + o) * C + ch]));
+    }
+    for (int i = threadIdx.x; i < C * co; i += blockDim.x) {
+        const int ch = i / co, o = i - ch * co;
+        wls[i] = __bfloat162float(__float2bfloat16_rn(w_l1[(long long)o * C + ch]));
+    }
+    for (int i = threadIdx.x; i < co; i += blockDim.x) { b1s[i] = b_r1[i]; bls[i] = b_l1[i]; }
+    __syncthreads();
+    const unsigned cg = co / 8, wq = w / PX;
+    const unsigned total = (unsigned)n * h * wq * cg;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int g = (int)(i % cg);
+        unsigned r = i / cg;
+        const int pw0 = (int)(r % wq) * PX; r /= wq;
+        const int ph = (int)(r % (unsigned)h);
+        const unsigned img = r / (unsigned)h;
+        const float* xi = x + (size_t)img * h * w * C;
+        float xa[KS][NX][C];                        // bf16(LeakyReLU(x)) of the neighbourhood, zero outside the image
+        float xr[2][PX][C];                         // raw x of rows ph, ph+1 (for the pooled residual)
+#pragma unroll
+        for (int dr = 0; dr < KS; ++dr) {
+            const int hh = ph + dr - PAD;
+#pragma unroll
+            for (int dq = 0; dq < NX; ++dq) {
+                const int ww = pw0 + dq - PAD;
+                const bool in = hh >= 0 && hh < h && ww >= 0 && ww < w;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float v = in ? __ldg(xi + (hh * w + ww) * C + ch) : 0.f;
+                    xa[dr][dq][ch] = __bfloat162float(__float2bfloat16_rn(lrelu_f(v, slope)));
+                    if (dr >= PAD && dr <= PAD + 1 && dq >= PAD && dq < PAD + PX) xr[dr - PAD][dq - PAD][ch] = v;
+                }
+            }
+        }
+        float acc[PX][8];
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = b1s[g * 8 + j];
+#pragma unroll
+        for (int dr = 0; dr < KS; ++dr)
+#pragma unroll
+            for (int dq = 0; dq < KS; ++dq)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float* wrow = w1s + ((dr * KS + dq) * C + ch) * co + g * 4;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wrow), w1v = *reinterpret_cast<const float4*>(wrow + co / 2);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1v.x, w1v.y, w1v.z, w1v.w};
+#pragma unroll
+                    for (int p = 0; p < PX; ++p)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xa[dr][p + dq][ch], wv[j], acc[p][j]);
+                }
+        bf16* trow = t_out + (((size_t)img * h + ph) * w + pw0) * co + g * 8;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            uint4 o;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(lrelu_f(acc[p][0], slope), lrelu_f(acc[p][1], slope));
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(lrelu_f(acc[p][2], slope), lrelu_f(acc[p][3], slope));
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(lrelu_f(acc[p][4], slope), lrelu_f(acc[p][5], slope));
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(lrelu_f(acc[p][6], slope), lrelu_f(acc[p][7], slope));
+            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(trow + (size_t)p * co) = o;
+        }
+        if (!(ph & 1)) {                            // even rows also produce the two pooled residual pixels under this quad
+#pragma unroll
+            for (int pp = 0; pp < PX / 2; ++pp) {
+                float rs[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rs[j] = bls[g * 8 + j];
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float xp = __bfloat162float(__float2bfloat16_rn(0.25f * (xr[0][2 * pp][ch] + xr[0][2 * pp + 1][ch] + xr[1][2 * pp][ch] + xr[1][2 * pp + 1][ch])));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rs[j] = fmaf(xp, wls[ch * co + g * 8 + j], rs[j]);
+                }
+                float* dst = res_out + (((size_t)img * (h / 2) + ph / 2) * (w / 2) + pw0 / 2 + pp) * co + g * 8;
+                *reinterpret_cast<float4*>(dst) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(rs[4], rs[5], rs[6], rs[7]);
+            }
+        }
+    }
+}
+
 // The conv-operand producer: out = f(x) in the operand dtype, f = identity / LeakyReLU / nearest-upsample x2 (out is [n,2h,2w,c]).
 // One pass (4 B read, 2 B written per element on the bf16 path) instead of activation kernel + cast kernel.
 template <typename TI, typename TO>
@@ -528,6 +718,40 @@ int gim_unpool2_cast(const float* gy, void* gx_bf16, int n, int h, int wd, int c
     GIM_REQUIRE(c % 8 == 0 && aligned16(gy) && aligned16(gx_bf16), "unpool2_cast: needs c % 8 == 0 and 16-byte aligned tensors");
     unpool2_cast_kernel<<<ew_grid(total / 8, 256, 1), 256, 0, (cudaStream_t)s>>>(gy, (bf16*)gx_bf16, n, h, wd, c, scale);
     return check_launch("unpool2_cast");
+}
+int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, const float* w_l1, const float* b_l1, void* t_bf16, float* res_pooled,
+                        int n, int h, int wd, int c, int cout, int ksize, float slope, gim_stream_t s) {
+    GIM_REQUIRE(n > 0 && h > 1 && wd > 1 && c > 0 && cout > 0, "first_block_fwd: empty shape");
+    GIM_REQUIRE(ksize >= 1 && (ksize & 1) && c * ksize * ksize <= 64 && cout % 8 == 0 && !(h & 1) && !(wd & 1), "first_block_fwd: unsupported shape");
+    GIM_REQUIRE(aligned16(t_bf16) && aligned16(res_pooled), "first_block_fwd: outputs must be 16-byte aligned");
+    GIM_REQUIRE((long long)n * h * wd * (cout / 8) < 2147483647LL, "first_block_fwd: too many elements for 32-bit indexing");
+    const size_t smem = sizeof(float) * ((size_t)ksize * ksize * c * cout + (size_t)c * cout + 2 * (size_t)cout);
+    GIM_REQUIRE(smem <= 96 * 1024, "first_block_fwd: weights do not fit in shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(first_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+            return fail(GIM_E_CUDA, "first_block_fwd: cannot raise dynamic shared memory limit");
+        attr_set = true;
+    }
+    const long long total = (long long)n * h * wd * (cout / 8);
+    if (ksize == 3 && (c == 1 || c == 3) && wd % 4 == 0) {      // the two image formats of the GIM configs: grey and RGB, 3x3
+        static bool quad_attr = false;
+        if (!quad_attr) {
+            if (cudaFuncSetAttribute(first_block_quad_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(first_block_quad_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+                return fail(GIM_E_CUDA, "first_block_fwd: cannot raise dynamic shared memory limit");
+            quad_attr = true;
+        }
+        int gq = ew_grid(total / 4, 256, 2);
+        if (gq > 8 * num_sms()) gq = 8 * num_sms();
+        if (c == 1) first_block_quad_kernel<1, 3><<<gq, 256, smem, (cudaStream_t)s>>>(x, w_r1, b_r1, w_l1, b_l1, (bf16*)t_bf16, res_pooled, n, h, wd, cout, slope);
+        else first_block_quad_kernel<3, 3><<<gq, 256, smem, (cudaStream_t)s>>>(x, w_r1, b_r1, w_l1, b_l1, (bf16*)t_bf16, res_pooled, n, h, wd, cout, slope);
+        return check_launch("first_block_quad");
+    }
+    int grid = ew_grid(total, 256, 4);
+    if (grid > 8 * num_sms()) grid = 8 * num_sms();            // every CTA stages the weights once: keep them few and long-lived
+    first_block_kernel<<<grid, 256, smem, (cudaStream_t)s>>>(x, w_r1, b_r1, w_l1, b_l1, (bf16*)t_bf16, res_pooled, n, h, wd, c, cout, ksize, slope);
+    return check_launch("first_block_fwd");
 }
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t s) {
     int hw = h * wd;

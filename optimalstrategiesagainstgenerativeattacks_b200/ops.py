@@ -491,12 +491,35 @@ class ResBlockDownFn(Function):
         od = torch.bfloat16
         x32 = _c(x32)
         n, h, w, ci = x32.shape
-        if xl is None:
-            xl = _prepare_operand(x32, PRE_LRELU, slope)
-        wl_t, w1_t, w2_t = _weight_as(_c(wl), od, False), _weight_as(_c(w1), od, False), _weight_as(_c(w2), od, False)
-        co = w2_t.shape[1]
         skinny = ci % 8 != 0
         even = h % 2 == 0 and w % 2 == 0
+        wl, w1, w2 = _c(wl), _c(w1), _c(w2)
+        co = w2.shape[1]
+        lazy = skinny and even and ci * ks * ks <= 64 and co % 32 == 0
+        if lazy:
+            # image-side block: both input convolutions are K <= 64 outer products -> one HBM-bound kernel, no im2col, no operand tensors
+            y32 = _empty((n, h // 2, w // 2, co), torch.float32, x32)
+            tl = _empty((n, h, w, co), od, x32)
+            C.call("gim_first_block_fwd", C.ptr(x32), C.ptr(w1), C.ptr(b1), C.ptr(wl), C.ptr(bl), C.ptr(tl), C.ptr(y32), n, h, w, ci, co, ks, slope)
+            _conv_tc_fused(tl, _weight_as(w2, od, False), b2, ks, torch.float32, EPI_POOL | EPI_ADD, addend=y32, out=y32)
+            yb = yl = None
+            if want_ops:
+                yb = torch.empty_like(y32, dtype=od)
+                yl = torch.empty_like(y32, dtype=od)
+                C.call("gim_cast", C.ptr(y32), C.F32, C.ptr(yb), C.BF16, y32.numel())
+                C.call("gim_operand_prepare", C.ptr(y32), C.F32, C.ptr(yl), C.BF16, n, h // 2, w // 2, co, PRE_LRELU, slope)
+            ctx.cfg = (ks, slope, skinny, even, (n, h, w, ci, co), want_ops)
+            ctx.lazy = True
+            ctx.save_for_backward(x32, None, None, tl, wl, w1, w2)
+            ctx.biases = (bl, b1, b2)
+            if want_ops:
+                ctx.mark_non_differentiable(yb, yl)
+                return y32, yb, yl
+            return y32, None, None
+        ctx.lazy = False
+        if xl is None:
+            xl = _prepare_operand(x32, PRE_LRELU, slope)
+        wl_t, w1_t, w2_t = _weight_as(wl, od, False), _weight_as(w1, od, False), _weight_as(w2, od, False)
         if skinny:
             xr, w1_e = _skinny_in(xl, w1_t, ks)
             k1 = 1
@@ -549,6 +572,18 @@ class ResBlockDownFn(Function):
         od = torch.bfloat16
         taps = ks * ks
         gy = _c(gy)
+        if ctx.lazy:
+            # the forward ran the fused image-side kernel: build the tensor-core operands only if a gradient that needs them is requested
+            x32 = xa
+            xa = xr = xl = None
+            want_any_w = (not _state["input_grads_only"]) and (ctx.needs_input_grad[3] or ctx.needs_input_grad[5])
+            if want_any_w or ctx.needs_input_grad[0]:
+                xl = _prepare_operand(x32, PRE_LRELU, slope)
+            if want_any_w:
+                xp32 = _empty((n, h // 2, w // 2, ci), torch.float32, x32)
+                C.call("gim_pool2_sum", C.ptr(x32), None, C.ptr(xp32), n, h, w, ci, 0.25, C.F32)
+                xa = _im2col(_operand(xp32), 1, 1, _round_up(ci, 8))
+                xr = _im2col(xl, ks, 1, _round_up(taps * ci, 8))
         g = _empty((n, h, w, co), od, gy)                      # AvgPool backward, written once as the bf16 operand
         C.call("gim_unpool2_cast", C.ptr(gy), C.ptr(g), n, h, w, co, 0.25)
         gl = _operand(gy) if even else g                       # gradient of the residual branch: at the pooled resolution when it ran there

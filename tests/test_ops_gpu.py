@@ -374,7 +374,8 @@ def test_conv_with_fused_prologue(prec, tol):
         assert rel_err(nchw(dX), gX) < tol and rel_err(unpack_w(dW, k), gW) < tol and rel_err(dB, gB) < tol
 
 
-@pytest.mark.parametrize("shape", [(3, 64, 128, 3, 16, 16), (2, 1, 128, 3, 32, 32), (2, 2, 64, 9, 16, 16), (4, 256, 512, 3, 8, 8), (2, 32, 64, 3, 13, 9)])
+@pytest.mark.parametrize("shape", [(3, 64, 128, 3, 16, 16), (2, 1, 128, 3, 32, 32), (2, 2, 64, 9, 16, 16), (4, 256, 512, 3, 8, 8), (2, 32, 64, 3, 13, 9),
+                                   (2, 3, 64, 3, 16, 16), (1, 2, 32, 3, 6, 10)])
 def test_res_block_down_fused(shape):
     """The block-level fused ResBlockDown (bf16 path: epilogue-fused LeakyReLU / masks / residual add, multi-output pooling) against
     the float64 statement of model_blocks.py:486-514, and against the composition of elementary operators it replaces."""
