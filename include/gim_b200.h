@@ -144,6 +144,10 @@ int gim_unpool2_cast(const float* gy, void* gx_bf16, int n, int h, int wd, int c
  * Operands rounded to bf16 like the tensor-core path.  c*k*k <= 64, cout % 8 == 0, even h and w. */
 int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, const float* w_l1, const float* b_l1, void* t_bf16, float* res_pooled,
                         int n, int h, int wd, int c, int cout, int ksize, float slope, gim_stream_t stream);
+/* weight gradients of the same two convolutions (3x3, c = 1 or 3): gw_r1 fp32 packed [9][cout][c] from gt = bf16 masked gradient of the
+ * k x k conv output [n,h,w,cout]; gw_l1 fp32 [cout][c] from gy = fp32 gradient of the pooled block output [n,h/2,w/2,cout]; both overwritten */
+int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_pooled, float* gw_r1, float* gw_l1,
+                          int n, int h, int wd, int c, int cout, int ksize, float slope, gim_stream_t stream);
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
 int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
 /* dst[row][dst_off + j] = src[row][src_off + j], j<c  (channel concat / split, gim_img_models.py:385) */

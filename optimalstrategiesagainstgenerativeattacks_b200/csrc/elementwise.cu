@@ -571,6 +571,127 @@ __global__ void __launch_bounds__(256) first_block_quad_kernel(const float* __re
     }
 }
 
+// Weight gradients of the same two image-side convolutions in one pass over the gradients:
+//   gw_r1[tap][co][c] = sum_pix gt[pix][co] * bf16(LeakyReLU(x))[pix+tap][c]          (gt: bf16 masked gradient of the k x k conv output)
+//   gw_l1[co][c]      = sum_pp bf16(gy)[pp][co] * bf16(AvgPool2(x))[pp][c]           (gy: fp32 gradient of the pooled block output)
+// One thread = one image row x NCH output channels: it walks the row with a sliding 3 x 3 window of activated inputs (three new loads
+// per pixel; all index arithmetic hoisted out of the loop) and TAPS*C*NCH register accumulators.  Lanes of a warp hold consecutive
+// channel groups, so the gradient row is read with full 256-byte transactions.  Threads of a CTA are combined in shared memory, CTAs
+// with fp32 atomics (outputs zeroed by the caller).
+template <int C, int NCH>
+__global__ void __launch_bounds__(256) first_block_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ gt, const float* __restrict__ gy,
+                                                                float* __restrict__ gw_r1, float* __restrict__ gw_l1, int n, int h, int w, int co,
+                                                                float slope) {
+    constexpr int KS = 3, TAPS = 9, KK = TAPS * C;
+    extern __shared__ float red[];                  // [KK + C][co] block-level partial sums
+    for (int i = threadIdx.x; i < (KK + C) * co; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const unsigned cg = co / NCH;
+    const unsigned total = (unsigned)n * h * cg;    // (image, row, channel group)
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = (int)(i % cg);
+    if (i < total) {
+        const unsigned rr = i / cg;
+        const int ph = (int)(rr % (unsigned)h);
+        const unsigned img = rr / (unsigned)h;
+        const float* xi = x + (size_t)img * h * w * C;
+        const bf16* grow = gt + (((size_t)img * h + ph) * w) * co + g * NCH;
+        const float* gyrow = gy + (((size_t)img * (h / 2) + ph / 2) * (w / 2)) * co + g * NCH;
+        float acc[KK][NCH], accl[C][NCH];
+#pragma unroll
+        for (int k = 0; k < KK; ++k)
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) acc[k][j] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) accl[ch][j] = 0.f;
+        // sliding window win[dr][dq][ch] = bf16(LeakyReLU(x[ph+dr-1][pw+dq-1][ch])), zero outside the image
+        float win[KS][KS][C];
+        const bool row_ok[KS] = {ph - 1 >= 0, true, ph + 1 < h};
+#pragma unroll
+        for (int dr = 0; dr < KS; ++dr)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                win[dr][0][ch] = 0.f;
+                win[dr][1][ch] = 0.f;               // becomes column -1 after the first shift
+                win[dr][2][ch] = row_ok[dr] ? __bfloat162float(__float2bfloat16_rn(lrelu_f(__ldg(xi + ((ph + dr - 1) * w) * C + ch), slope))) : 0.f;
+            }
+        constexpr int PF = 1;                       // pixels per step (deeper software pipelining measured slower: registers halve the occupancy)
+        for (int pw0 = 0; pw0 < w; pw0 += PF) {
+            uint2 graw[PF];
+            float xnew[PF][KS][C];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int pw = pw0 + u;
+                graw[u] = pw < w ? *reinterpret_cast<const uint2*>(grow + (size_t)pw * co) : make_uint2(0u, 0u);        // NCH == 4: 8 bytes
+#pragma unroll
+                for (int dr = 0; dr < KS; ++dr)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch)
+                        xnew[u][dr][ch] = (row_ok[dr] && pw + 1 < w) ? __ldg(xi + ((ph + dr - 1) * w + pw + 1) * C + ch) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int pw = pw0 + u;
+                if (pw >= w) break;
+#pragma unroll
+                for (int dr = 0; dr < KS; ++dr)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        win[dr][0][ch] = win[dr][1][ch];
+                        win[dr][1][ch] = win[dr][2][ch];
+                        win[dr][2][ch] = __bfloat162float(__float2bfloat16_rn(lrelu_f(xnew[u][dr][ch], slope)));      // lrelu(0) = 0 outside
+                    }
+                float gv[NCH];
+                {
+                    const bf16* e = reinterpret_cast<const bf16*>(&graw[u]);
+#pragma unroll
+                    for (int q = 0; q < NCH; ++q) gv[q] = __bfloat162float(e[q]);
+                }
+#pragma unroll
+                for (int dr = 0; dr < KS; ++dr)
+#pragma unroll
+                    for (int dq = 0; dq < KS; ++dq)
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+                            for (int j = 0; j < NCH; ++j) acc[(dr * KS + dq) * C + ch][j] = fmaf(win[dr][dq][ch], gv[j], acc[(dr * KS + dq) * C + ch][j]);
+                if (!(ph & 1) && !(pw & 1)) {       // residual branch at the pooled resolution
+                    const float4 gq = __ldg(reinterpret_cast<const float4*>(gyrow + (size_t)(pw / 2) * co));
+                    const float gl[4] = {__bfloat162float(__float2bfloat16_rn(gq.x)), __bfloat162float(__float2bfloat16_rn(gq.y)),
+                                         __bfloat162float(__float2bfloat16_rn(gq.z)), __bfloat162float(__float2bfloat16_rn(gq.w))};
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        const float* q = xi + (ph * w + pw) * C + ch;
+                        const float xp = __bfloat162float(__float2bfloat16_rn(0.25f * (__ldg(q) + __ldg(q + C) + __ldg(q + w * C) + __ldg(q + w * C + C))));
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) accl[ch][j] = fmaf(xp, gl[j], accl[ch][j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KK; ++k)
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) atomicAdd(&red[k * co + g * NCH + j], acc[k][j]);
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) atomicAdd(&red[(KK + ch) * co + g * NCH + j], accl[ch][j]);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < KK * co; q += blockDim.x) {
+        const int k = q / co, o = q - k * co;       // k = tap*C + ch  ->  gw_r1[tap][o][ch]
+        const int tap = k / C, ch = k - tap * C;
+        atomicAdd(&gw_r1[((size_t)tap * co + o) * C + ch], red[q]);
+    }
+    for (int q = threadIdx.x; q < C * co; q += blockDim.x) {
+        const int ch = q / co, o = q - ch * co;
+        atomicAdd(&gw_l1[(size_t)o * C + ch], red[KK * co + q]);
+    }
+}
+
 // The conv-operand producer: out = f(x) in the operand dtype, f = identity / LeakyReLU / nearest-upsample x2 (out is [n,2h,2w,c]).
 // One pass (4 B read, 2 B written per element on the bf16 path) instead of activation kernel + cast kernel.
 template <typename TI, typename TO>
@@ -752,6 +873,22 @@ int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, co
     if (grid > 8 * num_sms()) grid = 8 * num_sms();            // every CTA stages the weights once: keep them few and long-lived
     first_block_kernel<<<grid, 256, smem, (cudaStream_t)s>>>(x, w_r1, b_r1, w_l1, b_l1, (bf16*)t_bf16, res_pooled, n, h, wd, c, cout, ksize, slope);
     return check_launch("first_block_fwd");
+}
+int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_pooled, float* gw_r1, float* gw_l1, int n, int h, int wd, int c, int cout,
+                          int ksize, float slope, gim_stream_t s) {
+    GIM_REQUIRE(n > 0 && h > 1 && wd > 1 && !(h & 1) && !(wd & 1), "first_block_wgrad: bad shape");
+    GIM_REQUIRE(ksize == 3 && (c == 1 || c == 3) && cout % 8 == 0, "first_block_wgrad: unsupported shape");
+    GIM_REQUIRE((long long)n * h * wd * (cout / 4) < 2147483647LL, "first_block_wgrad: too many elements for 32-bit indexing");
+    cudaStream_t st = (cudaStream_t)s;
+    if (cudaMemsetAsync(gw_r1, 0, sizeof(float) * 9 * (size_t)cout * c, st) != cudaSuccess || cudaMemsetAsync(gw_l1, 0, sizeof(float) * (size_t)cout * c, st) != cudaSuccess)
+        return fail(GIM_E_CUDA, "first_block_wgrad memset");
+    const size_t smem = sizeof(float) * (size_t)(9 * c + c) * cout;
+    GIM_REQUIRE(smem <= 48 * 1024, "first_block_wgrad: partial sums do not fit in shared memory");
+    const long long threads = (long long)n * h * (cout / 4);
+    const int grid = (int)((threads + 255) / 256);
+    if (c == 1) first_block_wgrad_kernel<1, 4><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
+    else first_block_wgrad_kernel<3, 4><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
+    return check_launch("first_block_wgrad");
 }
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t s) {
     int hw = h * wd;

@@ -572,31 +572,44 @@ class ResBlockDownFn(Function):
         od = torch.bfloat16
         taps = ks * ks
         gy = _c(gy)
+        fused_wgrad = False
         if ctx.lazy:
             # the forward ran the fused image-side kernel: build the tensor-core operands only if a gradient that needs them is requested
             x32 = xa
             xa = xr = xl = None
             want_any_w = (not _state["input_grads_only"]) and (ctx.needs_input_grad[3] or ctx.needs_input_grad[5])
-            if want_any_w or ctx.needs_input_grad[0]:
+            fused_wgrad = want_any_w and ks == 3 and ci in (1, 3) and co % 8 == 0
+            if (want_any_w and not fused_wgrad) or ctx.needs_input_grad[0]:
                 xl = _prepare_operand(x32, PRE_LRELU, slope)
-            if want_any_w:
+            if want_any_w and not fused_wgrad:
                 xp32 = _empty((n, h // 2, w // 2, ci), torch.float32, x32)
                 C.call("gim_pool2_sum", C.ptr(x32), None, C.ptr(xp32), n, h, w, ci, 0.25, C.F32)
                 xa = _im2col(_operand(xp32), 1, 1, _round_up(ci, 8))
                 xr = _im2col(xl, ks, 1, _round_up(taps * ci, 8))
         g = _empty((n, h, w, co), od, gy)                      # AvgPool backward, written once as the bf16 operand
         C.call("gim_unpool2_cast", C.ptr(gy), C.ptr(g), n, h, w, co, 0.25)
-        gl = _operand(gy) if even else g                       # gradient of the residual branch: at the pooled resolution when it ran there
+        need_gl = ctx.needs_input_grad[0] or ((not _state["input_grads_only"]) and ctx.needs_input_grad[3] and not fused_wgrad)
+        # gradient of the residual branch: at the pooled resolution when it ran there
+        gl = (_operand(gy) if even else g) if need_gl else None
         gt = _conv_tc_fused(g, _weight_as(w2, od, True), None, ks, od, EPI_MASK, slope, mask_ref=tl)      # d/d(conv_r1 output), masked
         gwl = gbl = gw1 = gb1 = gw2 = gb2 = None
         want_w = not _state["input_grads_only"]
-        if want_w and ctx.needs_input_grad[3]:
+        if fused_wgrad:
+            # both image-side weight gradients in one pass over the gradients (K <= 27 outer products: no im2col, no tensor-core launch)
+            gw1 = _empty((taps, co, ci), torch.float32, gy)
+            gwl = _empty((1, co, ci), torch.float32, gy)
+            C.call("gim_first_block_wgrad", C.ptr(x32), C.ptr(gt), C.ptr(gy), C.ptr(gw1), C.ptr(gwl), n, h, w, ci, co, ks, slope)
+            if not ctx.needs_input_grad[3]:
+                gwl = None
+            if not ctx.needs_input_grad[5]:
+                gw1 = None
+        if want_w and ctx.needs_input_grad[3] and not fused_wgrad:
             gwl = _wgrad_raw(xa, gl, 1)
             if skinny:
                 gwl = _unskinny_gw(gwl, 1, co, ci)
         if want_w and ctx.needs_input_grad[7]:
             gw2 = _wgrad_raw(tl, g, ks)
-        if want_w and ctx.needs_input_grad[5]:
+        if want_w and ctx.needs_input_grad[5] and not fused_wgrad:
             gw1 = _wgrad_raw(xr, gt, 1 if skinny else ks)
             if skinny:
                 gw1 = _unskinny_gw(gw1, taps, co, ci)

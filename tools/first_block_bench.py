@@ -1,4 +1,4 @@
-"""Times gim_first_block_fwd (the fused image-side kernel of the first ResBlockDown) alone: python tools/first_block_bench.py"""
+"""Times the fused image-side kernels of the first ResBlockDown alone: python tools/first_block_bench.py"""
 import os
 import sys
 
@@ -16,15 +16,20 @@ wl = torch.randn((1, co, c), device=dev)
 b1, bl = torch.randn(co, device=dev), torch.randn(co, device=dev)
 t = torch.empty((n, h, w, co), device=dev, dtype=torch.bfloat16)
 r = torch.empty((n, h // 2, w // 2, co), device=dev)
-f = lambda: C.call("gim_first_block_fwd", C.ptr(x), C.ptr(w1), C.ptr(b1), C.ptr(wl), C.ptr(bl), C.ptr(t), C.ptr(r), n, h, w, c, co, k, 0.2)
-for _ in range(3):
-    f()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(10):
-    f()
-e1.record()
-torch.cuda.synchronize()
-us = e0.elapsed_time(e1) * 100
-print("first_block_fwd n=%d %dx%d c=%d co=%d k=%d: %.1f us, %.2f TB/s written" % (n, h, w, c, co, k, us, (t.numel() * 2 + r.numel() * 4) / us / 1e6))
+gt = torch.randn((n, h, w, co), device=dev).bfloat16()
+gy = torch.randn((n, h // 2, w // 2, co), device=dev)
+gw1, gwl = torch.empty((k * k, co, c), device=dev), torch.empty((1, co, c), device=dev)
+fwd = lambda: C.call("gim_first_block_fwd", C.ptr(x), C.ptr(w1), C.ptr(b1), C.ptr(wl), C.ptr(bl), C.ptr(t), C.ptr(r), n, h, w, c, co, k, 0.2)
+wg = lambda: C.call("gim_first_block_wgrad", C.ptr(x), C.ptr(gt), C.ptr(gy), C.ptr(gw1), C.ptr(gwl), n, h, w, c, co, k, 0.2)
+for name, f, nbytes in (("fwd", fwd, t.numel() * 2 + r.numel() * 4), ("wgrad", wg, gt.numel() * 2 + gy.numel() * 4)):
+    for _ in range(3):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 100
+    print("first_block_%s n=%d %dx%d c=%d co=%d k=%d: %.1f us, %.2f TB/s" % (name, n, h, w, c, co, k, us, nbytes / us / 1e6))
