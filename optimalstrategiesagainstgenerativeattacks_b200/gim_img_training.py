@@ -1,0 +1,189 @@
+"""The image-GIM training loop -- mirrors the reference's training/gim_img_training.py (`eval_step` :96-154, `train_epoch`
+:186-357, `train_gim_imgs` :360-445) on the B200 path.
+
+Kept: function names, arguments, the per-iteration order (global step, LR schedule, G-step or G-eval, D-step), the logged
+categories / keys, `save_every` / `eval_every` / `tb_log_every` / `tb_log_enc_every` cadence, checkpoint files.
+Changed for a GPU that runs > 2000 episodes/s:
+  * batches come from a device-resident `ResidentGIMDataSet.iter_batches` when the dataset offers it (else a DataLoader);
+  * nothing is read back per iteration: the log buffers hold device scalars and are reduced on the device every `tb_log_every`
+    iterations (the reference calls `.item()` a dozen times per iteration in its Gaussian loop and per log interval here);
+  * with `use_cuda_graph=True` (and n_au_steps == 1) the whole G+D iteration is one CUDA-graph replay (`cuda_graph.GraphedIteration`);
+  * several GPUs = one process per GPU under torchrun (`ddp.attach`), not nn.DataParallel: `device_ids` lists the local device only;
+  * the image grids of `sample_and_save_imgs` (:34-73, PIL / tensorboard) are not produced.
+`logger` is anything with `add_scalar(category=, k=, v=, global_step=)`; `ScalarLog` below keeps the values in memory.
+"""
+import itertools
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ddp
+from . import model_blocks as mb
+from .gim_img_trainer import GIMImgTrainer
+from .training_steps import au_eval_step, au_train_step, im_eval_step, im_train_step
+from .utils import DataParallelMock, get_device
+
+
+class ScalarLog:
+    """Minimal stand-in for the reference's Logger (training/logger.py): records add_scalar calls."""
+
+    def __init__(self):
+        self.scalars = {}
+
+    def add_scalar(self, category, k, v, global_step):
+        self.scalars.setdefault((category, k), []).append((int(global_step), float(v)))
+
+
+def _batches(ds, batch_size, shuffle, num_workers, drop_last=True):
+    if hasattr(ds, "iter_batches"):
+        n = len(ds) // batch_size if drop_last else (len(ds) + batch_size - 1) // batch_size
+        return ds.iter_batches(batch_size, shuffle=shuffle, drop_last=drop_last), n
+    from torch.utils.data import DataLoader
+    loader = DataLoader(ds, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers, drop_last=drop_last)
+    return loader, len(loader)
+
+
+def _mean(buf):
+    return torch.stack([t.reshape(()) for t in buf]).mean().item()
+
+
+def eval_step(device, trainer, ds, logger, batch_size):
+    """Reference :96-154: G-eval + D-eval over the validation split, nine scalars logged."""
+    stats = {k: [] for k in ("au_loss", "au_loss_on_real", "au_loss_on_fake", "au_out_on_real", "au_out_on_fake", "au_acc", "au_acc_on_real",
+                             "au_acc_on_fake", "im_loss")}
+    global_step = trainer.module.get_global_step()
+    batches, n_iters = _batches(ds, batch_size, False, 0)
+    for data_batch in itertools.islice(batches, n_iters):
+        real_sample, leaked_sample, si_sample = (data_batch[k].to(device) for k in ("real_sample", "leaked_sample", "si_sample"))
+        im_loss, fake_sample, _ = im_eval_step(trainer=trainer, leaked_sample=leaked_sample, si_sample=si_sample)
+        (au_loss, au_loss_on_real, au_loss_on_fake, _reg, au_out_on_real, au_out_on_fake, au_pred_on_real, au_pred_on_fake, fake_sample) = au_eval_step(
+            trainer=trainer, real_sample=real_sample, fake_sample=fake_sample, si_sample=si_sample)
+        acc_real = au_pred_on_real.to(torch.float).mean()
+        acc_fake = torch.eq(au_pred_on_fake, 0).to(torch.float).mean()
+        for k, v in (("au_loss", au_loss), ("au_loss_on_real", au_loss_on_real), ("au_loss_on_fake", au_loss_on_fake), ("au_out_on_real", au_out_on_real),
+                     ("au_out_on_fake", au_out_on_fake), ("au_acc", 0.5 * (acc_real + acc_fake)), ("au_acc_on_real", acc_real), ("au_acc_on_fake", acc_fake),
+                     ("im_loss", im_loss)):
+            stats[k].append(v)
+    if not stats["au_loss"]:
+        return
+    for cat, key, name in (("eval losses", "dis loss", "au_loss"), ("eval losses", "dis loss on real", "au_loss_on_real"),
+                           ("eval losses", "dis loss on fake", "au_loss_on_fake"), ("eval au out", "au out on real", "au_out_on_real"),
+                           ("eval au out", "au out on fake", "au_out_on_fake"), ("eval accuracy", "dis acc", "au_acc"),
+                           ("eval accuracy", "dis acc on real", "au_acc_on_real"), ("eval accuracy", "dis acc on fake", "au_acc_on_fake"),
+                           ("eval losses", "gen loss", "im_loss")):
+        logger.add_scalar(category=cat, k=key, v=_mean(stats[name]), global_step=global_step)
+
+
+def _log_encodings(trainer, logger, real_sample, si_sample, fake_sample, global_step):
+    """Reference :300-340: feature statistics of D's two encoders on the current batch."""
+    au = trainer.module.authenticator
+    with torch.no_grad():
+        enc = {}
+        for which, encode in (("src", au.src_encode_sample), ("env", au.env_encode_sample)):
+            enc[which] = {"real": encode(real_sample), "si": encode(si_sample), "fake": encode(fake_sample)}
+        for which in ("src", "env"):
+            e = enc[which]
+            logger.add_scalar(category='train-au_%s_mean' % which, k='abs[real-si]', v=torch.abs(e["real"].mean(1) - e["si"].mean(1)).mean().item(),
+                              global_step=global_step)
+            logger.add_scalar(category='train-au_%s_mean' % which, k='abs[fake-si]', v=torch.abs(e["fake"].mean(1) - e["si"].mean(1)).mean().item(),
+                              global_step=global_step)
+            for name in ("real", "si", "fake"):
+                logger.add_scalar(category='train-au_%s_std' % which, k=name, v=mb.custom_std(e[name]).mean().item(), global_step=global_step)
+
+
+def train_epoch(device, logger, epoch, trainer, train_ds, val_ds, train_batch_size, val_batch_size, num_workers, save_every, eval_every, save_imgs_every,
+                train_eval_indices, val_eval_indices, tb_log_every=100, tb_log_enc_every=500, n_au_steps=1, dbg=False, use_cuda_graph=False):
+    """Reference :186-357.  One pass over `train_ds`."""
+    names = ("au_loss", "au_loss_on_real", "au_loss_on_fake", "au_reg", "au_out_on_real", "au_out_on_fake", "im_loss")
+    buf = {k: [] for k in names}
+    pred_real, pred_fake = [], []
+    batches, n_batches = _batches(train_ds, train_batch_size, True, num_workers)
+    num_iters = min(50, n_batches) if dbg else n_batches
+    graphed = None
+    for data_batch in itertools.islice(batches, num_iters):
+        real_sample, leaked_sample, si_sample = (data_batch[k].to(device) for k in ("real_sample", "leaked_sample", "si_sample"))
+        if use_cuda_graph and n_au_steps == 1 and trainer.module.reg_param == 0:
+            # whole iteration as one graph replay (host bookkeeping -- global step, LR schedule -- happens inside GraphedIteration)
+            if graphed is None:
+                from .cuda_graph import GraphedIteration
+                graphed = getattr(trainer, "_graphed_iteration", None) or GraphedIteration(trainer, leaked_sample, real_sample, si_sample)
+                trainer._graphed_iteration = graphed
+            out = graphed(leaked_sample, real_sample, si_sample)
+            global_step = trainer.module.global_step
+            im_loss, au_loss, au_loss_on_real, au_loss_on_fake, au_reg, au_out_on_real, au_out_on_fake = (t.clone() for t in out)
+            au_pred_on_real = au_pred_on_fake = None
+            fake_sample = None
+        else:
+            trainer.module.do_global_step()
+            trainer.module.update_learning_rate()
+            global_step = trainer.module.global_step
+            if (global_step + 1) % n_au_steps == 0:
+                im_loss, fake_sample, _ = im_train_step(trainer=trainer, leaked_sample=leaked_sample, si_sample=si_sample)
+            else:
+                im_loss, fake_sample, _ = im_eval_step(trainer=trainer, leaked_sample=leaked_sample, si_sample=si_sample)
+            (au_loss, au_loss_on_real, au_loss_on_fake, au_reg, au_out_on_real, au_out_on_fake, au_pred_on_real, au_pred_on_fake, fake_sample) = au_train_step(
+                trainer=trainer, real_sample=real_sample, fake_sample=fake_sample, si_sample=si_sample)
+        for k, v in zip(names, (au_loss, au_loss_on_real, au_loss_on_fake, au_reg, au_out_on_real, au_out_on_fake, im_loss)):
+            buf[k].append(v)
+        if au_pred_on_real is not None:
+            pred_real.append(au_pred_on_real.view(-1))
+            pred_fake.append(au_pred_on_fake.view(-1))
+
+        if global_step % tb_log_every == 0:
+            m = trainer.module
+            logger.add_scalar(category='lr', k='au', v=m.au_lr, global_step=global_step)
+            logger.add_scalar(category='lr', k='im', v=m.im_lr, global_step=global_step)
+            logger.add_scalar(category='lr', k='im_lm', v=m.im_noise_mapping_lr, global_step=global_step)
+            for cat, key, name in (('train_losses', 'dis_loss', "au_loss"), ('train_losses', 'dis_loss_on_real', "au_loss_on_real"),
+                                   ('train_losses', 'dis_loss_on_fake', "au_loss_on_fake"), ('train_losses', 'dis_reg', "au_reg"),
+                                   ('train_au_out', 'au_out_on_real', "au_out_on_real"), ('train_au_out', 'au_out_on_fake', "au_out_on_fake"),
+                                   ('train losses', 'gen loss', "im_loss")):
+                logger.add_scalar(category=cat, k=key, v=_mean(buf[name]), global_step=global_step)
+            if pred_real:
+                acc_real = torch.cat(pred_real).to(torch.float).mean()
+                acc_fake = torch.eq(torch.cat(pred_fake), 0).to(torch.float).mean()
+                logger.add_scalar(category='train_accuracy', k='dis_acc', v=(0.5 * (acc_real + acc_fake)).item(), global_step=global_step)
+                logger.add_scalar(category='train_accuracy', k='dis_acc_on_real', v=acc_real.item(), global_step=global_step)
+                logger.add_scalar(category='train_accuracy', k='dis_acc_on_fake', v=acc_fake.item(), global_step=global_step)
+            buf = {k: [] for k in names}
+            pred_real, pred_fake = [], []
+
+        if fake_sample is not None and global_step % tb_log_enc_every == 0:
+            _log_encodings(trainer, logger, real_sample, si_sample, fake_sample, global_step)
+        if global_step % save_every == 0 and (not dist.is_initialized() or dist.get_rank() == 0):
+            trainer.module.save(epoch=epoch)
+        if global_step % eval_every == 0 and val_ds is not None:
+            eval_step(device=device, trainer=trainer, ds=val_ds, logger=logger, batch_size=val_batch_size)
+
+
+def train_gim_imgs(device_name, device_ids, outdir, train_ds, val_ds, authenticator, impersonator, m, n, k, reg_param, remove_noise_mean, au_lr, im_lr,
+                   beta1, beta2, env_noise_mapping_lr, lr_gamma, milestones, resume_from_ckpt, n_epochs, batch_size, num_workers, save_every, eval_every,
+                   save_imgs_every, train_eval_indices, val_eval_indices, n_au_steps=1, dbg=False, logger=None, use_cuda_graph=False):
+    """Reference :360-445.  `batch_size` is the per-process batch; under torchrun each rank trains on its own episodes and the
+    gradients are averaged (ddp.attach), which reproduces nn.DataParallel's mean over the global batch."""
+    device = get_device(device_type=device_name, device_ids=device_ids)
+    logger = logger if logger is not None else ScalarLog()
+    authenticator, impersonator = authenticator.to(device), impersonator.to(device)
+    trainer = GIMImgTrainer(outdir=outdir, m=m, n=n, k=k, authenticator=authenticator, impersonator=impersonator, au_lr=au_lr, im_lr=im_lr,
+                            env_noise_mapping_lr=env_noise_mapping_lr, beta1=beta1, beta2=beta2, lr_milestones=milestones, lr_gamma=lr_gamma,
+                            reg_param=reg_param, remove_noise_mean=remove_noise_mean).to(device)
+    if resume_from_ckpt:
+        trainer.resume_from_ckpt(ckpt_path=resume_from_ckpt)
+        trainer.to(device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        ddp.attach(trainer.authenticator_opt)
+        ddp.attach(trainer.impersonator_opt)
+    trainer = DataParallelMock(trainer)
+    os.makedirs(outdir, exist_ok=True)
+    for ep in range(n_epochs):
+        try:
+            train_epoch(device=device, logger=logger, epoch=ep, trainer=trainer, train_ds=train_ds, val_ds=val_ds, train_batch_size=batch_size,
+                        val_batch_size=batch_size, num_workers=num_workers, save_every=save_every, eval_every=eval_every, save_imgs_every=save_imgs_every,
+                        train_eval_indices=train_eval_indices, val_eval_indices=val_eval_indices, n_au_steps=n_au_steps, dbg=dbg,
+                        use_cuda_graph=use_cuda_graph)
+        except KeyboardInterrupt:
+            trainer.module.save(epoch=ep)
+            raise
+    trainer.module.save(epoch=n_epochs - 1)
+    return trainer, logger

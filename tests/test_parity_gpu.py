@@ -381,3 +381,44 @@ def test_authentication_eval_vs_oracle(schemas, prec):
     res = AE.eval_dis_on_multiple_im("cuda", mk(), 2, 0, authenticator, {"replay": AE.Impersonator(AE.replay_impersonator),
                                                                          "rnd_src": AE.Impersonator(lambda leaked_sample, n: AE.rand_source_impersonator(leaked_sample, n, mk()))})
     assert set(res) == {"replay", "rnd_src"} and all(0.0 <= r["auc"] <= 1.0 for r in res.values())
+
+
+def test_training_loop_runs_logs_saves_and_resumes(schemas, tmp_path):
+    """the kept-name training loop (reference training/gim_img_training.py:186-445) on a device-resident episode
+    source: iterations advance the global step, the reference's scalar categories are logged without per-iteration host reads,
+    the validation pass and the checkpoint cadence run, a checkpoint resumes, and the CUDA-graph mode gives the same kind of log."""
+    import os
+    g, M = pkg()[0], pkg()[1]
+    from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_training as T
+    from optimalstrategiesagainstgenerativeattacks_b200 import img_datasets as D
+    g.set_precision("bf16")
+    classes = D.synthetic_classes(3, 8, 3, 16, seed=5) * 0.5
+    mk = lambda seed: D.ResidentGIMDataSet(classes, m=2, n=2, k=2, example_cnt_per_class=2, device="cuda", seed=seed)
+    common = dict(device_name="cuda", device_ids=[0], m=2, n=2, k=2, remove_noise_mean=True, au_lr=1e-4, im_lr=1e-4, beta1=0.0, beta2=0.99,
+                  env_noise_mapping_lr=1e-6, lr_gamma=0.3, milestones=(), batch_size=2, num_workers=0, save_every=2, eval_every=2, save_imgs_every=10 ** 9,
+                  train_eval_indices=[], val_eval_indices=[], n_au_steps=1)
+    torch.manual_seed(3)
+    out = str(tmp_path / "run")
+    trainer, log = T.train_gim_imgs(outdir=out, train_ds=mk(1), val_ds=mk(2), authenticator=M.get_au(16, 3, 64), impersonator=M.get_im(16, 3, 64),
+                                    reg_param=10.0, resume_from_ckpt=None, n_epochs=2, **common)
+    assert trainer.module.global_step == 5                                   # 2 epochs x 3 iterations, counted from 0
+    for key in (("train_losses", "dis_loss"), ("train_losses", "dis_reg"), ("train losses", "gen loss"), ("train_accuracy", "dis_acc"), ("lr", "au"),
+                ("eval losses", "dis loss"), ("eval accuracy", "dis acc"), ("train-au_src_std", "fake"), ("train-au_env_mean", "abs[fake-si]")):
+        assert key in log.scalars and all(np.isfinite(v) for _, v in log.scalars[key]), key
+    ckpts = sorted(os.listdir(os.path.join(out, "ckpts")))
+    assert ckpts and ckpts[-1].endswith(".pt")
+    # resume: the step counter and the weights come back
+    w_ref = trainer.module.authenticator.dis.mlp.model[4].weight.detach().clone()
+    trainer2, _ = T.train_gim_imgs(outdir=str(tmp_path / "run2"), train_ds=mk(1), val_ds=None, authenticator=M.get_au(16, 3, 64), impersonator=M.get_im(16, 3, 64),
+                                   reg_param=10.0, resume_from_ckpt=os.path.join(out, "ckpts", ckpts[-1]), n_epochs=0, **common)
+    assert trainer2.module.global_step == 5 and torch.equal(trainer2.module.authenticator.dis.mlp.model[4].weight, w_ref)
+    # whole-iteration CUDA graph (reg 0): same loop body as one graph replay per iteration; scalars logged every iteration here
+    tr3, _ = T.train_gim_imgs(outdir=str(tmp_path / "run3"), train_ds=mk(1), val_ds=None, authenticator=M.get_au(16, 3, 64), impersonator=M.get_im(16, 3, 64),
+                              reg_param=0.0, resume_from_ckpt=None, n_epochs=0, **common)
+    log3 = T.ScalarLog()
+    step0 = tr3.module.global_step
+    T.train_epoch(device=torch.device("cuda", 0), logger=log3, epoch=0, trainer=tr3, train_ds=mk(1), val_ds=None, train_batch_size=2, val_batch_size=2,
+                  num_workers=0, save_every=10 ** 9, eval_every=10 ** 9, save_imgs_every=10 ** 9, train_eval_indices=[], val_eval_indices=[], tb_log_every=1,
+                  tb_log_enc_every=10 ** 9, n_au_steps=1, use_cuda_graph=True)
+    vals = [v for _, v in log3.scalars[("train_losses", "dis_loss")]]
+    assert len(vals) == 3 and all(np.isfinite(v) for v in vals) and tr3.module.global_step > step0
