@@ -948,13 +948,17 @@ struct WgradTcParams {
     int total_tiles;
 };
 
-template <int kDummy>
+// kPair = 1: cta_group::2 -- the two CTAs of a cluster own 128 output channels each (M = 256) and each stages half of the input-
+// channel tile (N/2 columns of the MN-major B operand); loads of both complete on the leader's barrier, commits are multicast.
+template <int kPair>
 __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
                                                                float* __restrict__ gw, const WgradTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int a_bytes = 2 * kATileBytes;                               // 128 co = two 64-channel boxes
-    const int b_bytes = (p.block_n / 64) * kATileBytes;
+    const int b_cols = kPair ? p.block_n / 2 : p.block_n;              // input channels staged by this CTA
+    const int b_bytes = (b_cols / 64) * kATileBytes;
     const int stage_bytes = a_bytes + b_bytes;
     uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
@@ -962,11 +966,12 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
     uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int t = blockIdx.x;
+    int t = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tap = t % (p.ks * p.ks); t /= (p.ks * p.ks);
-    const int co_t = t % p.co_tiles;
-    const int ci_t = t / p.co_tiles;
-    const int co0 = co_t * 128, ci0 = ci_t * p.block_n;
+    const int co_groups = kPair ? p.co_tiles / 2 : p.co_tiles;
+    const int co_t = t % co_groups;
+    const int ci_t = t / co_groups;
+    const int co0 = (kPair ? co_t * 2 + (int)rank : co_t) * 128, ci0 = ci_t * p.block_n;
     const int pad = (p.ks - 1) / 2;
     const int dr = tap / p.ks - pad, dq = tap % p.ks - pad;
     const int tile_begin = blockIdx.y * p.tiles_per_split;
@@ -982,9 +987,11 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 1) {
+        if (kPair) tmem_alloc_2sm(tmem_slot, tmem_cols); else tmem_alloc(tmem_slot, tmem_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -993,24 +1000,33 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
             int s = 0;
             uint32_t ph = 1;
             int tw = tile_begin % p.tiles_w, th = (tile_begin / p.tiles_w) % p.tiles_h, tn = tile_begin / (p.tiles_w * p.tiles_h);
-            const int nb = p.block_n / 64;
+            const int nb = b_cols / 64;
+            const int cib = ci0 + (int)rank * b_cols;                   // first input channel staged by this CTA
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[s], ph);
                 const int w0 = tw * p.bw, h0 = th * p.bh, img0 = tn * p.bn;
                 uint8_t* sa = smem + s * stage_bytes;
                 uint8_t* sb = sa + a_bytes;
-                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                tma_load_4d(sa, &map_gy, &full_bar[s], co0, w0, h0, img0);
-                tma_load_4d(sa + kATileBytes, &map_gy, &full_bar[s], co0 + 64, w0, h0, img0);
-                for (int j = 0; j < nb; ++j)
-                    tma_load_4d(sb + j * kATileBytes, &map_x, &full_bar[s], ci0 + 64 * j, w0 + dq, h0 + dr, img0);
+                if (kPair) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)stage_bytes);      // both CTAs' bytes land on the leader's barrier
+                    tma_load_4d_2sm(sa, &map_gy, &full_bar[s], co0, w0, h0, img0);
+                    tma_load_4d_2sm(sa + kATileBytes, &map_gy, &full_bar[s], co0 + 64, w0, h0, img0);
+                    for (int j = 0; j < nb; ++j)
+                        tma_load_4d_2sm(sb + j * kATileBytes, &map_x, &full_bar[s], cib + 64 * j, w0 + dq, h0 + dr, img0);
+                } else {
+                    mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                    tma_load_4d(sa, &map_gy, &full_bar[s], co0, w0, h0, img0);
+                    tma_load_4d(sa + kATileBytes, &map_gy, &full_bar[s], co0 + 64, w0, h0, img0);
+                    for (int j = 0; j < nb; ++j)
+                        tma_load_4d(sb + j * kATileBytes, &map_x, &full_bar[s], cib + 64 * j, w0 + dq, h0 + dr, img0);
+                }
                 if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 1, 1);
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 1, 1, kPair ? 256u : 128u);
             const uint32_t s0 = smem_u32(smem);
             const uint64_t desc_a0 = make_desc_sw128(s0, kATileBytes, 1024), desc_b0 = make_desc_sw128(s0 + a_bytes, kATileBytes, 1024);
             const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
@@ -1023,13 +1039,15 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
                 tc_fence_after();
                 const uint32_t acc = kb != 0 ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < kBlockM / 16; ++k)                 // 128 pixels per stage = 8 MMAs of K = 16, 2 KB apart
-                    umma_bf16((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
-                umma_commit(&empty_bar[s]);
+                for (int k = 0; k < kBlockM / 16; ++k) {               // 128 pixels per stage = 8 MMAs of K = 16, 2 KB apart
+                    if (kPair) umma_bf16_2sm((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
+                    else umma_bf16((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
+                }
+                if (kPair) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
                 da += stage_step; db += stage_step;
                 if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
             }
-            umma_commit(tmem_full_bar);
+            if (kPair) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
         }
     } else {
         mbar_wait(tmem_full_bar, 0);
@@ -1052,10 +1070,10 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
+        if (kPair) tmem_dealloc_2sm(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -1263,12 +1281,17 @@ int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd
     long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     if (total > 2147483647LL) return fail(GIM_E_ARG, "conv_wgrad_tc: too many tiles");
     p.total_tiles = (int)total;
-    p.block_n = cin > 64 ? 128 : 64;
+    static const int wg_pair_mode = env_int("GIM_WGRAD_PAIR", 1);
+    // cta_group::2: 256 output channels per CTA pair, each CTA stages half of a 128- or 256-wide input-channel tile
+    // (measured, tools/conv_bench.py: +23 % on 256->256 @16x16, +5..6 % on the 8x8 layers, but -10..28 % on 1x1 and 4x4 layers, whose few
+    // large CTAs quantise badly -- so only with a filter and at least 256 pixel tiles)
+    const bool pair = wg_pair_mode && cout % 256 == 0 && cin % 128 == 0 && (wg_pair_mode > 1 || (ks > 1 && total >= 256));
+    p.block_n = pair ? (cin % 256 == 0 ? 256 : 128) : (cin > 64 ? 128 : 64);
     p.co_tiles = (cout + 127) / 128;
     p.ci_tiles = (cin + p.block_n - 1) / p.block_n;
-    const int stage_bytes = 2 * kATileBytes + (p.block_n / 64) * kATileBytes;
+    const int stage_bytes = 2 * kATileBytes + ((pair ? p.block_n / 2 : p.block_n) / 64) * kATileBytes;
     p.stages = (200 * 1024) / stage_bytes;
-    const long long out_tiles = (long long)ks * ks * p.co_tiles * p.ci_tiles;
+    const long long out_tiles = (long long)ks * ks * (pair ? p.co_tiles / 2 : p.co_tiles) * p.ci_tiles * (pair ? 2 : 1);      // CTAs along x
     long long want = ((long long)num_sms() * 2 + out_tiles - 1) / out_tiles;        // ~2 waves of CTAs over the chip
     long long max_split = (total + 3) / 4;                                         // at least ~4 pixel tiles per CTA
     if (max_split < 1) max_split = 1;
@@ -1289,6 +1312,26 @@ int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd
     }
     if (out_tiles > 2147483647LL) return fail(GIM_E_ARG, "conv_wgrad_tc: too many output tiles");
     dim3 grid((unsigned)out_tiles, splits);
+    if (pair) {
+        static bool attr_set_pair = false;
+        if (!attr_set_pair) {
+            if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                return fail(GIM_E_CUDA, "conv_wgrad_tc: cannot raise dynamic shared memory limit");
+            attr_set_pair = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, conv_wgrad_tc_kernel<1>, map_gy, map_x, gw, p) != cudaSuccess) return fail(GIM_E_CUDA, "conv_wgrad_tc: cluster launch failed");
+        return check_launch("conv_wgrad_tc_pair");
+    }
     conv_wgrad_tc_kernel<0><<<grid, 192, smem, st>>>(map_gy, map_x, gw, p);
     return check_launch("conv_wgrad_tc");
 }
