@@ -1,38 +1,80 @@
-"""Checkpoint container with the reference's on-disk schema (training/checkpoints.py:9-44): one torch.save'd dict
-{'global_step', 'last_epoch', <name>: state_dict ...}; files written by either implementation load in the other."""
+"""Checkpoint container for the GIM trainers.
+
+On-disk schema = the reference's (training/checkpoints.py:9-44): ONE `torch.save`d dict
+    {'global_step': int, 'last_epoch': int, <registered name>: <that object's state_dict()>, ...}
+so files written by either implementation load in the other.  What differs is how the file gets there:
+
+  * the state dicts are snapshotted to host memory first, so the training stream is only blocked for the device->host copies;
+  * the file is written to `<name>.tmp` and renamed, so a crash never leaves a truncated checkpoint behind;
+  * with `async_save=True` the serialisation + write run on a background thread (`wait()` joins it; `load` / the next `save`
+    wait for it on their own) -- at > 2000 episodes/s a synchronous 1 GB `torch.save` would cost hundreds of iterations.
+"""
 import os
+import threading
 
 import torch
 
 
+def _to_host(obj):
+    """Deep copy of a state_dict-like structure with every tensor moved to host memory."""
+    if torch.is_tensor(obj):
+        return obj.detach().to("cpu", copy=True)
+    if isinstance(obj, dict):
+        return type(obj)((k, _to_host(v)) for k, v in obj.items())
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_host(v) for v in obj)
+    return obj
+
+
 class CheckpointIO:
-    def __init__(self, checkpoint_dir, **kwargs):
-        self.module_dict = kwargs
+    def __init__(self, checkpoint_dir, async_save=False, **named_objects):
         self.checkpoint_dir = checkpoint_dir
+        self.module_dict = dict(named_objects)          # name -> anything with state_dict() / load_state_dict()
+        self.async_save = async_save
+        self._writer = None
         os.makedirs(checkpoint_dir, exist_ok=True)
 
-    def register_modules(self, **kwargs):
-        self.module_dict.update(kwargs)
+    def register_modules(self, **named_objects):
+        # NB the trainers register their GlobalStep under the name 'global_step': in the file that entry ({'global_step': n}) then
+        # replaces the plain integer written first -- the reference's files look exactly like this, so it is kept
+        self.module_dict.update(named_objects)
+
+    # -- writing -------------------------------------------------------------------------------------------------
+    def _write(self, payload, path):
+        tmp = path + ".tmp"
+        torch.save(payload, tmp)
+        os.replace(tmp, path)
+
+    def wait(self):
+        """Block until a background save (if any) has reached the disk."""
+        writer, self._writer = self._writer, None
+        if writer is not None:
+            writer.join()
 
     def save(self, global_step, last_epoch, filename):
-        filename = os.path.join(self.checkpoint_dir, filename)
-        outdict = {'global_step': global_step, "last_epoch": last_epoch}
-        for k, v in self.module_dict.items():
-            outdict[k] = v.state_dict()
-        torch.save(outdict, filename)
-
-    def load(self, filepath):
-        if os.path.exists(filepath):
-            print('=> Loading checkpoint...')
-            out_dict = torch.load(filepath, map_location='cpu')
-            global_step = out_dict['global_step']
-            last_epoch = out_dict['last_epoch']
-            for k, v in self.module_dict.items():
-                if k in out_dict:
-                    v.load_state_dict(out_dict[k])
-                else:
-                    print('Warning: Could not find %s in checkpoint!' % k)
+        self.wait()
+        payload = {"global_step": global_step, "last_epoch": last_epoch}
+        for name, obj in self.module_dict.items():
+            payload[name] = _to_host(obj.state_dict())
+        path = os.path.join(self.checkpoint_dir, filename)
+        if self.async_save:
+            self._writer = threading.Thread(target=self._write, args=(payload, path), daemon=False)
+            self._writer.start()
         else:
-            global_step = -1
-            last_epoch = -1
-        return global_step, last_epoch
+            self._write(payload, path)
+        return path
+
+    # -- reading -------------------------------------------------------------------------------------------------
+    def load(self, filepath):
+        """-> (global_step, last_epoch); (-1, -1) when the file does not exist (a fresh run), like the reference."""
+        self.wait()
+        if not os.path.exists(filepath):
+            return -1, -1
+        print('=> Loading checkpoint...')
+        stored = torch.load(filepath, map_location='cpu')
+        for name, obj in self.module_dict.items():
+            if name not in stored:
+                print('Warning: Could not find %s in checkpoint!' % name)
+                continue
+            obj.load_state_dict(stored[name])
+        return stored["global_step"], stored["last_epoch"]

@@ -26,151 +26,126 @@ class NHWC:
         self.t = t
 
 
+def _down_plan(img_size, img_channels, style_dim, min_n_channels):
+    """Channel plan of a down-sampling pyramid that ends at 4x4 (reference gim_img_models.py:27-33, 108-113):
+    -> (number of blocks, floor of the channel count, [c_in, c_1, ..., c_n], index of the block the attention precedes)."""
+    n_blocks = int(math.log2(img_size)) - 2
+    floor = int(max(min_n_channels, style_dim / (2 ** (n_blocks - 1))))
+    widths = [img_channels] + [min(style_dim, int(floor * (2 ** i))) for i in range(n_blocks)]
+    return n_blocks, floor, widths, int(math.ceil(n_blocks / 2))
+
+
+def _up_plan(n_blocks, img_channels, style_dim, floor):
+    """Mirror image for the up-sampling pyramids (reference :70-74, 151-156): widest first, image channels last."""
+    widths = [min(style_dim, int(floor * (2 ** i))) for i in range(n_blocks)][::-1] + [img_channels]
+    return widths, int(math.ceil(n_blocks / 2))
+
+
 class Encoder(nn.Module):
-    """Reference gim_img_models.py:19-57: [N, C, S, S] -> [N, style_dim]."""
+    """Reference gim_img_models.py:19-57: [N, C, S, S] -> [N, style_dim]: ResBlockDown pyramid to 4x4 (self-attention before block
+    `att_loc`), global max, LeakyReLU."""
 
     def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64, use_out_lrelu=True):
         super().__init__()
-        self.img_size = img_size
-        self.img_channels = img_channels
-        self.style_dim = style_dim
-        self.use_out_lrelu = use_out_lrelu
-        self.n_down_blocks = int(math.log2(img_size)) - 2
-        self.min_n_channels = int(max(min_n_channels, style_dim / (2 ** (self.n_down_blocks - 1))))
-        self.channel_sizes = [img_channels] + [min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_down_blocks)]
-        self.att_loc = int(math.ceil(self.n_down_blocks / 2))
-        self.lrelu = nn.LeakyReLU(0.2)
-        self.pool = nn.AdaptiveMaxPool2d((1, 1))
-        self.down_blocks = nn.ModuleList()
-        for i in range(self.n_down_blocks):
-            self.down_blocks.append(mb.ResBlockDown(self.channel_sizes[i], self.channel_sizes[i + 1]))
+        self.img_size, self.img_channels, self.style_dim, self.use_out_lrelu = img_size, img_channels, style_dim, use_out_lrelu
+        self.n_down_blocks, self.min_n_channels, self.channel_sizes, self.att_loc = _down_plan(img_size, img_channels, style_dim, min_n_channels)
+        self.down_blocks = nn.ModuleList(mb.ResBlockDown(ci, co) for ci, co in zip(self.channel_sizes[:-1], self.channel_sizes[1:]))
         self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
 
     def forward(self, x):
         x = _as_nhwc(x)
         mb.sn_prepare_module(self, skip=() if self.att_loc < self.n_down_blocks else (self.att,))
-        for i in range(self.n_down_blocks):
+        for i, block in enumerate(self.down_blocks):
             if i == self.att_loc:
                 x = self.att(x)
-            x = self.down_blocks[i](x, want_ops=i + 1 < self.n_down_blocks)       # the next consumer reads the bf16 operands
+            x = block(x, want_ops=i + 1 < self.n_down_blocks)       # the next consumer reads the bf16 operands
         if isinstance(x, ops.Act):
             x = x.t32
         x = ops.GlobalMaxFn.apply(x)
-        if self.use_out_lrelu:
-            x = ops.lrelu(x)
-        return x
+        return ops.lrelu(x) if self.use_out_lrelu else x
 
 
 class EnvDecoder(nn.Module):
-    """Reference gim_img_models.py:63-95: [N, style_dim] -> [N, C, S, S] (no output nonlinearity)."""
+    """Reference gim_img_models.py:63-95: [N, style_dim] -> [N, C, S, S]: ResBlockUp pyramid from 1x1 (no output nonlinearity)."""
 
     def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64):
         super().__init__()
-        self.img_size = img_size
-        self.img_channels = img_channels
-        self.style_dim = style_dim
-        self.min_n_channels = min_n_channels
+        self.img_size, self.img_channels, self.style_dim, self.min_n_channels = img_size, img_channels, style_dim, min_n_channels
         self.n_up_blocks = int(math.log2(img_size))
-        self.channel_sizes = list(
-            reversed([min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_up_blocks)])
-        ) + [img_channels]
-        self.att_loc = int(math.ceil(self.n_up_blocks / 2))
-        self.lrelu = nn.LeakyReLU(0.2)
-        self.up_blocks = nn.ModuleList()
-        for i in range(self.n_up_blocks):
-            self.up_blocks.append(mb.ResBlockUp(self.channel_sizes[i], self.channel_sizes[i + 1]))
+        self.channel_sizes, self.att_loc = _up_plan(self.n_up_blocks, img_channels, style_dim, min_n_channels)
+        self.up_blocks = nn.ModuleList(mb.ResBlockUp(ci, co) for ci, co in zip(self.channel_sizes[:-1], self.channel_sizes[1:]))
         self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
 
     def forward(self, x, nhwc_out=False):
         n, c = x.shape
-        x = x.reshape(n, 1, 1, c)
+        x = x.reshape(n, 1, 1, c)                          # a [N, C] feature vector is a 1x1 NHWC activation
         if x.dtype != ops.act_dtype():
             x = ops.to_nhwc(x.reshape(n, c, 1, 1))
         mb.sn_prepare_module(self, skip=() if self.att_loc < self.n_up_blocks else (self.att,))
-        for i in range(self.n_up_blocks):
+        for i, block in enumerate(self.up_blocks):
             if i == self.att_loc:
                 x = self.att(x)
-            x = self.up_blocks[i](x)
+            x = block(x)
         return NHWC(x) if nhwc_out else ops.from_nhwc(x)
 
 
 class Img2ImgDownModule(nn.Module):
-    """Reference gim_img_models.py:101-139."""
+    """Reference gim_img_models.py:101-139: ResBlockDown (9x9 in the first block) + affine InstanceNorm per level."""
 
     def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64):
         super().__init__()
-        self.img_size = img_size
-        self.img_channels = img_channels
-        self.style_dim = style_dim
-        self.n_down_blocks = int(math.log2(img_size)) - 2
-        self.min_n_channels = int(max(min_n_channels, style_dim / (2 ** (self.n_down_blocks - 1))))
-        self.channel_sizes = [img_channels] + [min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_down_blocks)]
-        self.att_loc = int(math.ceil(self.n_down_blocks / 2))
-        self.lrelu = nn.LeakyReLU(0.2)
-        self.pool = nn.AdaptiveMaxPool2d((1, 1))
-        self.down_blocks = nn.ModuleList()
-        self.in_layers = nn.ModuleList()
-        for i in range(self.n_down_blocks):
-            if i == 0:
-                self.down_blocks.append(mb.ResBlockDown(self.channel_sizes[i], self.channel_sizes[i + 1], conv_size=9, padding_size=4))
-            else:
-                self.down_blocks.append(mb.ResBlockDown(self.channel_sizes[i], self.channel_sizes[i + 1]))
-            self.in_layers.append(mb.InstanceNormAffine(self.channel_sizes[i + 1]))
+        self.img_size, self.img_channels, self.style_dim = img_size, img_channels, style_dim
+        self.n_down_blocks, self.min_n_channels, self.channel_sizes, self.att_loc = _down_plan(img_size, img_channels, style_dim, min_n_channels)
+        self.down_blocks, self.in_layers = nn.ModuleList(), nn.ModuleList()
+        for i, (ci, co) in enumerate(zip(self.channel_sizes[:-1], self.channel_sizes[1:])):
+            wide = {"conv_size": 9, "padding_size": 4} if i == 0 else {}
+            self.down_blocks.append(mb.ResBlockDown(ci, co, **wide))
+            self.in_layers.append(mb.InstanceNormAffine(co))
         self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
 
     def forward(self, x):
-        for i in range(self.n_down_blocks):
+        for i, (block, norm) in enumerate(zip(self.down_blocks, self.in_layers)):
             if i == self.att_loc:
                 x = self.att(x)
-            x = self.down_blocks[i](x)
-            x = self.in_layers[i](x.t32 if isinstance(x, ops.Act) else x)
+            x = block(x)
+            x = norm(x.t32 if isinstance(x, ops.Act) else x)
         return x
 
 
 class Img2ImgAdaInResModule(nn.Module):
-    """Reference gim_img_models.py:142-162."""
+    """Reference gim_img_models.py:142-162: `n_blocks` AdaResBlock2 at the bottleneck resolution."""
 
     def __init__(self, style_dim=512, n_blocks=5):
         super().__init__()
-        self.style_dim = style_dim
-        self.n_blocks = n_blocks
-        self.res_blocks = nn.ModuleList()
-        for i in range(self.n_blocks):
-            self.res_blocks.append(mb.AdaResBlock2(channels=style_dim, style_dim=style_dim))
+        self.style_dim, self.n_blocks = style_dim, n_blocks
+        self.res_blocks = nn.ModuleList(mb.AdaResBlock2(channels=style_dim, style_dim=style_dim) for _ in range(n_blocks))
 
     def forward(self, x, style, styles=None):
-        for i in range(self.n_blocks):
-            x = self.res_blocks[i](x=x, style=style, styles=None if styles is None else styles[i])
+        for i, block in enumerate(self.res_blocks):
+            x = block(x=x, style=style, styles=None if styles is None else styles[i])
         return x
 
 
 class Img2ImgAdaInUpModule(nn.Module):
-    """Reference gim_img_models.py:165-215 (tanh output)."""
+    """Reference gim_img_models.py:165-215: AdaResBlockUp2 pyramid back to the image (9x9 in the last block), tanh."""
 
     def __init__(self, img_size, img_channels, style_dim=512, min_n_channels=64):
         super().__init__()
-        self.img_size = img_size
-        self.img_channels = img_channels
-        self.style_dim = style_dim
+        self.img_size, self.img_channels, self.style_dim = img_size, img_channels, style_dim
         self.n_up_blocks = int(math.log2(img_size)) - 2
         self.min_n_channels = int(max(min_n_channels, style_dim / (2 ** (self.n_up_blocks - 1))))
-        self.channel_sizes = list(
-            reversed([min(style_dim, int(self.min_n_channels * (2 ** i))) for i in range(self.n_up_blocks)])
-        ) + [img_channels]
-        self.att_loc = int(math.ceil(self.n_up_blocks / 2))
+        self.channel_sizes, self.att_loc = _up_plan(self.n_up_blocks, img_channels, style_dim, self.min_n_channels)
         self.up_blocks = nn.ModuleList()
-        for i in range(self.n_up_blocks):
-            last = i == (self.n_up_blocks - 1)
-            self.up_blocks.append(mb.AdaResBlockUp2(
-                in_channels=self.channel_sizes[i], out_channels=self.channel_sizes[i + 1], style_dim=style_dim,
-                conv_size=9 if last else 3, padding_size=4 if last else 1))
+        for i, (ci, co) in enumerate(zip(self.channel_sizes[:-1], self.channel_sizes[1:])):
+            k = 9 if i == self.n_up_blocks - 1 else 3
+            self.up_blocks.append(mb.AdaResBlockUp2(in_channels=ci, out_channels=co, style_dim=style_dim, conv_size=k, padding_size=(k - 1) // 2))
         self.att = mb.SelfAttention(self.channel_sizes[self.att_loc])
 
     def forward(self, x, style, styles=None):
-        for i in range(self.n_up_blocks):
+        for i, block in enumerate(self.up_blocks):
             if i == self.att_loc:
                 x = self.att(x)
-            x = self.up_blocks[i](x=x, style=style, styles=None if styles is None else styles[i])
+            x = block(x=x, style=style, styles=None if styles is None else styles[i])
         return ops.TanhFn.apply(x)
 
 
@@ -179,21 +154,16 @@ class AdaInImage2Image(nn.Module):
 
     def __init__(self, img_size, in_channels, out_channels, style_dim, n_adain_res_blocks=5, min_n_channels=64):
         super().__init__()
-        self.img_size = img_size
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.style_dim = style_dim
-        self.n_adain_res_blocks = n_adain_res_blocks
-        self.min_n_channels = min_n_channels
-        self.lrelu = nn.LeakyReLU(0.2)
-        self.sigmoid = nn.Sigmoid()
+        self.img_size, self.in_channels, self.out_channels, self.style_dim = img_size, in_channels, out_channels, style_dim
+        self.n_adain_res_blocks, self.min_n_channels = n_adain_res_blocks, min_n_channels
         self.down_block = Img2ImgDownModule(img_size=img_size, img_channels=in_channels, style_dim=style_dim, min_n_channels=min_n_channels)
         self.adain_res_block = Img2ImgAdaInResModule(style_dim=style_dim, n_blocks=n_adain_res_blocks)
         self.adain_up_block = Img2ImgAdaInUpModule(img_size=img_size, img_channels=out_channels, style_dim=style_dim, min_n_channels=min_n_channels)
 
     def forward(self, x, style):
         x = _as_nhwc(x)
-        skip = [m.att for m in (self.down_block, self.adain_up_block) if not m.att_loc < len(getattr(m, 'down_blocks', getattr(m, 'up_blocks', ())))]
+        skip = [m.att for m, n_blocks in ((self.down_block, self.down_block.n_down_blocks), (self.adain_up_block, self.adain_up_block.n_up_blocks))
+                if not m.att_loc < n_blocks]
         mb.sn_prepare_module(self, skip=skip)
         # the 4 x (n_res + n_up) style Linears share their input: one GEMM over the concatenated weights
         blocks = list(self.adain_res_block.res_blocks) + list(self.adain_up_block.up_blocks)

@@ -71,3 +71,26 @@ def test_comp_acc_and_agents():
     ds = D.ResidentGIMDataSet(D.synthetic_classes(4, 16, 1, 4, seed=1), m=5, n=5, k=5, example_cnt_per_class=2, device="cpu", seed=2)
     fake = AE.rand_source_impersonator(leaked, 5, ds)
     assert fake.shape == (2, 5, 1, 4, 4)
+
+
+def test_checkpoint_io_schema_async_and_atomic(tmp_path):
+    """CheckpointIO keeps the reference's file schema (training/checkpoints.py:20-44), writes atomically and can save in the background."""
+    from optimalstrategiesagainstgenerativeattacks_b200.checkpoints import CheckpointIO
+    from optimalstrategiesagainstgenerativeattacks_b200.utils import GlobalStep
+    net = torch.nn.Linear(3, 2)
+    gs = GlobalStep()
+    gs.set(41)
+    for async_save in (False, True):
+        io = CheckpointIO(str(tmp_path / ("a%d" % async_save)), async_save=async_save, net=net)
+        io.register_modules(global_step=gs)
+        path = io.save(global_step=41, last_epoch=3, filename="model_00000041.pt")
+        io.wait()
+        stored = torch.load(path, map_location="cpu")
+        assert set(stored) == {"global_step", "last_epoch", "net"} and stored["last_epoch"] == 3
+        assert stored["global_step"] == {"global_step": 41}            # the registered GlobalStep replaces the integer, as in the reference
+        assert not [f for f in __import__("os").listdir(io.checkpoint_dir) if f.endswith(".tmp")]
+        net2, gs2 = torch.nn.Linear(3, 2), GlobalStep()
+        io2 = CheckpointIO(io.checkpoint_dir, net=net2, global_step=gs2)
+        step, epoch = io2.load(path)
+        assert epoch == 3 and gs2.get() == 41 and torch.equal(net2.weight, net.weight)
+        assert io2.load(str(tmp_path / "missing.pt")) == (-1, -1)
