@@ -449,3 +449,17 @@ def test_matmul_tensor_core_path():
                                                        b64.requires_grad_().transpose(1, 2) if tb else b64.requires_grad_()) * probe).sum(), (a64, b64))
                 gg = torch.autograd.grad((got * probe.float().cuda()).sum(), (a, b))
                 assert rel_err(gg[0], gr[0]) < 3e-5 and rel_err(gg[1], gr[1]) < 3e-5
+
+
+def test_full_size_conv_kernels():
+    """The tcgen05 kernels at the O workload's full per-pass size (640 images = B 128 x 5 samples): forward (incl. the cta_group::2 variant
+    and the fused LeakyReLU / mask epilogues) and weight gradient on the hot layer shapes, each checked on an image subset against torch
+    with the same bf16 operands (tools/conv_bench.py asserts rel < 2e-3 fp32-out / 1e-2 bf16-out)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "conv_bench.py"), "--reps", "1", "--shapes", "0,1,2,6,8"], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("shape n=640") == 5 and "rel" in res.stdout
