@@ -574,121 +574,105 @@ __global__ void __launch_bounds__(256) first_block_quad_kernel(const float* __re
 // Weight gradients of the same two image-side convolutions in one pass over the gradients:
 //   gw_r1[tap][co][c] = sum_pix gt[pix][co] * bf16(LeakyReLU(x))[pix+tap][c]          (gt: bf16 masked gradient of the k x k conv output)
 //   gw_l1[co][c]      = sum_pp bf16(gy)[pp][co] * bf16(AvgPool2(x))[pp][c]           (gy: fp32 gradient of the pooled block output)
-// One thread = one image row x NCH output channels: it walks the row with a sliding 3 x 3 window of activated inputs (three new loads
-// per pixel; all index arithmetic hoisted out of the loop) and TAPS*C*NCH register accumulators.  Lanes of a warp hold consecutive
-// channel groups, so the gradient row is read with full 256-byte transactions.  Threads of a CTA are combined in shared memory, CTAs
-// with fp32 atomics (outputs zeroed by the caller).
-template <int C, int NCH>
+// Persistent CTAs walk bands of kWgRows image rows.  The band's gradient rows are staged in shared memory with 16-byte coalesced loads,
+// the activated input band (with halo) next to them; thread = (output channel, pixel group) keeps its 9*C + C partial sums in
+// registers across all bands: per pixel one gradient read from smem feeds 9*C FMAs whose other operand is a broadcast.  One
+// shared-memory reduction and one round of fp32 atomics per CTA at the end (outputs zeroed by the caller).
+constexpr int kWgRows = 4;
+template <int C>
 __global__ void __launch_bounds__(256) first_block_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ gt, const float* __restrict__ gy,
                                                                 float* __restrict__ gw_r1, float* __restrict__ gw_l1, int n, int h, int w, int co,
                                                                 float slope) {
     constexpr int KS = 3, TAPS = 9, KK = TAPS * C;
-    extern __shared__ float red[];                  // [KK + C][co] block-level partial sums
-    for (int i = threadIdx.x; i < (KK + C) * co; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
-    const unsigned cg = co / NCH;
-    const unsigned total = (unsigned)n * h * cg;    // (image, row, channel group)
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = (int)(i % cg);
-    if (i < total) {
-        const unsigned rr = i / cg;
-        const int ph = (int)(rr % (unsigned)h);
-        const unsigned img = rr / (unsigned)h;
+    extern __shared__ __align__(16) unsigned char smem_wg[];
+    const int band_px = kWgRows * w;
+    bf16* gs = reinterpret_cast<bf16*>(smem_wg);                                  // [band_px][co]
+    float* xs = reinterpret_cast<float*>(smem_wg + (size_t)band_px * co * 2);     // [(kWgRows+2)][w+2][C] activated, zero outside the image
+    float* xps = xs + (kWgRows + 2) * (w + 2) * C;                                // [kWgRows/2][w/2][C] bf16(AvgPool2(x))
+    float* red = xps + (kWgRows / 2) * (w / 2) * C;                               // [KK + C][co]
+    const int groups = blockDim.x / co;              // pixel groups (host guarantees blockDim.x % co == 0)
+    const int o = threadIdx.x % co, grp = threadIdx.x / co;
+    float acc[KK], accl[C];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) accl[ch] = 0.f;
+    const int bands_per_img = h / kWgRows, total_bands = n * bands_per_img;
+    for (int band = blockIdx.x; band < total_bands; band += gridDim.x) {
+        const int img = band / bands_per_img, r0 = (band - img * bands_per_img) * kWgRows;
         const float* xi = x + (size_t)img * h * w * C;
-        const bf16* grow = gt + (((size_t)img * h + ph) * w) * co + g * NCH;
-        const float* gyrow = gy + (((size_t)img * (h / 2) + ph / 2) * (w / 2)) * co + g * NCH;
-        float acc[KK][NCH], accl[C][NCH];
+        __syncthreads();                             // previous band fully consumed
+        {   // gradient rows: contiguous band_px*co bf16 in global memory
+            const uint4* src = reinterpret_cast<const uint4*>(gt + ((size_t)img * h + r0) * w * co);
+            uint4* dst = reinterpret_cast<uint4*>(gs);
+            for (int i = threadIdx.x; i < band_px * co / 8; i += blockDim.x) dst[i] = src[i];
+        }
+        for (int i = threadIdx.x; i < (kWgRows + 2) * (w + 2) * C; i += blockDim.x) {
+            const int ch = i % C, q = (i / C) % (w + 2), r = i / (C * (w + 2));
+            const int hh = r0 + r - 1, ww = q - 1;
+            const float v = (hh >= 0 && hh < h && ww >= 0 && ww < w) ? __ldg(xi + (hh * w + ww) * C + ch) : 0.f;
+            xs[i] = __bfloat162float(__float2bfloat16_rn(lrelu_f(v, slope)));
+        }
+        for (int i = threadIdx.x; i < (kWgRows / 2) * (w / 2) * C; i += blockDim.x) {
+            const int ch = i % C, q = (i / C) % (w / 2), r = i / (C * (w / 2));
+            const float* p = xi + ((r0 + 2 * r) * w + 2 * q) * C + ch;
+            xps[i] = __bfloat162float(__float2bfloat16_rn(0.25f * (__ldg(p) + __ldg(p + C) + __ldg(p + w * C) + __ldg(p + w * C + C))));
+        }
+        __syncthreads();
+        // each pixel group walks its own column range of every band row with a sliding 3x3 window: per pixel one gradient read, three
+        // window reads (broadcasts) and 9*C FMAs; no divisions in the loop
+        const int q_lo = grp * w / groups, q_hi = (grp + 1) * w / groups;
+        for (int r = 0; r < kWgRows; ++r) {
+            float win[KS][KS][C];
 #pragma unroll
-        for (int k = 0; k < KK; ++k)
+            for (int dr = 0; dr < KS; ++dr)
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) acc[k][j] = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) accl[ch][j] = 0.f;
-        // sliding window win[dr][dq][ch] = bf16(LeakyReLU(x[ph+dr-1][pw+dq-1][ch])), zero outside the image
-        float win[KS][KS][C];
-        const bool row_ok[KS] = {ph - 1 >= 0, true, ph + 1 < h};
-#pragma unroll
-        for (int dr = 0; dr < KS; ++dr)
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                win[dr][0][ch] = 0.f;
-                win[dr][1][ch] = 0.f;               // becomes column -1 after the first shift
-                win[dr][2][ch] = row_ok[dr] ? __bfloat162float(__float2bfloat16_rn(lrelu_f(__ldg(xi + ((ph + dr - 1) * w) * C + ch), slope))) : 0.f;
-            }
-        constexpr int PF = 1;                       // pixels per step (deeper software pipelining measured slower: registers halve the occupancy)
-        for (int pw0 = 0; pw0 < w; pw0 += PF) {
-            uint2 graw[PF];
-            float xnew[PF][KS][C];
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int pw = pw0 + u;
-                graw[u] = pw < w ? *reinterpret_cast<const uint2*>(grow + (size_t)pw * co) : make_uint2(0u, 0u);        // NCH == 4: 8 bytes
-#pragma unroll
-                for (int dr = 0; dr < KS; ++dr)
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch)
-                        xnew[u][dr][ch] = (row_ok[dr] && pw + 1 < w) ? __ldg(xi + ((ph + dr - 1) * w + pw + 1) * C + ch) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int pw = pw0 + u;
-                if (pw >= w) break;
+                for (int ch = 0; ch < C; ++ch) {
+                    win[dr][1][ch] = xs[((r + dr) * (w + 2) + q_lo) * C + ch];
+                    win[dr][2][ch] = xs[((r + dr) * (w + 2) + q_lo + 1) * C + ch];
+                }
+            const bf16* grow_s = gs + (size_t)(r * w) * co + o;
+            for (int q = q_lo; q < q_hi; ++q) {
 #pragma unroll
                 for (int dr = 0; dr < KS; ++dr)
 #pragma unroll
                     for (int ch = 0; ch < C; ++ch) {
                         win[dr][0][ch] = win[dr][1][ch];
                         win[dr][1][ch] = win[dr][2][ch];
-                        win[dr][2][ch] = __bfloat162float(__float2bfloat16_rn(lrelu_f(xnew[u][dr][ch], slope)));      // lrelu(0) = 0 outside
+                        win[dr][2][ch] = xs[((r + dr) * (w + 2) + q + 2) * C + ch];
                     }
-                float gv[NCH];
-                {
-                    const bf16* e = reinterpret_cast<const bf16*>(&graw[u]);
-#pragma unroll
-                    for (int q = 0; q < NCH; ++q) gv[q] = __bfloat162float(e[q]);
-                }
+                const float g = __bfloat162float(grow_s[q * co]);
 #pragma unroll
                 for (int dr = 0; dr < KS; ++dr)
 #pragma unroll
                     for (int dq = 0; dq < KS; ++dq)
 #pragma unroll
-                        for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-                            for (int j = 0; j < NCH; ++j) acc[(dr * KS + dq) * C + ch][j] = fmaf(win[dr][dq][ch], gv[j], acc[(dr * KS + dq) * C + ch][j]);
-                if (!(ph & 1) && !(pw & 1)) {       // residual branch at the pooled resolution
-                    const float4 gq = __ldg(reinterpret_cast<const float4*>(gyrow + (size_t)(pw / 2) * co));
-                    const float gl[4] = {__bfloat162float(__float2bfloat16_rn(gq.x)), __bfloat162float(__float2bfloat16_rn(gq.y)),
-                                         __bfloat162float(__float2bfloat16_rn(gq.z)), __bfloat162float(__float2bfloat16_rn(gq.w))};
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        const float* q = xi + (ph * w + pw) * C + ch;
-                        const float xp = __bfloat162float(__float2bfloat16_rn(0.25f * (__ldg(q) + __ldg(q + C) + __ldg(q + w * C) + __ldg(q + w * C + C))));
-#pragma unroll
-                        for (int j = 0; j < NCH; ++j) accl[ch][j] = fmaf(xp, gl[j], accl[ch][j]);
-                    }
-                }
+                        for (int ch = 0; ch < C; ++ch) acc[(dr * KS + dq) * C + ch] = fmaf(g, win[dr][dq][ch], acc[(dr * KS + dq) * C + ch]);
             }
         }
+        const float* gyb = gy + (((size_t)img * (h / 2) + r0 / 2) * (w / 2)) * co + o;
+        for (int pp = grp; pp < (kWgRows / 2) * (w / 2); pp += groups) {
+            const float gl = __bfloat162float(__float2bfloat16_rn(__ldg(gyb + (size_t)pp * co)));
 #pragma unroll
-        for (int k = 0; k < KK; ++k)
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) atomicAdd(&red[k * co + g * NCH + j], acc[k][j]);
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) atomicAdd(&red[(KK + ch) * co + g * NCH + j], accl[ch][j]);
+            for (int ch = 0; ch < C; ++ch) accl[ch] = fmaf(gl, xps[pp * C + ch], accl[ch]);
+        }
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < (KK + C) * co; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KK; ++k) atomicAdd(&red[k * co + o], acc[k]);
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) atomicAdd(&red[(KK + ch) * co + o], accl[ch]);
+    __syncthreads();
     for (int q = threadIdx.x; q < KK * co; q += blockDim.x) {
-        const int k = q / co, o = q - k * co;       // k = tap*C + ch  ->  gw_r1[tap][o][ch]
+        const int k = q / co, oo = q - k * co;      // k = tap*C + ch  ->  gw_r1[tap][oo][ch]
         const int tap = k / C, ch = k - tap * C;
-        atomicAdd(&gw_r1[((size_t)tap * co + o) * C + ch], red[q]);
+        atomicAdd(&gw_r1[((size_t)tap * co + oo) * C + ch], red[q]);
     }
     for (int q = threadIdx.x; q < C * co; q += blockDim.x) {
-        const int ch = q / co, o = q - ch * co;
-        atomicAdd(&gw_l1[(size_t)o * C + ch], red[KK * co + q]);
+        const int ch = q / co, oo = q - ch * co;
+        atomicAdd(&gw_l1[(size_t)oo * C + ch], red[KK * co + q]);
     }
 }
 
@@ -876,18 +860,27 @@ int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, co
 }
 int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_pooled, float* gw_r1, float* gw_l1, int n, int h, int wd, int c, int cout,
                           int ksize, float slope, gim_stream_t s) {
-    GIM_REQUIRE(n > 0 && h > 1 && wd > 1 && !(h & 1) && !(wd & 1), "first_block_wgrad: bad shape");
-    GIM_REQUIRE(ksize == 3 && (c == 1 || c == 3) && cout % 8 == 0, "first_block_wgrad: unsupported shape");
-    GIM_REQUIRE((long long)n * h * wd * (cout / 4) < 2147483647LL, "first_block_wgrad: too many elements for 32-bit indexing");
+    GIM_REQUIRE(n > 0 && h >= kWgRows && wd > 1 && h % kWgRows == 0 && !(wd & 1), "first_block_wgrad: h must be a multiple of 4 and w even");
+    GIM_REQUIRE(ksize == 3 && (c == 1 || c == 3) && cout % 8 == 0 && cout <= 256 && 256 % cout == 0, "first_block_wgrad: unsupported shape");
+    GIM_REQUIRE(aligned16(gt_bf16), "first_block_wgrad: gradient tensor must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)s;
     if (cudaMemsetAsync(gw_r1, 0, sizeof(float) * 9 * (size_t)cout * c, st) != cudaSuccess || cudaMemsetAsync(gw_l1, 0, sizeof(float) * (size_t)cout * c, st) != cudaSuccess)
         return fail(GIM_E_CUDA, "first_block_wgrad memset");
-    const size_t smem = sizeof(float) * (size_t)(9 * c + c) * cout;
-    GIM_REQUIRE(smem <= 48 * 1024, "first_block_wgrad: partial sums do not fit in shared memory");
-    const long long threads = (long long)n * h * (cout / 4);
-    const int grid = (int)((threads + 255) / 256);
-    if (c == 1) first_block_wgrad_kernel<1, 4><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
-    else first_block_wgrad_kernel<3, 4><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
+    const size_t smem = (size_t)kWgRows * wd * cout * 2 + sizeof(float) * ((size_t)(kWgRows + 2) * (wd + 2) * c + (size_t)(kWgRows / 2) * (wd / 2) * c + (size_t)(9 * c + c) * cout);
+    GIM_REQUIRE(smem <= 200 * 1024, "first_block_wgrad: band does not fit in shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(first_block_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(first_block_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return fail(GIM_E_CUDA, "first_block_wgrad: cannot raise dynamic shared memory limit");
+        attr_set = true;
+    }
+    const int bands = n * (h / kWgRows);
+    const int per_sm = smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1);
+    int grid = per_sm * num_sms();
+    if (grid > bands) grid = bands;
+    if (c == 1) first_block_wgrad_kernel<1><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
+    else first_block_wgrad_kernel<3><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
     return check_launch("first_block_wgrad");
 }
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t s) {

@@ -578,7 +578,7 @@ class ResBlockDownFn(Function):
             x32 = xa
             xa = xr = xl = None
             want_any_w = (not _state["input_grads_only"]) and (ctx.needs_input_grad[3] or ctx.needs_input_grad[5])
-            fused_wgrad = want_any_w and ks == 3 and ci in (1, 3) and co % 8 == 0
+            fused_wgrad = want_any_w and ks == 3 and ci in (1, 3) and co % 8 == 0 and 256 % co == 0 and h % 4 == 0
             if (want_any_w and not fused_wgrad) or ctx.needs_input_grad[0]:
                 xl = _prepare_operand(x32, PRE_LRELU, slope)
             if want_any_w and not fused_wgrad:
