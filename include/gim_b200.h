@@ -204,6 +204,17 @@ int gim_softmax_rows_bwd(const float* gy, const float* y, float* gx, long long r
 /* gradient of softmax_rows_bwd(gy,y) w.r.t. y given upstream ggx (R1 double backward) */
 int gim_softmax_rows_bwd_bwd(const float* ggx, const float* gy, const float* y, float* g_y, long long rows, int cols, gim_stream_t stream);
 
+/* ---- fused SelfAttention core over an 8x8 map (model_blocks.py:517-549, between the three 1x1 convs and the block output) ----
+ * q (reference conv_g), k (conv_f) [n_img][64][channels/8], v (conv_h), x, y [n_img][64][channels], all fp32, contiguous:
+ *   attn[n][j][i] = softmax_i(<q_j, k_i>),  y[j] = gamma[0] * sum_i attn[j][i] v[i] + x[j].
+ * One CTA per image, everything staged in shared memory.  positions must be 64 and channels 128 or 256 (GIM_E_ARG otherwise:
+ * the caller composes gemm + softmax for other shapes and whenever a second-order graph is needed). */
+int gim_attention_fwd(const float* q, const float* k, const float* v, const float* x, const float* gamma, float* attn, float* y,
+                      int n_img, int positions, int channels, gim_stream_t stream);
+/* gradients w.r.t. q, k, v; dgamma_part[n_img] = per-image partial of d/dgamma (the caller sums them); d/dx = gy */
+int gim_attention_bwd(const float* gy, const float* q, const float* k, const float* v, const float* attn, const float* gamma,
+                      float* dq, float* dk, float* dv, float* dgamma_part, int n_img, int positions, int channels, gim_stream_t stream);
+
 /* ---- permutation-invariant set statistics over the sample axis (gim_basic_models.py:20-51, 152-172; model_blocks.py:41-48) ---- */
 /* x [b][s][d] fp32.  out_sum[b*ld + j] = scale * sum_s x ; out_std = sqrt(var_unbiased + eps) (zeros if s==1); either may be NULL */
 int gim_set_stats_fwd(const float* x, float* out_sum, float* out_std, int ld_out, int b, int s, int d, float scale, float eps, gim_stream_t stream);

@@ -181,6 +181,8 @@ class SelfAttention(nn.Module):
         f = self.conv_f(x).reshape(n, h * w, -1)          # keys    [n, N, c/8]
         g = self.conv_g(x).reshape(n, h * w, -1)          # queries [n, N, c/8]
         hp = self.conv_h(x).reshape(n, h * w, c)          # values  [n, N, c]
+        if ops.attention_fused_ok(h * w, c, f, g, hp, x):
+            return ops.AttentionCoreFn.apply(g, f, hp, x.reshape(n, h * w, c), self.gamma).reshape(n, h, w, c)
         p = ops.matmul(g, f, False, True, torch.float32)  # p[j, i] = <g_j, f_i> = attention_map[i, j]
         a = ops.SoftmaxRowsFn.apply(p)                    # softmax over i  (reference: dim=-2 of [i, j])
         out = ops.matmul(a, hp, False, False, x.dtype).reshape(n, h, w, c)

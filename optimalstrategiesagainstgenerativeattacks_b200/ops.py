@@ -1263,6 +1263,46 @@ class _SoftmaxBwdBwdY(Function):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# fused SelfAttention core (one CTA per image; first order only)
+# ------------------------------------------------------------------------------------------------------------
+ATTN_POSITIONS, ATTN_CHANNELS = 64, (128, 256)
+
+
+def attention_fused_ok(positions, channels, *tensors):
+    """The fused kernels cover the 8x8 maps of the 32x32 pyramids (64 positions, 128 / 256 channels), fp32, first-order graphs."""
+    return (not _state["composite"] and positions == ATTN_POSITIONS and channels in ATTN_CHANNELS
+            and all(t.dtype == torch.float32 for t in tensors))
+
+
+class AttentionCoreFn(Function):
+    """y = gamma * softmax_i(<q_j, k_i>) v + x for [n, 64, c/8] queries / keys and [n, 64, c] values / input
+    (reference model_blocks.py:536-548); one kernel forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, x, gamma):
+        q, k, v, x = _c(q), _c(k), _c(v), _c(x)
+        n, p, c = v.shape
+        attn = _empty((n, p, p), torch.float32, v)
+        y = torch.empty_like(x)
+        C.call("gim_attention_fwd", C.ptr(q), C.ptr(k), C.ptr(v), C.ptr(x), C.ptr(gamma), C.ptr(attn), C.ptr(y), n, p, c)
+        ctx.save_for_backward(q, k, v, attn, gamma)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        q, k, v, attn, gamma = ctx.saved_tensors
+        gy = _c(gy)
+        n, p, c = v.shape
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        part = _empty((n,), torch.float32, v)
+        C.call("gim_attention_bwd", C.ptr(gy), C.ptr(q), C.ptr(k), C.ptr(v), C.ptr(attn), C.ptr(gamma), C.ptr(dq), C.ptr(dk), C.ptr(dv), C.ptr(part),
+               n, p, c)
+        dgamma = part.sum().reshape(gamma.shape) if ctx.needs_input_grad[4] else None
+        return dq, dk, dv, gy.view_as(v), dgamma
+
+
+# ------------------------------------------------------------------------------------------------------------
 # set statistics over the sample axis
 # ------------------------------------------------------------------------------------------------------------
 class SetSumFn(Function):

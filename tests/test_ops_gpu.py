@@ -463,3 +463,53 @@ def test_full_size_conv_kernels():
                          timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("shape n=640") == 5 and "rel" in res.stdout
+
+
+@pytest.mark.parametrize("channels,n_img", [(128, 3), (256, 5), (256, 160)])
+def test_fused_attention_core(channels, n_img):
+    """gim_attention_fwd / _bwd (one CTA per image, 64 positions) against float64 torch and against the composed gemm + softmax route."""
+    ops = ops_mod()
+    p, d = 64, channels // 8
+    q64, k64 = (rnd(n_img, p, d, seed=s, scale=0.7).requires_grad_() for s in (1, 2))
+    v64, x64 = (rnd(n_img, p, channels, seed=s).requires_grad_() for s in (3, 4))
+    gm64 = torch.tensor([0.37], dtype=torch.float64, requires_grad=True)
+    probe = rnd(n_img, p, channels, seed=5)
+
+    def reference(q, k, v, x, gm):
+        return gm * torch.matmul(torch.softmax(torch.matmul(q, k.transpose(1, 2)), -1), v) + x
+
+    ref = reference(q64, k64, v64, x64, gm64)
+    gref = torch.autograd.grad((ref * probe).sum(), (q64, k64, v64, x64, gm64))
+    leaves = [t.detach().float().cuda().requires_grad_() for t in (q64, k64, v64, x64, gm64)]
+    assert ops.attention_fused_ok(p, channels, *leaves[:4])
+    got = ops.AttentionCoreFn.apply(*leaves)
+    assert rel_err(got, ref) < 1e-5
+    ggot = torch.autograd.grad((got * probe.float().cuda()).sum(), leaves)
+    for a_, b_ in zip(ggot, gref):
+        assert rel_err(a_, b_) < 2e-5
+    with ops.composite_mode():                  # second-order graphs take the composed route
+        assert not ops.attention_fused_ok(p, channels, *leaves[:4])
+
+
+def test_self_attention_module_routes_agree():
+    """SelfAttention at the O-config shape (8x8 map, 256 channels): fused route == composed route (fp32), gradients included."""
+    from optimalstrategiesagainstgenerativeattacks_b200 import model_blocks as mb
+    ops = ops_mod()
+    torch.manual_seed(0)
+    att = mb.SelfAttention(256).cuda().eval()
+    with torch.no_grad():
+        att.gamma.fill_(0.5)
+    x = torch.randn(4, 8, 8, 256, device="cuda").requires_grad_()
+    probe = torch.randn(4, 8, 8, 256, device="cuda")
+    params = [x, att.gamma, att.conv_f.weight_orig, att.conv_h.weight_orig]
+
+    def run():
+        y = att(x)
+        return y, torch.autograd.grad((y * probe).sum(), params)
+
+    y_f, g_f = run()
+    with ops.composite_mode():
+        y_c, g_c = run()
+    assert rel_err(y_f, y_c) < 1e-5
+    for a_, b_ in zip(g_f, g_c):
+        assert rel_err(a_, b_) < 1e-4
