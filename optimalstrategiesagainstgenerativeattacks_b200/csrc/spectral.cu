@@ -212,13 +212,14 @@ __global__ void __launch_bounds__(512) sn_unorm_multi_kernel(const __grid_consta
 // One CTA per 32(co) x 32(ci) tile: the [co][ci][taps] rows are read contiguously, transposed through shared memory in groups of
 // <= 9 taps, and all three outputs are written with ci- (resp. co-) contiguous rows.
 constexpr int kPackTaps = 9;
+constexpr int kShPitch = 32 * kPackTaps + 1;      // tile row r holds its (ci, tap) pairs in weight order: sh[r][cil * nt + tl]; odd pitch
 __global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constant__ SnChunk c) {
     const gim_sn_layer& L = c.l[blockIdx.y];
     const int taps = L.ksize * L.ksize, J = L.cin * taps;
     const int ci_tiles = (L.cin + 31) / 32, co_tiles = (L.cout + 31) / 32;
     if ((int)blockIdx.x >= ci_tiles * co_tiles) return;
     const int co0 = ((int)blockIdx.x / ci_tiles) * 32, ci0 = ((int)blockIdx.x % ci_tiles) * 32;
-    __shared__ float sh[kPackTaps][32][33];
+    __shared__ float sh[32 * kShPitch];
     const float inv = 1.f / L.aux[L.cout + J];
     bf16* wop = (bf16*)L.w_op;
     bf16* wfl = (bf16*)L.w_flip;
@@ -231,9 +232,13 @@ __global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constan
             const int co = co0 + r;
             if (co < L.cout) {
                 const float* row = L.w + ((long long)co * L.cin + ci0) * taps;
-                for (int e = tx; e < nci * nt; e += 32) {
-                    const int cil = e / nt, tl = e - cil * nt;
-                    sh[tl][r][cil] = row[cil * taps + t0 + tl] * inv;
+                if (nt == taps) {
+                    for (int e = tx; e < nci * nt; e += 32) sh[r * kShPitch + e] = row[e] * inv;
+                } else {
+                    for (int e = tx; e < nci * nt; e += 32) {
+                        const int cil = e / nt, tl = e - cil * nt;
+                        sh[r * kShPitch + e] = row[cil * taps + t0 + tl] * inv;
+                    }
                 }
             }
         }
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constan
                 // w_sn / w_op rows: fixed (t, co), ci contiguous
                 const int co = co0 + r;
                 if (co < L.cout && tx < nci) {
-                    const float v = sh[tl][r][tx];
+                    const float v = sh[r * kShPitch + tx * nt + tl];
                     const long long o = ((long long)t * L.cout + co) * L.cin + ci0 + tx;
                     L.w_sn[o] = v;
                     if (wop) wop[o] = __float2bfloat16_rn(v);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constan
                 // flipped rows: fixed (T-1-t, ci), co contiguous
                 const int ci = ci0 + r;
                 if (wfl && ci < L.cin && co0 + tx < L.cout)
-                    wfl[((long long)(taps - 1 - t) * L.cin + ci) * L.cout + co0 + tx] = __float2bfloat16_rn(sh[tl][tx][r]);
+                    wfl[((long long)(taps - 1 - t) * L.cin + ci) * L.cout + co0 + tx] = __float2bfloat16_rn(sh[tx * kShPitch + r * nt + tl]);
             }
         }
         __syncthreads();
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_multi_kernel(const __grid_cons
     const int ci_tiles = (L.cin + 31) / 32, co_tiles = (L.cout + 31) / 32;
     if ((int)blockIdx.x >= ci_tiles * co_tiles) return;
     const int co0 = ((int)blockIdx.x / ci_tiles) * 32, ci0 = ((int)blockIdx.x % ci_tiles) * 32;
-    __shared__ float sh[kPackTaps][32][33];
+    __shared__ float sh[32 * kShPitch];
     __shared__ float red[33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int nci = min(32, L.cin - ci0);
@@ -283,16 +288,20 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_multi_kernel(const __grid_cons
         for (int tl = 0; tl < nt; ++tl)
             for (int r = ty; r < 32; r += 8) {
                 const int co = co0 + r;
-                if (co < L.cout && tx < nci) sh[tl][r][tx] = L.g[((long long)(t0 + tl) * L.cout + co) * L.cin + ci0 + tx];
+                if (co < L.cout && tx < nci) sh[r * kShPitch + tx * nt + tl] = L.g[((long long)(t0 + tl) * L.cout + co) * L.cin + ci0 + tx];
             }
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
             const int co = co0 + r;
             if (co < L.cout) {
                 const float* row = L.w + ((long long)co * L.cin + ci0) * taps;
-                for (int e = tx; e < nci * nt; e += 32) {
-                    const int cil = e / nt, tl = e - cil * nt;
-                    acc = fmaf(sh[tl][r][cil], row[cil * taps + t0 + tl], acc);
+                if (nt == taps) {
+                    for (int e = tx; e < nci * nt; e += 32) acc = fmaf(sh[r * kShPitch + e], row[e], acc);
+                } else {
+                    for (int e = tx; e < nci * nt; e += 32) {
+                        const int cil = e / nt, tl = e - cil * nt;
+                        acc = fmaf(sh[r * kShPitch + e], row[cil * taps + t0 + tl], acc);
+                    }
                 }
             }
         }
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_multi_kernel(const __grid_co
     const int ci_tiles = (L.cin + 31) / 32, co_tiles = (L.cout + 31) / 32;
     if ((int)blockIdx.x >= ci_tiles * co_tiles) return;
     const int co0 = ((int)blockIdx.x / ci_tiles) * 32, ci0 = ((int)blockIdx.x % ci_tiles) * 32;
-    __shared__ float sh[kPackTaps][32][33];
+    __shared__ float sh[32 * kShPitch];
     const float inv = 1.f / *L.sigma;
     const float k = (*L.scratch) * inv * inv;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_multi_kernel(const __grid_co
         for (int tl = 0; tl < nt; ++tl)
             for (int r = ty; r < 32; r += 8) {
                 const int co = co0 + r;
-                if (co < L.cout && tx < nci) sh[tl][r][tx] = L.g[((long long)(t0 + tl) * L.cout + co) * L.cin + ci0 + tx];
+                if (co < L.cout && tx < nci) sh[r * kShPitch + tx * nt + tl] = L.g[((long long)(t0 + tl) * L.cout + co) * L.cin + ci0 + tx];
             }
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
@@ -326,11 +335,15 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_multi_kernel(const __grid_co
             if (co < L.cout) {
                 float* row = L.grad + ((long long)co * L.cin + ci0) * taps;
                 const float uco = L.u[co];
+                const float* vrow = L.v + (long long)ci0 * taps;
                 for (int e = tx; e < nci * nt; e += 32) {
-                    const int cil = e / nt, tl = e - cil * nt;
-                    const float val = sh[tl][r][cil] * inv - k * uco * L.v[(ci0 + cil) * taps + t0 + tl];
-                    float* dst = row + cil * taps + t0 + tl;
-                    *dst = L.accumulate ? *dst + val : val;
+                    int off = e;
+                    if (nt != taps) {
+                        const int cil = e / nt;
+                        off = cil * taps + t0 + (e - cil * nt);
+                    }
+                    const float val = sh[r * kShPitch + e] * inv - k * uco * vrow[off];
+                    row[off] = L.accumulate ? row[off] + val : val;
                 }
             }
         }

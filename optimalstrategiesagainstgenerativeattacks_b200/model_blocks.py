@@ -319,9 +319,6 @@ def batched_style_projections(blocks, style):
     if pad:
         ws.append(style.new_zeros((pad, style.shape[-1])))
         bs.append(style.new_zeros((pad,)))
-    y = ops.linear(style, torch.cat(ws, dim=0), torch.cat(bs, dim=0))
-    outs, off = [], 0
-    for n in sizes:
-        outs.append(y[:, off:off + n])
-        off += n
+    y = ops.linear(style, ops.cat_params(ws), ops.cat_params(bs))
+    outs = torch.split(y, sizes + ([pad] if pad else []), dim=-1)      # (split, not slices: its backward is one concatenation)
     return [tuple(outs[4 * i:4 * i + 4]) for i in range(len(blocks))]

@@ -469,6 +469,32 @@ def _bias_grad(x, param):
     return _colsum(x)
 
 
+class CatParamsFn(Function):
+    """torch.cat(tensors, 0) of parameter-like tensors.  Inside `deferred_weight_grads()` the backward adds the row blocks of the gradient
+    straight into the leaves' .grad with one multi-tensor launch (instead of one AccumulateGrad add per tensor) and returns None."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        ctx.tensors = tensors
+        return torch.cat(tensors, 0)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        ts = ctx.tensors
+        parts = torch.split(_c(g), [t.shape[0] for t in ts], 0)
+        want = [i for i, t in enumerate(ts) if ctx.needs_input_grad[i]]
+        if _state["defer_sn"] and want and all(ts[i].is_leaf and ts[i].grad is not None and ts[i].grad.is_contiguous()
+                                                and ts[i].grad.dtype == parts[i].dtype for i in want):
+            torch._foreach_add_([ts[i].grad for i in want], [parts[i] for i in want])
+            return (None,) * len(ts)
+        return tuple(parts[i] if ctx.needs_input_grad[i] else None for i in range(len(ts)))
+
+
+def cat_params(tensors):
+    return CatParamsFn.apply(*tensors)
+
+
 def _colsum(x):
     c = x.shape[-1]
     out = _empty((c,), torch.float32, x)
