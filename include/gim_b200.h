@@ -205,15 +205,19 @@ int gim_softmax_rows_bwd(const float* gy, const float* y, float* gx, long long r
 int gim_softmax_rows_bwd_bwd(const float* ggx, const float* gy, const float* y, float* g_y, long long rows, int cols, gim_stream_t stream);
 
 /* ---- fused SelfAttention core over an 8x8 map (model_blocks.py:517-549, between the three 1x1 convs and the block output) ----
- * q (reference conv_g), k (conv_f) [n_img][64][channels/8], v (conv_h), x, y [n_img][64][channels], all fp32, contiguous:
+ * q (reference conv_g), k (conv_f): 64 rows of channels/8 floats per image, `ld_qk` floats between rows; v (conv_h): 64 rows of
+ * `channels` floats, `ld_v` between rows (the three may be column blocks of ONE [n_img][64][2*channels/8 + channels] projection:
+ * ld_qk = ld_v = its row length); x, y [n_img][64][channels] and attn [n_img][64][64] contiguous; all fp32, 16-byte aligned:
  *   attn[n][j][i] = softmax_i(<q_j, k_i>),  y[j] = gamma[0] * sum_i attn[j][i] v[i] + x[j].
  * One CTA per image, everything staged in shared memory.  positions must be 64 and channels 128 or 256 (GIM_E_ARG otherwise:
  * the caller composes gemm + softmax for other shapes and whenever a second-order graph is needed). */
-int gim_attention_fwd(const float* q, const float* k, const float* v, const float* x, const float* gamma, float* attn, float* y,
-                      int n_img, int positions, int channels, gim_stream_t stream);
-/* gradients w.r.t. q, k, v; dgamma_part[n_img] = per-image partial of d/dgamma (the caller sums them); d/dx = gy */
-int gim_attention_bwd(const float* gy, const float* q, const float* k, const float* v, const float* attn, const float* gamma,
-                      float* dq, float* dk, float* dv, float* dgamma_part, int n_img, int positions, int channels, gim_stream_t stream);
+int gim_attention_fwd(const float* q, const float* k, const float* v, int ld_qk, int ld_v, const float* x, const float* gamma,
+                      float* attn, float* y, int n_img, int positions, int channels, gim_stream_t stream);
+/* gradients w.r.t. q, k, v (written with the same row pitches as q, k, v); dgamma_part[n_img] = per-image partial of d/dgamma
+ * (the caller sums them); d/dx = gy */
+int gim_attention_bwd(const float* gy, const float* q, const float* k, const float* v, int ld_qk, int ld_v, const float* attn,
+                      const float* gamma, float* dq, float* dk, float* dv, float* dgamma_part, int n_img, int positions, int channels,
+                      gim_stream_t stream);
 
 /* ---- permutation-invariant set statistics over the sample axis (gim_basic_models.py:20-51, 152-172; model_blocks.py:41-48) ---- */
 /* x [b][s][d] fp32.  out_sum[b*ld + j] = scale * sum_s x ; out_std = sqrt(var_unbiased + eps) (zeros if s==1); either may be NULL */

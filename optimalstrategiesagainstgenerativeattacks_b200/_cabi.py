@@ -63,8 +63,8 @@ PROTOTYPES = {
     "gim_softmax_rows_fwd": "pplip",
     "gim_softmax_rows_bwd": "ppplip",
     "gim_softmax_rows_bwd_bwd": "pppplip",
-    "gim_attention_fwd": "pppppppiiip",
-    "gim_attention_bwd": "ppppppppppiiip",
+    "gim_attention_fwd": "pppiippppiiip",
+    "gim_attention_bwd": "ppppiippppppiiip",
     "gim_set_stats_fwd": "pppiiiiffp",
     "gim_set_stats_bwd": "ppippiiiffp",
     "gim_set_std_bwd_bwd": "ppippp" + "iiifp",

@@ -21,11 +21,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
-// rows x (4*row_f4) fp32 matrix, contiguous in global memory -> smem with `pitch` floats per row (pitch % 4 == 0)
-__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int rows, int row_f4, int pitch) {
+// rows x (4*row_f4) fp32 matrix with `ld` floats between rows in global memory -> smem with `pitch` floats per row (both % 4 == 0)
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int rows, int row_f4, int pitch, int ld) {
     for (int e = threadIdx.x; e < rows * row_f4; e += blockDim.x) {
         int r = e / row_f4, c4 = e - r * row_f4;
-        cp_async16(dst + r * pitch + c4 * 4, src + (size_t)e * 4);
+        cp_async16(dst + r * pitch + c4 * 4, src + (size_t)r * ld + c4 * 4);
     }
 }
 
@@ -40,8 +40,8 @@ template <int C> struct AttnSmem {
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                                       const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ attn,
-                                                       float* __restrict__ y) {
+                                                       int ld_qk, int ld_v, const float* __restrict__ x, const float* __restrict__ gamma,
+                                                       float* __restrict__ attn, float* __restrict__ y) {
     constexpr int P = kAttP, AP = kAttAP, D = C / 8, DP = D + 4, CPL = C / 128;
     extern __shared__ __align__(16) float att_smem[];
     float* v_s = att_smem;             // [P][C]      values, rows contiguous
@@ -50,10 +50,10 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const float* __restric
     float* k_s = q_s + P * DP;         // [P][DP]
     const int img = blockIdx.x, tid = threadIdx.x;
 
-    stage_rows(q_s, q + (size_t)img * P * D, P, D / 4, DP);
-    stage_rows(k_s, k + (size_t)img * P * D, P, D / 4, DP);
+    stage_rows(q_s, q + (size_t)img * P * ld_qk, P, D / 4, DP, ld_qk);
+    stage_rows(k_s, k + (size_t)img * P * ld_qk, P, D / 4, DP, ld_qk);
     cp_async_wait_all();
-    stage_rows(v_s, v + (size_t)img * P * C, P, C / 4, C);          // lands while the scores are computed
+    stage_rows(v_s, v + (size_t)img * P * ld_v, P, C / 4, C, ld_v);          // lands while the scores are computed
     asm volatile("cp.async.commit_group;" ::: "memory");
     __syncthreads();
 
@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ q, const float* __restrict__ k,
-                                                       const float* __restrict__ v, const float* __restrict__ attn, const float* __restrict__ gamma,
-                                                       float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
-                                                       float* __restrict__ dgamma_part) {
+                                                       const float* __restrict__ v, int ld_qk, int ld_v, const float* __restrict__ attn,
+                                                       const float* __restrict__ gamma, float* __restrict__ dq, float* __restrict__ dk,
+                                                       float* __restrict__ dv, float* __restrict__ dgamma_part) {
     constexpr int P = kAttP, AP = kAttAP, D = C / 8, DP = D + 4, CP = C + 4, CPL = C / 128, NDG = D / 4;
     extern __shared__ __align__(16) float att_smem[];
     float* g_s = att_smem;             // [P][CP]   dy
@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
     float* red = k_s + P * DP;         // 64 floats of reduction scratch
     const int img = blockIdx.x, tid = threadIdx.x;
 
-    stage_rows(g_s, gy + (size_t)img * P * C, P, C / 4, CP);
-    stage_rows(v_s, v + (size_t)img * P * C, P, C / 4, CP);
-    stage_rows(a_s, attn + (size_t)img * P * P, P, P / 4, AP);
-    stage_rows(q_s, q + (size_t)img * P * D, P, D / 4, DP);
-    stage_rows(k_s, k + (size_t)img * P * D, P, D / 4, DP);
+    stage_rows(g_s, gy + (size_t)img * P * C, P, C / 4, CP, C);
+    stage_rows(v_s, v + (size_t)img * P * ld_v, P, C / 4, CP, ld_v);
+    stage_rows(a_s, attn + (size_t)img * P * P, P, P / 4, AP, P);
+    stage_rows(q_s, q + (size_t)img * P * ld_qk, P, D / 4, DP, ld_qk);
+    stage_rows(k_s, k + (size_t)img * P * ld_qk, P, D / 4, DP, ld_qk);
     cp_async_wait_all();
     __syncthreads();
 
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
 #pragma unroll
             for (int p = 0; p < CPL; ++p) {
                 float4 o = {gm * acc[r][4 * p + 0], gm * acc[r][4 * p + 1], gm * acc[r][4 * p + 2], gm * acc[r][4 * p + 3]};
-                *reinterpret_cast<float4*>(dv + ((size_t)img * P + i0 + r) * C + p * 128 + 4 * l) = o;
+                *reinterpret_cast<float4*>(dv + ((size_t)img * P + i0 + r) * ld_v + p * 128 + 4 * l) = o;
             }
     }
 
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                *reinterpret_cast<float4*>(dk + ((size_t)img * P + 4 * ig + r) * D + 4 * dg) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                *reinterpret_cast<float4*>(dk + ((size_t)img * P + 4 * ig + r) * ld_qk + 4 * dg) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         }
     } else {
         const int u = tid - 128;
@@ -294,32 +294,32 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                *reinterpret_cast<float4*>(dq + ((size_t)img * P + 4 * jg + r) * D + 4 * dg) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                *reinterpret_cast<float4*>(dq + ((size_t)img * P + 4 * jg + r) * ld_qk + 4 * dg) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         }
     }
 }
 
-template <int C> static int launch_fwd(const float* q, const float* k, const float* v, const float* x, const float* gamma, float* attn, float* y,
-                                       int n_img, cudaStream_t st) {
+template <int C> static int launch_fwd(const float* q, const float* k, const float* v, int ld_qk, int ld_v, const float* x, const float* gamma,
+                                       float* attn, float* y, int n_img, cudaStream_t st) {
     static bool configured = false;
     const int smem = AttnSmem<C>::fwd_floats * (int)sizeof(float);
     if (!configured) {
         if (cudaFuncSetAttribute(attn_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return fail(GIM_E_CUDA, "attention_fwd: smem opt-in failed");
         configured = true;
     }
-    attn_fwd_kernel<C><<<n_img, 256, smem, st>>>(q, k, v, x, gamma, attn, y);
+    attn_fwd_kernel<C><<<n_img, 256, smem, st>>>(q, k, v, ld_qk, ld_v, x, gamma, attn, y);
     return check_launch("attention_fwd");
 }
 
-template <int C> static int launch_bwd(const float* gy, const float* q, const float* k, const float* v, const float* attn, const float* gamma, float* dq,
-                                       float* dk, float* dv, float* dgamma_part, int n_img, cudaStream_t st) {
+template <int C> static int launch_bwd(const float* gy, const float* q, const float* k, const float* v, int ld_qk, int ld_v, const float* attn,
+                                       const float* gamma, float* dq, float* dk, float* dv, float* dgamma_part, int n_img, cudaStream_t st) {
     static bool configured = false;
     const int smem = AttnSmem<C>::bwd_floats * (int)sizeof(float);
     if (!configured) {
         if (cudaFuncSetAttribute(attn_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return fail(GIM_E_CUDA, "attention_bwd: smem opt-in failed");
         configured = true;
     }
-    attn_bwd_kernel<C><<<n_img, 256, smem, st>>>(gy, q, k, v, attn, gamma, dq, dk, dv, dgamma_part);
+    attn_bwd_kernel<C><<<n_img, 256, smem, st>>>(gy, q, k, v, ld_qk, ld_v, attn, gamma, dq, dk, dv, dgamma_part);
     return check_launch("attention_bwd");
 }
 
@@ -331,20 +331,25 @@ static bool attention_supported(int positions, int channels) { return positions 
 
 extern "C" {
 
-int gim_attention_fwd(const float* q, const float* k, const float* v, const float* x, const float* gamma, float* attn, float* y, int n_img, int positions,
-                      int channels, gim_stream_t s) {
+int gim_attention_fwd(const float* q, const float* k, const float* v, int ld_qk, int ld_v, const float* x, const float* gamma, float* attn, float* y,
+                      int n_img, int positions, int channels, gim_stream_t s) {
     if (n_img <= 0) return GIM_OK;
     GIM_REQUIRE(attention_supported(positions, channels), "attention_fwd: fused kernel covers 64 positions and 128 / 256 channels");
-    return channels == 128 ? launch_fwd<128>(q, k, v, x, gamma, attn, y, n_img, (cudaStream_t)s)
-                           : launch_fwd<256>(q, k, v, x, gamma, attn, y, n_img, (cudaStream_t)s);
+    GIM_REQUIRE(ld_qk >= channels / 8 && ld_v >= channels && ld_qk % 4 == 0 && ld_v % 4 == 0, "attention_fwd: row pitches must be multiples of 4 floats");
+    GIM_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)x | (uintptr_t)y | (uintptr_t)attn) & 15) == 0, "attention_fwd: 16-byte alignment");
+    return channels == 128 ? launch_fwd<128>(q, k, v, ld_qk, ld_v, x, gamma, attn, y, n_img, (cudaStream_t)s)
+                           : launch_fwd<256>(q, k, v, ld_qk, ld_v, x, gamma, attn, y, n_img, (cudaStream_t)s);
 }
 
-int gim_attention_bwd(const float* gy, const float* q, const float* k, const float* v, const float* attn, const float* gamma, float* dq, float* dk,
-                      float* dv, float* dgamma_part, int n_img, int positions, int channels, gim_stream_t s) {
+int gim_attention_bwd(const float* gy, const float* q, const float* k, const float* v, int ld_qk, int ld_v, const float* attn, const float* gamma,
+                      float* dq, float* dk, float* dv, float* dgamma_part, int n_img, int positions, int channels, gim_stream_t s) {
     if (n_img <= 0) return GIM_OK;
     GIM_REQUIRE(attention_supported(positions, channels), "attention_bwd: fused kernel covers 64 positions and 128 / 256 channels");
-    return channels == 128 ? launch_bwd<128>(gy, q, k, v, attn, gamma, dq, dk, dv, dgamma_part, n_img, (cudaStream_t)s)
-                           : launch_bwd<256>(gy, q, k, v, attn, gamma, dq, dk, dv, dgamma_part, n_img, (cudaStream_t)s);
+    GIM_REQUIRE(ld_qk >= channels / 8 && ld_v >= channels && ld_qk % 4 == 0 && ld_v % 4 == 0, "attention_bwd: row pitches must be multiples of 4 floats");
+    GIM_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)gy | (uintptr_t)attn | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+                "attention_bwd: 16-byte alignment");
+    return channels == 128 ? launch_bwd<128>(gy, q, k, v, ld_qk, ld_v, attn, gamma, dq, dk, dv, dgamma_part, n_img, (cudaStream_t)s)
+                           : launch_bwd<256>(gy, q, k, v, ld_qk, ld_v, attn, gamma, dq, dk, dv, dgamma_part, n_img, (cudaStream_t)s);
 }
 
 }  // extern "C"

@@ -178,11 +178,15 @@ class SelfAttention(nn.Module):
             ops.register_operand(x.t32, x.tb)             # the three 1x1 convs read the bf16 copy the pooling kernel already wrote
             x = x.t32
         n, h, w, c = x.shape
+        if ops.attention_fused_ok(h * w, c, x):
+            # 8x8 maps: the three projections are ONE 1x1 convolution [keys | queries | values] (x is read once; one input-gradient and
+            # one weight-gradient launch instead of three) feeding the fused attention kernels
+            convs = (self.conv_f, self.conv_g, self.conv_h)
+            kqv = ops.conv2d(x, ops.merged_sn_weight(convs), ops.cat_params([m.bias for m in convs]), 1)
+            return ops.AttentionPackedFn.apply(kqv.reshape(n, h * w, -1), x.reshape(n, h * w, c), self.gamma).reshape(n, h, w, c)
         f = self.conv_f(x).reshape(n, h * w, -1)          # keys    [n, N, c/8]
         g = self.conv_g(x).reshape(n, h * w, -1)          # queries [n, N, c/8]
         hp = self.conv_h(x).reshape(n, h * w, c)          # values  [n, N, c]
-        if ops.attention_fused_ok(h * w, c, f, g, hp, x):
-            return ops.AttentionCoreFn.apply(g, f, hp, x.reshape(n, h * w, c), self.gamma).reshape(n, h, w, c)
         p = ops.matmul(g, f, False, True, torch.float32)  # p[j, i] = <g_j, f_i> = attention_map[i, j]
         a = ops.SoftmaxRowsFn.apply(p)                    # softmax over i  (reference: dim=-2 of [i, j])
         out = ops.matmul(a, hp, False, False, x.dtype).reshape(n, h, w, c)

@@ -159,7 +159,7 @@ def _weight_as(w32, dtype, flip):
         return w32
     if dtype == torch.bfloat16:
         hit = _wops.get(id(w32))
-        if hit is not None and hit[0]() is w32:
+        if hit is not None and hit[0]() is w32 and hit[2 if flip else 1] is not None:
             return hit[2] if flip else hit[1]
     out = _empty((taps, ci, co) if flip else (taps, co, ci), dtype, w32)
     C.call("gim_weight_flip" if flip else "gim_weight_cast", C.ptr(w32), C.ptr(out), taps, co, ci, C.dtype_code(out))
@@ -792,15 +792,23 @@ def sn_prepare(convs, training, eps):
         return
     dev = convs[0].weight_orig.device
     bf = _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT
-    n32 = nbf = 0
+    # buffer layout: every packed W/sigma first, in module order (so the weights of consecutive layers are adjacent -- the attention
+    # block reads its three 1x1 projections as ONE [1, 2c/8 + c, c] weight, see merged_sn_weight), then the per-layer vectors
+    dims = [(m.out_channels, m.in_channels, m.kernel_size) for m in convs]
+    tots = [co * ci * k * k for co, ci, k in dims]
+    n32 = sum(_round_up(t, 4) for t in tots)
+    n_op = sum(_round_up(t, 8) for t in tots)
+    nbf = n_op
+    o_w = o_b = 0
     plan = []
-    for m in convs:
-        co, ci, k = m.out_channels, m.in_channels, m.kernel_size
-        tot, j = co * ci * k * k, ci * k * k
-        o_sn, o_aux, o_scr = n32, n32 + _round_up(tot, 4), n32 + _round_up(tot, 4) + _round_up(co + j + 1, 4)
+    for m, (co, ci, k), tot in zip(convs, dims, tots):
+        j = ci * k * k
+        o_sn, o_aux, o_scr = o_w, n32, n32 + _round_up(co + j + 1, 4)
         n32 = o_scr + _round_up(j + co, 4)
-        o_op, o_fl = nbf, nbf + _round_up(tot, 8)
+        o_op, o_fl = o_b, nbf
         nbf = o_fl + _round_up(tot, 8)
+        o_w += _round_up(tot, 4)
+        o_b += _round_up(tot, 8)
         plan.append((m, co, ci, k, tot, j, o_sn, o_aux, o_scr, o_op, o_fl))
     f32 = torch.empty(n32, dtype=torch.float32, device=dev)
     b16 = torch.empty(nbf, dtype=torch.bfloat16, device=dev) if bf else None
@@ -819,7 +827,7 @@ def sn_prepare(convs, training, eps):
         e.w_op = w_op.data_ptr() if bf else None
         e.w_flip = w_fl.data_ptr() if bf else None
         e.cout, e.cin, e.ksize, e.reserved = co, ci, k, 0
-        m._prepared = (w_sn, aux, w_op, w_fl, w._version)
+        m._prepared = (w_sn, aux, w_op, w_fl, w._version, (f32, o_sn, b16, o_op))
     import ctypes
     C.call("gim_sn_forward_multi", ctypes.cast(table, ctypes.c_void_p), len(plan), 1 if training else 0, eps)
 
@@ -850,6 +858,80 @@ def sn_prepared_weight(weight_orig, prepared):
                 del _wops[key]
         _wops[id(w)] = (weakref.ref(w), prepared[2], prepared[3])
     return w
+
+
+class _MergedRowsFn(Function):
+    """[1, co_1 + co_2 + .., ci] weight over 1x1 weights that already lie one after the other in the batched spectral-norm buffer:
+    no copy forward, row blocks of the gradient backward."""
+
+    @staticmethod
+    def forward(ctx, holder, *ws):
+        f32, off = holder
+        ctx.rows = [w.shape[1] for w in ws]
+        ci = ws[0].shape[2]
+        return f32[off:off + sum(ctx.rows) * ci].view(1, sum(ctx.rows), ci)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return (None,) + tuple(torch.split(_c(g), ctx.rows, 1))
+
+
+def merged_sn_weight(convs):
+    """Packed fp32 weight [1, sum(cout), cin] of several spectral-normalised 1x1 convolutions over the same input, so that they run as
+    ONE convolution (and one input-gradient / weight-gradient launch).  After a batched sn_prepare the per-layer results are adjacent in
+    one buffer and the merged weight (and its bf16 operand) is just a view; otherwise the rows are concatenated."""
+    preps = [m._prepared for m in convs]
+    ws = [m.effective_weight() for m in convs]
+    if any(w.shape[0] != 1 for w in ws):
+        raise RuntimeError("merged_sn_weight: 1x1 convolutions only")
+    ok = all(p is not None and len(p) > 5 and p[0] is not None for p in preps)
+    if ok:
+        f32, off0, b16, op0 = preps[0][5]
+        off, op = off0, op0
+        for p, w in zip(preps, ws):
+            ok = ok and p[5][0] is f32 and p[5][1] == off and (b16 is None or p[5][3] == op) and p[0].data_ptr() == w.data_ptr()
+            off += w.numel()
+            op += w.numel()
+    if not ok:
+        return torch.cat(ws, dim=1)
+    merged = _MergedRowsFn.apply((f32, off0), *ws)
+    if b16 is not None:
+        _wops[id(merged)] = (weakref.ref(merged), b16[op0:op0 + merged.numel()].view(merged.shape), None)
+    return merged
+
+
+class AttentionPackedFn(Function):
+    """AttentionCoreFn over ONE projection tensor kqv [n, 64, 2d + c] = [keys | queries | values] (d = c/8): the kernels read the three
+    column blocks in place and the backward writes their gradients into one tensor of the same layout."""
+
+    @staticmethod
+    def forward(ctx, kqv, x, gamma):
+        kqv, x = _c(kqv), _c(x)
+        n, p, c = x.shape
+        d, ld = c // 8, kqv.shape[2]
+        attn = _empty((n, p, p), torch.float32, x)
+        y = torch.empty_like(x)
+        base = C.ptr(kqv)
+        C.call("gim_attention_fwd", base + 4 * d, base, base + 8 * d, ld, ld, C.ptr(x), C.ptr(gamma), C.ptr(attn), C.ptr(y), n, p, c)
+        ctx.save_for_backward(kqv, attn, gamma)
+        ctx.dims = (n, p, c)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        kqv, attn, gamma = ctx.saved_tensors
+        n, p, c = ctx.dims
+        d, ld = c // 8, kqv.shape[2]
+        gy = _c(gy)
+        dkqv = torch.empty_like(kqv)
+        part = _empty((n,), torch.float32, kqv)
+        base, dbase = C.ptr(kqv), C.ptr(dkqv)
+        C.call("gim_attention_bwd", C.ptr(gy), base + 4 * d, base, base + 8 * d, ld, ld, C.ptr(attn), C.ptr(gamma),
+               dbase + 4 * d, dbase, dbase + 8 * d, C.ptr(part), n, p, c)
+        dgamma = part.sum().reshape(gamma.shape) if ctx.needs_input_grad[2] else None
+        return dkqv, gy.view(n, p, c), dgamma
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -1310,7 +1392,7 @@ class AttentionCoreFn(Function):
         n, p, c = v.shape
         attn = _empty((n, p, p), torch.float32, v)
         y = torch.empty_like(x)
-        C.call("gim_attention_fwd", C.ptr(q), C.ptr(k), C.ptr(v), C.ptr(x), C.ptr(gamma), C.ptr(attn), C.ptr(y), n, p, c)
+        C.call("gim_attention_fwd", C.ptr(q), C.ptr(k), C.ptr(v), q.shape[2], c, C.ptr(x), C.ptr(gamma), C.ptr(attn), C.ptr(y), n, p, c)
         ctx.save_for_backward(q, k, v, attn, gamma)
         return y
 
@@ -1322,8 +1404,8 @@ class AttentionCoreFn(Function):
         n, p, c = v.shape
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         part = _empty((n,), torch.float32, v)
-        C.call("gim_attention_bwd", C.ptr(gy), C.ptr(q), C.ptr(k), C.ptr(v), C.ptr(attn), C.ptr(gamma), C.ptr(dq), C.ptr(dk), C.ptr(dv), C.ptr(part),
-               n, p, c)
+        C.call("gim_attention_bwd", C.ptr(gy), C.ptr(q), C.ptr(k), C.ptr(v), q.shape[2], c, C.ptr(attn), C.ptr(gamma), C.ptr(dq), C.ptr(dk), C.ptr(dv),
+               C.ptr(part), n, p, c)
         dgamma = part.sum().reshape(gamma.shape) if ctx.needs_input_grad[4] else None
         return dq, dk, dv, gy.view_as(v), dgamma
 

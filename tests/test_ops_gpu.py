@@ -513,3 +513,42 @@ def test_self_attention_module_routes_agree():
     assert rel_err(y_f, y_c) < 1e-5
     for a_, b_ in zip(g_f, g_c):
         assert rel_err(a_, b_) < 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", BF16_TOL)])
+def test_encoder_merged_attention_projections(precision, tol):
+    """Full-size O-config encoder (1x32x32 -> 512; attention on the 8x8 x 256 map): the default route -- batched spectral norm, the three
+    attention projections as one merged 1x1 convolution, fused attention kernels, direct .grad accumulation -- against the composed
+    route (`composite_mode`: three convolutions, gemm + softmax), outputs and parameter gradients."""
+    from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_models as gm
+    ops = ops_mod()
+    ops.set_precision(precision)
+    torch.manual_seed(1)
+    enc = gm.Encoder(img_size=32, img_channels=1, style_dim=512).cuda().train()
+    with torch.no_grad():
+        enc.att.gamma.fill_(0.7)
+        warm = torch.randn(4, 1, 32, 32, device="cuda")
+        for _ in range(6):                      # let the power iterations settle, then freeze u / v (eval)
+            enc(warm)
+    enc.eval()
+    x = torch.randn(6, 1, 32, 32, device="cuda")
+    probe = torch.randn(6, 512, device="cuda")
+    names = ["att.gamma", "att.conv_f.weight_orig", "att.conv_g.bias", "att.conv_h.weight_orig", "att.conv_h.bias", "down_blocks.1.conv_r1.weight_orig",
+             "down_blocks.2.conv_r2.bias"]
+    params = dict(enc.named_parameters())
+
+    def run(composed):
+        for p_ in enc.parameters():
+            p_.grad = torch.zeros_like(p_)
+        with (ops.composite_mode() if composed else torch.enable_grad()):
+            y = enc(x)
+            with ops.deferred_weight_grads():
+                (y * probe).sum().backward()
+        return y.detach().clone(), [params[n].grad.detach().clone() for n in names]
+
+    y_f, g_f = run(False)
+    y_c, g_c = run(True)
+    assert rel_err(y_f, y_c) < tol
+    for name, a_, b_ in zip(names, g_f, g_c):
+        assert float(b_.abs().max()) > 0, name
+        assert rel_err(a_, b_) < (tol if precision == "fp32" else 2.5 * tol), name
