@@ -146,7 +146,9 @@ int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, co
                         int n, int h, int wd, int c, int cout, int ksize, float slope, gim_stream_t stream);
 /* weight gradients of the same two convolutions (3x3, c = 1 or 3): gw_r1 fp32 packed [9][cout][c] from gt = bf16 masked gradient of the
  * k x k conv output [n,h,w,cout]; gw_l1 fp32 [cout][c] from gy = fp32 gradient of the pooled block output [n,h/2,w/2,cout]; both overwritten */
-int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_pooled, float* gw_r1, float* gw_l1,
+/* `scratch` (>= 10*cout*c floats, ideally 32 x that; may be NULL): the tensor-core pass lets each CTA add into one of several zeroed
+ * copies of the result held there and folds them afterwards; without scratch the CUDA-core pass adds into gw_* directly */
+int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_pooled, float* gw_r1, float* gw_l1, float* scratch, long long scratch_floats,
                           int n, int h, int wd, int c, int cout, int ksize, float slope, gim_stream_t stream);
 int gim_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);
 int gim_nhwc_to_nchw(const void* x, float* y, int n, int c, int h, int wd, int dtype, gim_stream_t stream);

@@ -23,7 +23,7 @@ PROTOTYPES = {
     "gim_conv2d_fwd_fused": "ppppppiiiiiiiifp",
     "gim_pool2_multi": "pppppiiiiffp",
     "gim_first_block_fwd": "pppppppiiiiiifp",
-    "gim_first_block_wgrad": "pppppiiiiiifp",
+    "gim_first_block_wgrad": "ppppppliiiiiifp",
     "gim_unpool2_cast": "ppiiiifp",
     "gim_conv2d_wgrad": "pppiiiiiiiip",
     "gim_weight_cast": "ppiiiip",

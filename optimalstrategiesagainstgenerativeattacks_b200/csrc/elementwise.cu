@@ -676,6 +676,300 @@ __global__ void __launch_bounds__(256) first_block_wgrad_kernel(const float* __r
     }
 }
 
+// Tensor-core variant of the same pass (cout <= 128): per band the weight gradient of the k x k conv is the GEMM
+//   gw_r1[co][tap*C+ch] += sum_{pix in band} gt[pix][co] * patch[pix][tap*C+ch]      (M = co, N = 9C padded to 16 / 32, K = pixels)
+// on mma.sync.m16n8k16 (bf16 x bf16 -> fp32): the gradient band is staged with cp.async exactly as it lies in memory ([pix][co]) and the
+// im2col patch tile [pix][N] is built in shared memory from the activated input band; both operands have the contraction index (pixel)
+// as their ROW index, so both fragments come from ldmatrix.trans.  Row pitches are padded by 16 bytes (conflict-free ldmatrix).  Warp w
+// owns output channels 16w..16w+15 and keeps its N/8 x 4 accumulators across all bands of the persistent CTA; the 1x1 residual gradient
+// stays on the FFMA path (one FMA per pooled gradient element).  The pass is bound by reading gt (2 B/element) and gy (4 B per pooled
+// element) once.
+// im2col patch tile of a band: ps[pix][tap*C+ch] = bf16(xs[r+dr][q+dq][ch]) (zero beyond 9C), one 16-byte store per 8 columns; the tap
+// arithmetic is resolved at compile time (the chunk index is matched against an unrolled loop), one runtime division per item
+template <int C, int NP, int PP>
+__device__ __forceinline__ void build_patch_tile(bf16* ps, const float* xs, int band_px, int w) {
+    constexpr int KK = 9 * C, CH = NP / 8;
+    for (int item = threadIdx.x; item < band_px * CH; item += blockDim.x) {
+        const int pix = item / CH, chunk = item - pix * CH;
+        const int r = pix / w, q = pix - r * w;
+        const float* base = xs + (r * (w + 2) + q) * C;
+        const int rowp = (w + 2) * C;
+        uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc) {
+            if (chunk == cc) {
+#pragma unroll
+                for (int j2 = 0; j2 < 4; ++j2) {
+                    float v[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int nn = cc * 8 + j2 * 2 + e;
+                        const int tap = nn / C, ch = nn - tap * C, dr = tap / 3, dq = tap - dr * 3;
+                        v[e] = nn < KK ? base[dr * rowp + dq * C + ch] : 0.f;
+                    }
+                    const __nv_bfloat162 hv = __floats2bfloat162_rn(v[0], v[1]);
+                    pk[j2] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(ps + (size_t)pix * PP + chunk * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_16816_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) first_block_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ gt, const float* __restrict__ gy,
+                                                                    float* __restrict__ partial, int replicas, int n, int h, int w, int co,
+                                                                    float slope) {
+    constexpr int KS = 3, TAPS = 9, KK = TAPS * C, NP = (KK + 15) / 16 * 16, NT = NP / 8, PP = NP + 8;
+    // every CTA adds its sums into one of `replicas` zeroed copies of [gw_r1 (9*co*C) | gw_l1 (co*C)]: hundreds of CTAs adding into the
+    // same 5 KB would serialise in two L2 slices; first_block_wgrad_reduce_kernel folds the copies afterwards
+    float* gw_r1 = partial + (size_t)(blockIdx.x % replicas) * (KK + C) * co;
+    float* gw_l1 = gw_r1 + (size_t)KK * co;
+    extern __shared__ __align__(16) unsigned char smem_wg[];
+    const int band_px = kWgRows * w, gp = co + 8;                                  // gp, PP: padded row pitches in bf16 elements
+    bf16* gs = reinterpret_cast<bf16*>(smem_wg);                                   // [band_px][gp]   gradient band, as in memory
+    bf16* ps = gs + (size_t)band_px * gp;                                          // [band_px][PP]   im2col patches of the activated input
+    float* xs = reinterpret_cast<float*>(ps + (size_t)band_px * PP);               // [(kWgRows+2)][w+2][C] activated, zero outside the image
+    float* xps = xs + (kWgRows + 2) * (w + 2) * C;                                 // [kWgRows/2][w/2][C] bf16(AvgPool2(x))
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m0 = warp * 16;                        // this warp's output channels (idle when m0 >= co)
+    float acc[NT][4], accl[4][C];                    // accl: residual gradient of channels l_c4..l_c4+3 over this thread's pooled pixels
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) accl[j][ch] = 0.f;
+    const int chunks_per_row = co / 8;               // 16-byte chunks of a gradient row; the host guarantees 256 % chunks_per_row == 0
+    const int g_r = threadIdx.x / chunks_per_row, g_c8 = (threadIdx.x - g_r * chunks_per_row) * 8, g_rstep = blockDim.x / chunks_per_row;
+    const int l_c4 = (threadIdx.x % (co / 4)) * 4, l_grp = threadIdx.x / (co / 4), l_groups = blockDim.x / (co / 4);
+    const int bands_per_img = h / kWgRows, total_bands = n * bands_per_img;
+    for (int band = blockIdx.x; band < total_bands; band += gridDim.x) {
+        const int img = band / bands_per_img, r0 = (band - img * bands_per_img) * kWgRows;
+        const float* xi = x + (size_t)img * h * w * C;
+        __syncthreads();                             // previous band fully consumed
+        {
+            const bf16* src = gt + ((size_t)img * h + r0) * w * co;
+            for (int r = g_r; r < band_px; r += g_rstep) cp_async_16(gs + (size_t)r * gp + g_c8, src + (size_t)r * co + g_c8);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int i = threadIdx.x; i < (kWgRows + 2) * (w + 2) * C; i += blockDim.x) {
+            const int ch = i % C, q = (i / C) % (w + 2), r = i / (C * (w + 2));
+            const int hh = r0 + r - 1, ww = q - 1;
+            const float v = (hh >= 0 && hh < h && ww >= 0 && ww < w) ? __ldg(xi + (hh * w + ww) * C + ch) : 0.f;
+            xs[i] = lrelu_f(v, slope);
+        }
+        for (int i = threadIdx.x; i < (kWgRows / 2) * (w / 2) * C; i += blockDim.x) {
+            const int ch = i % C, q = (i / C) % (w / 2), r = i / (C * (w / 2));
+            const float* p = xi + ((r0 + 2 * r) * w + 2 * q) * C + ch;
+            xps[i] = __bfloat162float(__float2bfloat16_rn(0.25f * (__ldg(p) + __ldg(p + C) + __ldg(p + w * C) + __ldg(p + w * C + C))));
+        }
+        __syncthreads();
+        build_patch_tile<C, NP, PP>(ps, xs, band_px, w);
+        // 1x1 residual gradient (FFMA): thread = (output channel o, pixel group)
+        {
+            const float* gyb = gy + (((size_t)img * (h / 2) + r0 / 2) * (w / 2)) * co + l_c4;
+#pragma unroll 4
+            for (int pp = l_grp; pp < (kWgRows / 2) * (w / 2); pp += l_groups) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gyb + (size_t)pp * co));
+                const float gl[4] = {__bfloat162float(__float2bfloat16_rn(g4.x)), __bfloat162float(__float2bfloat16_rn(g4.y)),
+                                     __bfloat162float(__float2bfloat16_rn(g4.z)), __bfloat162float(__float2bfloat16_rn(g4.w))};
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float xp = xps[pp * C + ch];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) accl[j][ch] = fmaf(gl[j], xp, accl[j][ch]);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (m0 < co) {
+            // ldmatrix.trans row addresses: A matrices (co 0-7 | 8-15) x (pix 0-7 | 8-15); B matrices (pix 0-7 | 8-15) x (n-tile pair)
+            const bf16* a_ptr = gs + (size_t)((lane & 7) + ((lane >> 4) << 3)) * gp + m0 + (((lane >> 3) & 1) << 3);
+            const bf16* b_ptr = ps + (size_t)((lane & 7) + (((lane >> 3) & 1) << 3)) * PP + ((lane >> 4) << 3);
+            for (int k0 = 0; k0 < band_px; k0 += 16) {
+                uint32_t a[4];
+                ldmatrix_x4_trans(a, a_ptr + (size_t)k0 * gp);
+#pragma unroll
+                for (int t2 = 0; t2 < NT / 2; ++t2) {
+                    uint32_t b[4];
+                    ldmatrix_x4_trans(b, b_ptr + (size_t)k0 * PP + t2 * 16);
+                    mma_16816_bf16(acc[2 * t2], a, b[0], b[1]);
+                    mma_16816_bf16(acc[2 * t2 + 1], a, b[2], b[3]);
+                }
+            }
+        }
+    }
+    if (m0 < co) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int oo = m0 + (lane >> 2) + ((e >> 1) << 3), nn = t * 8 + ((lane & 3) << 1) + (e & 1);      // C fragment: rows g / g+8, cols 2q / 2q+1
+                if (nn < KK) {
+                    const int tap = nn / C, ch = nn - tap * C;
+                    atomicAdd(&gw_r1[((size_t)tap * co + oo) * C + ch], acc[t][e]);
+                }
+            }
+    }
+    __syncthreads();                                 // all MMA reads of the last band are done: the patch tile is free
+    float* lred = reinterpret_cast<float*>(ps);      // [co][C]
+    for (int i = threadIdx.x; i < co * C; i += blockDim.x) lred[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) atomicAdd(&lred[(l_c4 + j) * C + ch], accl[j][ch]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < co * C; i += blockDim.x) atomicAdd(&gw_l1[i], lred[i]);
+}
+
+// out[i] = sum over replicas of partial[r][i]; the first n1 values go to gw_r1, the rest to gw_l1
+__global__ void __launch_bounds__(256) first_block_wgrad_reduce_kernel(const float* __restrict__ partial, int replicas, int n1, int n2, float* __restrict__ gw_r1,
+                                                                       float* __restrict__ gw_l1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, total = n1 + n2;
+    if (i >= total) return;
+    float sum = 0.f;
+    for (int r = 0; r < replicas; ++r) sum += partial[(size_t)r * total + i];
+    if (i < n1) gw_r1[i] = sum; else gw_l1[i - n1] = sum;
+}
+
+// Tensor-core variant of the first-block forward (cout 64 / 128): per band of kWgRows image rows the k x k conv is the GEMM
+//   acc[pix][co] = sum_k patch[pix][k] * W[co][k]        (M = pixels, N = co, K = 9C padded to 16 / 32)
+// on mma.sync.m16n8k16: the im2col patch tile [pix][K] is built in shared memory from the activated band, the weights are kept
+// transposed [co][K] in shared memory for the lifetime of the persistent CTA (both K-contiguous: plain ldmatrix).  Warp = 16 pixels x all
+// output channels; epilogue bias + LeakyReLU -> bf16 pairs -> per-warp staging tile -> 16-byte coalesced stores (the 16 x co tile is one
+// contiguous 4 KB run of the output).  The pooled 1x1 residual (an outer product) stays on FFMA with float4 stores.
+__device__ __forceinline__ void ldmatrix_x4_plain(uint32_t (&r)[4], const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+template <int C, int CO>
+__global__ void __launch_bounds__(256) first_block_mma_kernel(const float* __restrict__ x, const float* __restrict__ w_r1, const float* __restrict__ b_r1,
+                                                              const float* __restrict__ w_l1, const float* __restrict__ b_l1, bf16* __restrict__ t_out,
+                                                              float* __restrict__ res_out, int n, int h, int w, float slope) {
+    constexpr int KS = 3, TAPS = 9, KK = TAPS * C, NP = (KK + 15) / 16 * 16, KSTEPS = NP / 16, PP = NP + 8, NT = CO / 8, SP = CO + 8;
+    extern __shared__ __align__(16) unsigned char smem_fb[];
+    const int band_px = kWgRows * w;
+    bf16* wT = reinterpret_cast<bf16*>(smem_fb);                                   // [CO][PP]        bf16(W)[co][tap*C+ch], zero padded
+    bf16* ps = wT + CO * PP;                                                       // [band_px][PP]   im2col patches of bf16(LeakyReLU(x))
+    bf16* stage = ps + (size_t)band_px * PP;                                       // [8 warps][16][SP]
+    float* xs = reinterpret_cast<float*>(stage + 8 * 16 * SP);                     // [(kWgRows+2)][w+2][C]
+    float* xps = xs + (kWgRows + 2) * (w + 2) * C;                                 // [kWgRows/2][w/2][C] bf16(AvgPool2(x))
+    float* wls = xps + (kWgRows / 2) * (w / 2) * C;                                // [C][CO]
+    float* b1s = wls + C * CO;
+    float* bls = b1s + CO;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < CO * PP; i += blockDim.x) {
+        const int o = i / PP, k = i - o * PP;
+        float v = 0.f;
+        if (k < KK) {
+            const int tap = k / C, ch = k - tap * C;
+            v = w_r1[((size_t)tap * CO + o) * C + ch];
+        }
+        wT[i] = __float2bfloat16_rn(v);
+    }
+    for (int i = threadIdx.x; i < C * CO; i += blockDim.x) {
+        const int ch = i / CO, o = i - ch * CO;
+        wls[i] = __bfloat162float(__float2bfloat16_rn(w_l1[(size_t)o * C + ch]));
+    }
+    for (int i = threadIdx.x; i < CO; i += blockDim.x) { b1s[i] = b_r1[i]; bls[i] = b_l1[i]; }
+    bf16* my_stage = stage + (size_t)warp * 16 * SP;
+    const int bands_per_img = h / kWgRows, total_bands = n * bands_per_img;
+    for (int band = blockIdx.x; band < total_bands; band += gridDim.x) {
+        const int img = band / bands_per_img, r0 = (band - img * bands_per_img) * kWgRows;
+        const float* xi = x + (size_t)img * h * w * C;
+        __syncthreads();                             // previous band fully consumed (and, first time, the weights are in place)
+        for (int i = threadIdx.x; i < (kWgRows + 2) * (w + 2) * C; i += blockDim.x) {
+            const int ch = i % C, q = (i / C) % (w + 2), r = i / (C * (w + 2));
+            const int hh = r0 + r - 1, ww = q - 1;
+            const float v = (hh >= 0 && hh < h && ww >= 0 && ww < w) ? __ldg(xi + (hh * w + ww) * C + ch) : 0.f;
+            xs[i] = lrelu_f(v, slope);
+        }
+        for (int i = threadIdx.x; i < (kWgRows / 2) * (w / 2) * C; i += blockDim.x) {
+            const int ch = i % C, q = (i / C) % (w / 2), r = i / (C * (w / 2));
+            const float* p = xi + ((r0 + 2 * r) * w + 2 * q) * C + ch;
+            xps[i] = __bfloat162float(__float2bfloat16_rn(0.25f * (__ldg(p) + __ldg(p + C) + __ldg(p + w * C) + __ldg(p + w * C + C))));
+        }
+        __syncthreads();
+        build_patch_tile<C, NP, PP>(ps, xs, band_px, w);
+        // pooled 1x1 residual: the band's two pooled rows are one contiguous [w][CO] run of the output
+        {
+            float* rdst = res_out + (((size_t)img * (h / 2) + r0 / 2) * (w / 2)) * CO;
+            for (int i = threadIdx.x; i < (kWgRows / 2) * (w / 2) * (CO / 4); i += blockDim.x) {
+                const int pp = i / (CO / 4), c4 = (i - pp * (CO / 4)) * 4;
+                float4 o = *reinterpret_cast<const float4*>(bls + c4);
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float xp = xps[pp * C + ch];
+                    const float4 wv = *reinterpret_cast<const float4*>(wls + ch * CO + c4);
+                    o.x = fmaf(xp, wv.x, o.x); o.y = fmaf(xp, wv.y, o.y); o.z = fmaf(xp, wv.z, o.z); o.w = fmaf(xp, wv.w, o.w);
+                }
+                *reinterpret_cast<float4*>(rdst + (size_t)pp * CO + c4) = o;
+            }
+        }
+        __syncthreads();
+        bf16* tdst = t_out + ((size_t)img * h + r0) * w * CO;
+        for (int mt = warp; mt < band_px / 16; mt += 8) {
+            uint32_t a[KSTEPS][4];
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks)     // A 16x16: (rows 0-7,k 0-7) (rows 8-15,k 0-7) (rows 0-7,k 8-15) (rows 8-15,k 8-15)
+                ldmatrix_x4_plain(a[ks], ps + (size_t)(mt * 16 + (lane & 15)) * PP + ks * 16 + ((lane >> 4) << 3));
+            float acc[NT][4];                        // start from the bias (columns 8t + 2q, 8t + 2q + 1 of both row halves)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float2 bb = *reinterpret_cast<const float2*>(b1s + t * 8 + ((lane & 3) << 1));
+                acc[t][0] = bb.x; acc[t][1] = bb.y; acc[t][2] = bb.x; acc[t][3] = bb.y;
+            }
+#pragma unroll
+            for (int t2 = 0; t2 < NT / 2; ++t2)
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {   // B, two n8 tiles per x4: (n 0-7,k 0-7) (n 0-7,k 8-15) (n 8-15,k 0-7) (n 8-15,k 8-15)
+                    uint32_t b[4];
+                    ldmatrix_x4_plain(b, wT + (size_t)(t2 * 16 + (lane & 7) + ((lane >> 4) << 3)) * PP + ks * 16 + (((lane >> 3) & 1) << 3));
+                    mma_16816_bf16(acc[2 * t2], a[ks], b[0], b[1]);
+                    mma_16816_bf16(acc[2 * t2 + 1], a[ks], b[2], b[3]);
+                }
+            __syncwarp();                            // the previous tile's staging reads are done
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int col = t * 8 + ((lane & 3) << 1);
+                // LeakyReLU(v) = max(v, slope * v) for 0 <= slope <= 1 (checked by the host)
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(acc[t][0], slope * acc[t][0]), fmaxf(acc[t][1], slope * acc[t][1]));
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(acc[t][2], slope * acc[t][2]), fmaxf(acc[t][3], slope * acc[t][3]));
+                *reinterpret_cast<__nv_bfloat162*>(my_stage + (size_t)(lane >> 2) * SP + col) = lo;
+                *reinterpret_cast<__nv_bfloat162*>(my_stage + (size_t)((lane >> 2) + 8) * SP + col) = hi;
+            }
+            __syncwarp();
+            constexpr int CH = CO / 8;               // 16-byte chunks per pixel row
+            bf16* tile = tdst + (size_t)mt * 16 * CO;
+#pragma unroll
+            for (int i = lane; i < 16 * CH; i += 32) {
+                const int r = i / CH, c8 = (i - r * CH) * 8;
+                *reinterpret_cast<uint4*>(tile + (size_t)r * CO + c8) = *reinterpret_cast<const uint4*>(my_stage + (size_t)r * SP + c8);
+            }
+        }
+    }
+}
+
 // The conv-operand producer: out = f(x) in the operand dtype, f = identity / LeakyReLU / nearest-upsample x2 (out is [n,2h,2w,c]).
 // One pass (4 B read, 2 B written per element on the bf16 path) instead of activation kernel + cast kernel.
 template <typename TI, typename TO>
@@ -839,6 +1133,32 @@ int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, co
         attr_set = true;
     }
     const long long total = (long long)n * h * wd * (cout / 8);
+    static const bool fwd_simt_only = getenv("GIM_FB_FWD_SIMT") != nullptr;
+    if (!fwd_simt_only && ksize == 3 && (c == 1 || c == 3) && (cout == 128 || cout == 64) && wd % 4 == 0 && h % kWgRows == 0 && slope >= 0.f && slope <= 1.f) {     // tensor-core pass
+        const int np = (9 * c + 15) / 16 * 16;
+        const size_t smem_mma = 2 * ((size_t)cout * (np + 8) + (size_t)kWgRows * wd * (np + 8) + (size_t)8 * 16 * (cout + 8)) +
+                                sizeof(float) * ((size_t)(kWgRows + 2) * (wd + 2) * c + (size_t)(kWgRows / 2) * (wd / 2) * c + (size_t)c * cout + 2 * (size_t)cout);
+        GIM_REQUIRE(smem_mma <= 200 * 1024, "first_block_fwd: band does not fit in shared memory");
+        const void* fn = c == 1 ? (cout == 128 ? (const void*)first_block_mma_kernel<1, 128> : (const void*)first_block_mma_kernel<1, 64>)
+                                : (cout == 128 ? (const void*)first_block_mma_kernel<3, 128> : (const void*)first_block_mma_kernel<3, 64>);
+        static bool mma_attr = false;
+        if (!mma_attr) {
+            if (cudaFuncSetAttribute(first_block_mma_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(first_block_mma_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(first_block_mma_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(first_block_mma_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+                return fail(GIM_E_CUDA, "first_block_fwd: cannot raise dynamic shared memory limit");
+            mma_attr = true;
+        }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem_mma) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const int bands = n * (h / kWgRows);
+        int grid = per_sm * num_sms();
+        if (grid > bands) grid = bands;
+        void* args[] = {(void*)&x, (void*)&w_r1, (void*)&b_r1, (void*)&w_l1, (void*)&b_l1, (void*)&t_bf16, (void*)&res_pooled, (void*)&n, (void*)&h, (void*)&wd, (void*)&slope};
+        if (cudaLaunchKernel(fn, dim3(grid), dim3(256), args, smem_mma, (cudaStream_t)s) != cudaSuccess) return fail(GIM_E_CUDA, "first_block_mma launch failed");
+        return check_launch("first_block_mma");
+    }
     if (ksize == 3 && (c == 1 || c == 3) && wd % 4 == 0) {      // the two image formats of the GIM configs: grey and RGB, 3x3
         static bool quad_attr = false;
         if (!quad_attr) {
@@ -858,14 +1178,46 @@ int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, co
     first_block_kernel<<<grid, 256, smem, (cudaStream_t)s>>>(x, w_r1, b_r1, w_l1, b_l1, (bf16*)t_bf16, res_pooled, n, h, wd, c, cout, ksize, slope);
     return check_launch("first_block_fwd");
 }
-int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_pooled, float* gw_r1, float* gw_l1, int n, int h, int wd, int c, int cout,
-                          int ksize, float slope, gim_stream_t s) {
+int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_pooled, float* gw_r1, float* gw_l1, float* scratch, long long scratch_floats,
+                          int n, int h, int wd, int c, int cout, int ksize, float slope, gim_stream_t s) {
     GIM_REQUIRE(n > 0 && h >= kWgRows && wd > 1 && h % kWgRows == 0 && !(wd & 1), "first_block_wgrad: h must be a multiple of 4 and w even");
     GIM_REQUIRE(ksize == 3 && (c == 1 || c == 3) && cout % 8 == 0 && cout <= 256 && 256 % cout == 0, "first_block_wgrad: unsupported shape");
     GIM_REQUIRE(aligned16(gt_bf16), "first_block_wgrad: gradient tensor must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)s;
-    if (cudaMemsetAsync(gw_r1, 0, sizeof(float) * 9 * (size_t)cout * c, st) != cudaSuccess || cudaMemsetAsync(gw_l1, 0, sizeof(float) * (size_t)cout * c, st) != cudaSuccess)
+    static const bool simt_only = getenv("GIM_FB_WGRAD_SIMT") != nullptr;
+    const long long out_floats = 10LL * cout * c;
+    const bool mma = !simt_only && cout % 16 == 0 && cout <= 128 && wd % 4 == 0 && scratch && scratch_floats >= out_floats;
+    if (!mma && (cudaMemsetAsync(gw_r1, 0, sizeof(float) * 9 * (size_t)cout * c, st) != cudaSuccess ||
+                 cudaMemsetAsync(gw_l1, 0, sizeof(float) * (size_t)cout * c, st) != cudaSuccess))
         return fail(GIM_E_CUDA, "first_block_wgrad memset");
+    if (mma) {                                        // tensor-core pass (band_px = 4 * wd is a multiple of 16)
+        int replicas = (int)(scratch_floats / out_floats);
+        if (replicas > 32) replicas = 32;
+        if (cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)replicas * out_floats, st) != cudaSuccess) return fail(GIM_E_CUDA, "first_block_wgrad memset");
+        const int np = (9 * c + 15) / 16 * 16;
+        const size_t smem_mma = (size_t)kWgRows * wd * ((cout + 8) + (np + 8)) * 2 + sizeof(float) * ((size_t)(kWgRows + 2) * (wd + 2) * c + (size_t)(kWgRows / 2) * (wd / 2) * c);
+        GIM_REQUIRE(smem_mma <= 200 * 1024, "first_block_wgrad: band does not fit in shared memory");
+        static bool mma_attr = false;
+        if (!mma_attr) {
+            if (cudaFuncSetAttribute(first_block_wgrad_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(first_block_wgrad_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+                return fail(GIM_E_CUDA, "first_block_wgrad: cannot raise dynamic shared memory limit");
+            mma_attr = true;
+        }
+        const int bands = n * (h / kWgRows);
+        int per_sm = 0;                               // persistent grid = exactly the resident CTAs (registers and smem both count)
+        cudaError_t oe = c == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_block_wgrad_mma_kernel<1>, 256, smem_mma)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_block_wgrad_mma_kernel<3>, 256, smem_mma);
+        if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+        int grid = per_sm * num_sms();
+        if (grid > bands) grid = bands;
+        if (c == 1) first_block_wgrad_mma_kernel<1><<<grid, 256, smem_mma, st>>>(x, (const bf16*)gt_bf16, gy_pooled, scratch, replicas, n, h, wd, cout, slope);
+        else first_block_wgrad_mma_kernel<3><<<grid, 256, smem_mma, st>>>(x, (const bf16*)gt_bf16, gy_pooled, scratch, replicas, n, h, wd, cout, slope);
+        int rc = check_launch("first_block_wgrad_mma");
+        if (rc != GIM_OK) return rc;
+        first_block_wgrad_reduce_kernel<<<(unsigned)((out_floats + 255) / 256), 256, 0, st>>>(scratch, replicas, 9 * cout * c, cout * c, gw_r1, gw_l1);
+        return check_launch("first_block_wgrad_reduce");
+    }
     const size_t smem = (size_t)kWgRows * wd * cout * 2 + sizeof(float) * ((size_t)(kWgRows + 2) * (wd + 2) * c + (size_t)(kWgRows / 2) * (wd / 2) * c + (size_t)(9 * c + c) * cout);
     GIM_REQUIRE(smem <= 200 * 1024, "first_block_wgrad: band does not fit in shared memory");
     static bool attr_set = false;

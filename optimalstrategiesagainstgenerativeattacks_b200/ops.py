@@ -624,7 +624,9 @@ class ResBlockDownFn(Function):
             # both image-side weight gradients in one pass over the gradients (K <= 27 outer products: no im2col, no tensor-core launch)
             gw1 = _empty((taps, co, ci), torch.float32, gy)
             gwl = _empty((1, co, ci), torch.float32, gy)
-            C.call("gim_first_block_wgrad", C.ptr(x32), C.ptr(gt), C.ptr(gy), C.ptr(gw1), C.ptr(gwl), n, h, w, ci, co, ks, slope)
+            scratch = _empty((32 * 10 * co * ci,), torch.float32, gy)        # per-CTA-group copies of the two results (see gim_b200.h)
+            C.call("gim_first_block_wgrad", C.ptr(x32), C.ptr(gt), C.ptr(gy), C.ptr(gw1), C.ptr(gwl), C.ptr(scratch), scratch.numel(), n, h, w, ci, co, ks,
+                   slope)
             if not ctx.needs_input_grad[3]:
                 gwl = None
             if not ctx.needs_input_grad[5]:

@@ -18,9 +18,10 @@ t = torch.empty((n, h, w, co), device=dev, dtype=torch.bfloat16)
 r = torch.empty((n, h // 2, w // 2, co), device=dev)
 gt = torch.randn((n, h, w, co), device=dev).bfloat16()
 gy = torch.randn((n, h // 2, w // 2, co), device=dev)
+scr = torch.empty(32 * 10 * co * c, device=dev)
 gw1, gwl = torch.empty((k * k, co, c), device=dev), torch.empty((1, co, c), device=dev)
 fwd = lambda: C.call("gim_first_block_fwd", C.ptr(x), C.ptr(w1), C.ptr(b1), C.ptr(wl), C.ptr(bl), C.ptr(t), C.ptr(r), n, h, w, c, co, k, 0.2)
-wg = lambda: C.call("gim_first_block_wgrad", C.ptr(x), C.ptr(gt), C.ptr(gy), C.ptr(gw1), C.ptr(gwl), n, h, w, c, co, k, 0.2)
+wg = lambda: C.call("gim_first_block_wgrad", C.ptr(x), C.ptr(gt), C.ptr(gy), C.ptr(gw1), C.ptr(gwl), C.ptr(scr), scr.numel(), n, h, w, c, co, k, 0.2)
 for name, f, nbytes in (("fwd", fwd, t.numel() * 2 + r.numel() * 4), ("wgrad", wg, gt.numel() * 2 + gy.numel() * 4)):
     for _ in range(3):
         f()
