@@ -136,14 +136,15 @@ __global__ void norm_bwd_coeffs_kernel(int mode, const float* __restrict__ m2, c
 }
 
 // InstanceNorm affine parameter gradients: reduce over the image axis (one thread per channel; n*c is tiny)
-// grid (ceil(c/32)), block (32, 8): lanes = adjacent channels (coalesced rows of the [n][c] arrays), 8 image-lanes reduced in smem
-__global__ void __launch_bounds__(256) in_param_grad_kernel(const float* __restrict__ m2, const float* __restrict__ s1, const float* __restrict__ s2,
+// grid (ceil(c/32)), block (32, 32): lanes = adjacent channels (coalesced rows of the [n][c] arrays), 32 image-lanes reduced in smem
+// (the loop over images is a chain of dependent-latency loads: 1024 threads keep it at n/32 steps)
+__global__ void __launch_bounds__(1024) in_param_grad_kernel(const float* __restrict__ m2, const float* __restrict__ s1, const float* __restrict__ s2,
                                                             float* __restrict__ g_scale, float* __restrict__ g_shift, int n, int hw, int c, float eps) {
-    __shared__ float sh1[8][33], sh2[8][33];
+    __shared__ float sh1[32][33], sh2[32][33];
     int ch = blockIdx.x * 32 + threadIdx.x;
     float gs = 0.f, gb = 0.f;
     if (ch < c)
-        for (int img = threadIdx.y; img < n; img += 8) {
+        for (int img = threadIdx.y; img < n; img += 32) {
             int i = img * c + ch;
             gs += rsqrtf(m2[i] / (float)hw + eps) * s2[i];
             gb += s1[i];
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) in_param_grad_kernel(const float* __restr
     if (threadIdx.y == 0 && ch < c) {
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a += sh1[j][threadIdx.x]; b += sh2[j][threadIdx.x]; }
+        for (int j = 0; j < 32; ++j) { a += sh1[j][threadIdx.x]; b += sh2[j][threadIdx.x]; }
         g_scale[ch] = a;
         g_shift[ch] = b;
     }
@@ -209,7 +210,7 @@ int gim_norm_bwd_coeffs(int mode, const float* m2, const float* s1, const float*
     norm_bwd_coeffs_kernel<<<(n * c + 255) / 256, 256, 0, (cudaStream_t)s>>>(mode, m2, s1, s2, p_scale, A, B, C, g_scale, g_shift, n, hw, c, eps);
     int rc = check_launch("norm_bwd_coeffs");
     if (rc != GIM_OK || mode != 0) return rc;
-    in_param_grad_kernel<<<(c + 31) / 32, dim3(32, 8), 0, (cudaStream_t)s>>>(m2, s1, s2, g_scale, g_shift, n, hw, c, eps);
+    in_param_grad_kernel<<<(c + 31) / 32, dim3(32, 32), 0, (cudaStream_t)s>>>(m2, s1, s2, g_scale, g_shift, n, hw, c, eps);
     return check_launch("in_param_grad");
 }
 
