@@ -73,6 +73,9 @@ int gim_weight_flip(const float* w, void* out, int taps, int cout, int cin, int 
 int gim_colsum(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t stream);
 /* out[c] += sum_rows x[row][c]: accumulates straight into a parameter's .grad (no memset, no separate accumulation kernel) */
 int gim_colsum_acc(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t stream);
+/* y = bf16(x) and sums[c] (+)= column sums of the fp32 [rows][c] matrix x in one pass (Conv2d backward: operand copy of the output
+ * gradient + bias gradient); c = 8 * 2^k <= 2048; accumulate != 0 adds into sums (e.g. straight into bias.grad) */
+int gim_cast_colsum(const float* x, void* y_bf16, float* sums, long long rows, int c, int accumulate, gim_stream_t stream);
 
 /* ---- spectral norm: torch.nn.utils.spectral_norm hook, 1 power iteration (model_blocks.py:492-495 etc.) ---- */
 /* weight_orig [cout][cin][k][k] fp32; u[cout], v[cin*k*k] updated in place when power_iter!=0;

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "gim_weight_flip": "ppiiiip",
     "gim_colsum": "pplii" + "p",
     "gim_colsum_acc": "pplii" + "p",
+    "gim_cast_colsum": "pppliip",
     "gim_sn_forward": "pppifpppppiiip",
     "gim_sn_backward": "pppppppiiip",
     "gim_sn_forward_multi": "piifp",

@@ -232,6 +232,39 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
     }
 }
 
+// bf16 operand copy and column sums of an fp32 [rows][c] gradient in ONE pass (Conv2d backward needs both: the operand of the
+// input-/weight-gradient convolutions and the bias gradient).  Thread = 8 adjacent channels (two 16-byte loads, one 16-byte store) of
+// a fixed channel group; rows advance by blockDim/(c/8) per step; per-CTA partial sums meet in shared memory, one atomic per channel
+// and CTA.  c/8 must divide 256.
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ x, bf16* __restrict__ y, float* __restrict__ sums, long long rows, int c) {
+    __shared__ float red[2048];                       // [row lane][c] for c <= 2048 / (256 / (c/8)) ... sized for the worst case c = 2048
+    const int groups = c >> 3, cg = threadIdx.x % groups, rl = threadIdx.x / groups, rlanes = blockDim.x / groups;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long r = (long long)blockIdx.x * rlanes + rl; r < rows; r += (long long)gridDim.x * rlanes) {
+        const float4* src = reinterpret_cast<const float4*>(x + r * c + cg * 8);
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w), p2 = __floats2bfloat162_rn(b.x, b.y),
+                       p3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(y + r * c + cg * 8) = o;
+    }
+    // threads with the same channel group: thread (rl, cg) holds red[rl * c + cg * 8 + j]; rlanes * c == 2048
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl * c + cg * 8 + j] = acc[j];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float t = 0.f;
+        for (int q = 0; q < rlanes; ++q) t += red[q * c + ch];
+        atomicAdd(&sums[ch], t);
+    }
+}
+
 template <typename T, typename TO>
 static int conv_fwd_simt(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
     long long npix = (long long)n * h * wd;
@@ -341,6 +374,20 @@ static int colsum_launch(const void* x, float* out, long long rows, int c, int d
 
 int gim_colsum(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t s) { return colsum_launch(x, out, rows, c, dtype, false, s); }
 int gim_colsum_acc(const void* x, float* out, long long rows, int c, int dtype, gim_stream_t s) { return colsum_launch(x, out, rows, c, dtype, true, s); }
+
+int gim_cast_colsum(const float* x, void* y_bf16, float* sums, long long rows, int c, int accumulate, gim_stream_t s) {
+    if (c <= 0) return GIM_OK;
+    GIM_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "cast_colsum: channels must be 8 * 2^k <= 2048");
+    GIM_REQUIRE((((uintptr_t)x | (uintptr_t)y_bf16) & 15) == 0, "cast_colsum: 16-byte alignment");
+    if (!accumulate && cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)c, (cudaStream_t)s) != cudaSuccess) return fail(GIM_E_CUDA, "cast_colsum memset");
+    if (rows <= 0) return GIM_OK;
+    const int rlanes = 256 / (c / 8);
+    long long want = (rows + rlanes * 4 - 1) / (rlanes * 4);                  // >= 4 row steps per CTA
+    if (want > 2LL * num_sms()) want = 2LL * num_sms();
+    if (want < 1) want = 1;
+    cast_colsum_kernel<<<(unsigned)want, 256, 0, (cudaStream_t)s>>>(x, (bf16*)y_bf16, sums, rows, c);
+    return check_launch("cast_colsum");
+}
 
 static int colsum_launch(const void* x, float* out, long long rows, int c, int dtype, bool accumulate, gim_stream_t s) {
     if (c <= 0) return GIM_OK;

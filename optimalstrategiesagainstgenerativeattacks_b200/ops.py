@@ -325,6 +325,11 @@ class Conv2dFn(Function):
         ks, pre, slope, has_bias = ctx.cfg
         gy = _c(gy)
         gx = gw = gb = None
+        want_gb = has_bias and ctx.needs_input_grad[2] and not _state["input_grads_only"]
+        if want_gb and not torch.is_grad_enabled():
+            # first-order pass: the bias gradient comes out of the pass that rounds gy to the bf16 operand (and goes straight into bias.grad)
+            gb = _bias_grad_with_operand(gy, ctx.bias_param)
+            want_gb = False
         if ctx.needs_input_grad[0]:
             gx = ConvTransposeFn.apply(gy, w32, ks)
             if pre == PRE_LRELU:
@@ -334,9 +339,8 @@ class Conv2dFn(Function):
         if not _state["input_grads_only"]:
             if ctx.needs_input_grad[1]:
                 gw = WgradFn.apply(xs, gy, ks)
-            if has_bias and ctx.needs_input_grad[2]:
-                # first-order pass: straight into bias.grad; when a graph of the backward is being built, the differentiable operator
-                gb = ColSumFn.apply(gy) if torch.is_grad_enabled() else _bias_grad(gy, ctx.bias_param)
+            if want_gb:                                # a graph of the backward is being built: the differentiable operator
+                gb = ColSumFn.apply(gy)
         return gx, gw, gb, None, None, None
 
 
@@ -456,6 +460,31 @@ def _skinny_in(xop, w_t, ks):
 
 def _unskinny_gw(gw2, taps, co, ci):
     return gw2[0, :, :taps * ci].reshape(co, taps, ci).permute(1, 0, 2).contiguous()
+
+
+def _cast_colsum_ok(g):
+    c = g.shape[-1]
+    return (_state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and g.dtype == torch.float32 and c % 8 == 0 and c <= 2048
+            and 256 % (c // 8) == 0 and (c // 8) & (c // 8 - 1) == 0 and g.data_ptr() % 16 == 0)
+
+
+def _bias_grad_with_operand(g, param):
+    """Bias gradient of a convolution whose output gradient `g` (fp32) is also about to be rounded to the bf16 operand of the input- and
+    weight-gradient convolutions: one pass writes the operand copy (registered, so _operand(g) finds it) and the column sums -- straight
+    into the leaf's .grad inside `deferred_weight_grads()`, like _bias_grad."""
+    if not _cast_colsum_ok(g):
+        return _bias_grad(g, param)
+    hit = _cast_memo.get(id(g))
+    if hit is not None and hit[0]() is g and hit[1] == g._version:
+        return _bias_grad(g, param)                # operand copy already exists
+    c = g.shape[-1]
+    op = torch.empty(g.shape, dtype=torch.bfloat16, device=g.device)
+    direct = (_state["defer_sn"] and param is not None and param.is_leaf and param.requires_grad and param.dtype == torch.float32 and param.is_contiguous()
+              and param.grad is not None and param.grad.is_contiguous())
+    out = param.grad if direct else _empty((c,), torch.float32, g)
+    C.call("gim_cast_colsum", C.ptr(g), C.ptr(op), C.ptr(out), g.numel() // c, c, 1 if direct else 0)
+    register_operand(g, op)
+    return None if direct else out
 
 
 def _bias_grad(x, param):
