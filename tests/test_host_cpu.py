@@ -94,3 +94,39 @@ def test_checkpoint_io_schema_async_and_atomic(tmp_path):
         step, epoch = io2.load(path)
         assert epoch == 3 and gs2.get() == 41 and torch.equal(net2.weight, net.weight)
         assert io2.load(str(tmp_path / "missing.pt")) == (-1, -1)
+
+
+def test_cat_params_direct_accumulation_and_merged_rows():
+    """Host-side autograd plumbing of the merged projections (no kernel involved): CatParamsFn hands out row blocks of the gradient, or --
+    inside deferred_weight_grads() with allocated .grad -- adds them straight into the leaves; _MergedRowsFn is a view forward and a split
+    backward."""
+    import torch
+    from optimalstrategiesagainstgenerativeattacks_b200 import ops
+    torch.manual_seed(0)
+    ws = [torch.randn(r, 4, requires_grad=True) for r in (2, 3, 5)]
+    pad = torch.zeros(6, 4)
+    probe = torch.randn(16, 4)
+    ref = torch.autograd.grad((torch.cat(ws + [pad], 0) * probe).sum(), ws)
+    got = torch.autograd.grad((ops.cat_params(ws + [pad]) * probe).sum(), ws)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    for w in ws:
+        w.grad = torch.ones_like(w)
+    with ops.deferred_weight_grads():
+        (ops.cat_params(ws + [pad]) * probe).sum().backward()
+    for w, r in zip(ws, ref):
+        assert torch.allclose(w.grad, r + 1.0)
+    # without the context the ordinary AccumulateGrad route gives the same result
+    for w in ws:
+        w.grad = torch.ones_like(w)
+    (ops.cat_params(ws + [pad]) * probe).sum().backward()
+    for w, r in zip(ws, ref):
+        assert torch.allclose(w.grad, r + 1.0)
+
+    buf = torch.arange(40, dtype=torch.float32)
+    parts = [buf[0:8].view(1, 2, 4).clone().requires_grad_(), buf[8:20].view(1, 3, 4).clone().requires_grad_()]
+    merged = ops._MergedRowsFn.apply((buf, 0), *parts)
+    assert merged.shape == (1, 5, 4) and merged.data_ptr() == buf.data_ptr()
+    g = torch.randn(1, 5, 4)
+    ga, gb = torch.autograd.grad((merged * g).sum(), parts)
+    assert torch.equal(ga, g[:, :2]) and torch.equal(gb, g[:, 2:])
