@@ -2,18 +2,28 @@
 """bench.py -- GIM train episodes/sec (fwd+bwd G+D) on N B200s of one node (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload O|V] [--batch B] [--precision bf16|fp32]
+                  [--no-secondary] [--no-cpu-baseline] [--no-gpu-baseline] [--check]
 
 A "step" is one training iteration = one attacker (G) step + one authenticator (D) step over B episodes per GPU through the
 kept trainer API (GIMImgTrainer + im_train_step / au_train_step).  Default workload = BASELINE.json configs[1]: synthetic
 Omniglot-shaped episodes, m=n=k=5, at the reference's own Omniglot resolution 1x32x32 (the reference Impersonator cannot run
 at 105x105), reg 0, Adam(0, 0.99), lrs 1e-6/1e-5/1e-7, bf16 tensor-core path.
 
-Rank 0 prints ONE JSON line (see the contract in the task statement): `value` = whole-job episodes/s with inputs resident in
-HBM; `e2e` = the same through the public API with pinned-host inputs copied in and the losses read back every step;
-`roofline` = the dominant kernel (tcgen05 implicit-GEMM conv) against the measured bf16 peak; `cpu_baseline` = the CPU oracle
-port of the same step timed on this box's host cores on a bounded sample.  `--impl reference` times that CPU port alone.
+Rank 0 prints ONE JSON line on stdout (everything else goes to stderr):
+  value            whole-job episodes/s, inputs resident in HBM
+  e2e              the same through the public API with pinned-host inputs copied in and the losses read back every step
+  roofline         the dominant kernel (tcgen05 implicit-GEMM conv forward/input-gradient) against the measured bf16 peak
+  secondary        BASELINE configs[2] (VoxCeleb2-shaped 3x64x64, R1 reg=10): weak scaling at 32 episodes/GPU and strong scaling
+                   at the published global batch of 128 episodes (128/N per GPU), same timing rules
+  cpu_baseline     the reference's own trainer (oracle/_ref, kind "reference"; else the oracle port, kind "port") on this box's
+                   host cores: B=8, 2 warm-up + 5 timed iterations; N=1 only
+  gpu_eager_baseline  the same unmodified reference code with device='cuda' (eager PyTorch/cuDNN, default fp32 flags) at the
+                   GPU arm's batch: the GPU bar of BASELINE.md section 5.4; N=1 only
+`--impl reference` times the reference CPU leg alone (same config/metric/unit).  `--check` (N >= 2) verifies the data-parallel
+path instead of timing it: sharded gradients == global-batch gradients, replicas stay bit-identical.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -33,8 +43,10 @@ WORKLOADS = {
     "O": (32, 1, 0.0, 1e-6, 1e-5, 1e-7, 281.0, "GIM Omniglot-shaped 1x32x32 m=n=k=5 reg=0 (BASELINE configs[1] at the reference's Omniglot resolution)"),
     "V": (64, 3, 10.0, 1e-4, 1e-4, 1e-6, 494.0, "GIM VoxCeleb2-shaped 3x64x64 m=n=k=5 R1 reg=10 (BASELINE configs[2])"),
 }
+DEFAULT_BATCH = {"O": 128, "V": 32}
 M_, N_, K_ = 5, 5, 5
 STYLE = 512
+METRIC = "GIM train episodes/sec (fwd+bwd G+D)"
 
 
 def parse():
@@ -46,10 +58,20 @@ def parse():
     ap.add_argument("--workload", default="O", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU per step (default 128 for O, 32 for V)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--check", action="store_true", help="verify the data-parallel path (run under torchrun with N >= 2)")
     return ap.parse_args()
+
+
+def config_of(workload, batch, world):
+    """The static description of the workload: identical in the GPU arm and in the reference arm."""
+    return {"workload": WORKLOADS[workload][7], "episodes_per_gpu_per_step": batch, "m": M_, "n": N_, "k": K_, "style_dim": STYLE,
+            "parallelism": "dp%d" % world, "algorithmic_gflop_per_episode": WORKLOADS[workload][6],
+            "cache": "working set (activations of %d images/step) >> 126 MB L2; 2 rotating input batches" % (batch * 45)}
 
 
 def synth_batch(b, ch, size, seed, device, pin=False):
@@ -64,17 +86,39 @@ def synth_batch(b, ch, size, seed, device, pin=False):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU leg: the oracle port of the same training iteration (test infrastructure used as the *measured baseline* only)
+# reference legs: the UNMODIFIED reference (oracle/_ref/reference.zip, packed by oracle/build_ref.py) or, when it is absent,
+# the oracle port of the same training iteration.  Test infrastructure used as the *measured baseline* only.
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_iteration_factory(workload, batch):
+def reference_iteration_factory(workload, batch, device):
+    """-> (iteration(), kind).  kind 'reference': training/gim_img_trainer.py + gim_img_training.py:157-183 of the reference itself."""
     import torch
+    from oracle import ref_shim
+    size, ch, reg, au_lr, im_lr, map_lr = WORKLOADS[workload][:6]
+    leaked, real, si = synth_batch(batch, ch, size, 1234, device)
+    if ref_shim.available() is not None:
+        ref_shim.install()
+        import models.gim_img_models as RM
+        import training.gim_img_training as RL
+        from training.gim_img_trainer import GIMImgTrainer as RefTrainer
+        from training.utils import DataParallelMock as RefMock
+        torch.manual_seed(1)
+        au, im = RM.get_au(size, ch, STYLE).to(device), RM.get_im(size, ch, STYLE).to(device)
+        tr = RefMock(RefTrainer(tempfile.mkdtemp(prefix="gim_ref_"), M_, N_, K_, au, im, au_lr, im_lr, map_lr, reg_param=reg).to(device))
+
+        def iteration():
+            tr.module.do_global_step()
+            tr.module.update_learning_rate()
+            _, fake, _ = RL.im_train_step(tr, leaked, si)
+            o = RL.au_train_step(tr, real, fake, si)
+            return o[0]
+        return iteration, "reference"
+
     from oracle import gim_oracle as O
     from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_models as M
-    size, ch, reg, au_lr, im_lr, map_lr = WORKLOADS[workload][:6]
     torch.manual_seed(1)
-    au, im = M.get_au(size, ch, STYLE), M.get_im(size, ch, STYLE)       # same initialisation as the GPU arm (CPU tensors)
-    pa = {k: v.detach().clone() for k, v in au.state_dict().items()}
-    pi = {k: v.detach().clone() for k, v in im.state_dict().items()}
+    au, im = M.get_au(size, ch, STYLE), M.get_im(size, ch, STYLE)       # same initialisation as the GPU arm
+    pa = {k: v.detach().clone().to(device) for k, v in au.state_dict().items()}
+    pi = {k: v.detach().clone().to(device) for k, v in im.state_dict().items()}
     a_names = [k for k, _ in au.named_parameters()]
     i_names = [k for k, _ in im.named_parameters()]
     for n_ in a_names:
@@ -83,12 +127,11 @@ def cpu_iteration_factory(workload, batch):
         pi[n_].requires_grad_()
     st_a = {"step": 0, "m": [torch.zeros_like(pa[x]) for x in a_names], "v": [torch.zeros_like(pa[x]) for x in a_names]}
     st_i = {"step": 0, "m": [torch.zeros_like(pi[x]) for x in i_names], "v": [torch.zeros_like(pi[x]) for x in i_names]}
-    leaked, real, si = synth_batch(batch, ch, size, 1234, "cpu")
 
     def iteration():
         for v in list(pa.values()) + list(pi.values()):
             v.grad = None
-        z = torch.randn((batch, N_, STYLE))
+        z = torch.randn((batch, N_, STYLE), device=device)
         fake = O.impersonator(pi, leaked, N_, z)
         O.gan_loss(O.authenticator(pa, fake, si), 1.0).mean().backward()
         O.adam_step([pi[x] for x in i_names], [pi[x].grad for x in i_names], st_i, im_lr, 0.0, 0.99)
@@ -97,41 +140,53 @@ def cpu_iteration_factory(workload, batch):
         out = O.img_authenticator_forward(pa, fake.detach(), real.clone(), si.clone(), reg)
         out[0].mean().backward()
         O.adam_step([pa[x] for x in a_names], [pa[x].grad for x in a_names], st_a, au_lr, 0.0, 0.99)
-        return float(out[0].mean())
-    return iteration
+        return out[0].mean().detach()
+    return iteration, "port"
 
 
-def time_cpu(workload, batch, steps, warmup):
+def time_reference(workload, batch, steps, warmup, device="cpu"):
+    """-> (baseline dict, seconds per iteration)."""
     import torch
+    on_gpu = str(device).startswith("cuda")
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    it = cpu_iteration_factory(workload, batch)
+    if not on_gpu:
+        torch.set_num_threads(cores)
+    it, kind = reference_iteration_factory(workload, batch, device)
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
     for _ in range(warmup):
         it()
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         it()
+    sync()
     dt = time.perf_counter() - t0
-    return {"value": batch * steps / dt, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d iterations of %d episodes (oracle/gim_oracle.py, torch CPU fp32, all host threads), %d warm-up" % (steps, batch, warmup)}, dt / steps
+    what = ("the reference's own GIMImgTrainer + im_train_step/au_train_step (oracle/_ref/reference.zip, unmodified)" if kind == "reference"
+            else "oracle/gim_oracle.py port of the iteration")
+    if on_gpu:
+        sample = "%d iterations of %d episodes, %d warm-up: %s on cuda, eager PyTorch/cuDNN, default flags (fp32 storage, cudnn.allow_tf32=%s, matmul tf32=%s)" % (
+            steps, batch, warmup, what, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        return {"value": batch * steps / dt, "unit": "episodes/s", "kind": kind, "sample": sample, "ms_per_step": dt / steps * 1e3,
+                "episodes_per_step": batch}, dt / steps
+    sample = "%d iterations of %d episodes, %d warm-up: %s, torch CPU fp32, all host threads" % (steps, batch, warmup, what)
+    return {"value": batch * steps / dt, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample}, dt / steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 2))
-    cb, ms = time_cpu(args.workload, args.cpu_batch, steps, warmup)
-    line = {
-        "impl": "reference", "metric": "GIM train episodes/sec (fwd+bwd G+D)", "value": cb["value"], "unit": "episodes/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][7], "episodes_per_step": args.cpu_batch, "m": M_, "n": N_, "k": K_, "device": "host CPU"},
+        return None
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cb, sec = time_reference(args.workload, args.cpu_batch, steps, warmup)
+    B = args.batch or DEFAULT_BATCH[args.workload]
+    return {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "episodes/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(args.workload, B, max(1, args.gpus)),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -182,9 +237,47 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Dist:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py --impl ours needs a CUDA device: the GIM hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events, max over ranks -> milliseconds."""
+        import torch
+        import torch.distributed as dist
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+
+def measure_workload(args, D, workload, B, want_roofline, sample_clocks):
+    """Build the trainer for one workload, capture the whole iteration as a CUDA graph, time `value` and `e2e`."""
     import torch
-    import torch.distributed as dist
     import optimalstrategiesagainstgenerativeattacks_b200 as gim
     from optimalstrategiesagainstgenerativeattacks_b200 import _cabi, ddp, ops
     from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_models as M
@@ -192,19 +285,8 @@ def run_ours(args):
     from optimalstrategiesagainstgenerativeattacks_b200.training_steps import au_train_step, im_train_step
     from optimalstrategiesagainstgenerativeattacks_b200.utils import DataParallelMock
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py --impl ours needs a CUDA device: the GIM hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _cabi.lib()                                   # fail loudly now if the extension is missing
-
-    size, ch, reg, au_lr, im_lr, map_lr, gflop_ep, desc = WORKLOADS[args.workload]
-    B = args.batch or (128 if args.workload == "O" else 32)
+    world, rank, dev = D.world, D.rank, D.dev
+    size, ch, reg, au_lr, im_lr, map_lr, gflop_ep, desc = WORKLOADS[workload]
     gim.set_precision(args.precision)
     torch.manual_seed(1)                          # train_gim_on_imgs.py:6
     au, im = M.get_au(size, ch, STYLE).to(dev), M.get_im(size, ch, STYLE).to(dev)
@@ -226,24 +308,6 @@ def run_ours(args):
         im_loss, fake, _ = im_train_step(trainer, leaked, si)
         o = au_train_step(trainer, real, fake, si)
         return im_loss, o[0]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for s in range(steps):
-            fn(s)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
 
     graphed = None
     if not args.no_graph:
@@ -271,32 +335,73 @@ def run_ours(args):
 
     for s in range(max(3, args.warmup)):
         step_resident(s)
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(D.local) if (sample_clocks and rank == 0) else None
+    if sampler:
         sampler.start()
     _cabi.launch_count(reset=True)
-    ms_total = timed(step_resident, args.steps)
+    ms_total = D.timed(step_resident, args.steps)
     launches = graphed.launches_per_replay * args.steps if graphed is not None else _cabi.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     step_e2e(0)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = D.timed(step_e2e, args.steps)
+    res = {"workload": workload, "desc": desc, "B": B, "ms_total": ms_total, "ms_e2e": ms_e2e, "launches": launches, "clocks": clocks,
+           "h2d_bytes": h2d_bytes, "graph": graphed is not None, "gflop_ep": gflop_ep,
+           "eps": B * world * args.steps / (ms_total * 1e-3), "eps_e2e": B * world * args.steps / (ms_e2e * 1e-3)}
 
-    # dominant-kernel roofline: one extra iteration with CUDA events around every tensor-core conv launch
-    ops.set_stream_parallelism(False)             # one stream: a bracketed launch must not share the GPU with the other encoder branch
-    ops.conv_profile_begin()
-    iteration(*dev_pool[0])                       # eager, so that events can bracket each launch
-    torch.cuda.synchronize()
-    prof = ops.conv_profile_end()
-    ops.set_stream_parallelism(True)
-    shapes = prof.pop("_shapes", {})
-    if rank == 0 and os.environ.get("GIM_PROFILE_SHAPES"):
-        for key, (fl, ms, cnt) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:40]:
-            print("shape %-14s n=%-6d h=%-3d w=%-3d ci=%-4d co=%-4d k=%d  x%-3d %8.3f ms %7.1f TFLOP/s" % (key + (cnt, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0)),
-                  file=sys.stderr)
+    if want_roofline:
+        # dominant-kernel roofline: one extra iteration with CUDA events around every tensor-core conv launch
+        ops.set_stream_parallelism(False)         # one stream: a bracketed launch must not share the GPU with the other encoder branch
+        ops.conv_profile_begin()
+        iteration(*dev_pool[0])                   # eager, so that events can bracket each launch
+        torch.cuda.synchronize()
+        prof = ops.conv_profile_end()
+        ops.set_stream_parallelism(True)
+        shapes = prof.pop("_shapes", {})
+        if rank == 0 and os.environ.get("GIM_PROFILE_SHAPES"):
+            for key, (fl, ms, cnt) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:48]:
+                print("shape[%s] %-14s n=%-6d h=%-3d w=%-3d ci=%-4d co=%-4d k=%d  x%-3d %8.3f ms %7.1f TFLOP/s" % ((workload,) + key + (cnt, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0)),
+                      file=sys.stderr)
+        res["prof"] = prof
+    # release this workload's memory before the next one is built
+    del graphed, trainer, au, im, dev_pool
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def block_of(res, world, steps, warmup):
+    return {"workload": res["desc"], "value": res["eps"], "unit": "episodes/s", "ms_per_step": res["ms_total"] / steps, "episodes_per_gpu_per_step": res["B"],
+            "global_batch": res["B"] * world, "steps": steps, "warmup": warmup, "cuda_graph": res["graph"],
+            "e2e": {"value": res["eps_e2e"], "unit": "episodes/s", "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": 8,
+                    "ms_per_step": res["ms_e2e"] / steps},
+            "gpu_launches": res["launches"], "algorithmic_gflop_per_episode": res["gflop_ep"],
+            "whole_step_model_tflops_per_gpu": res["gflop_ep"] * 1e-3 * res["eps"] / world}
+
+
+def run_ours(args):
+    import torch
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi
+    D = Dist()
+    world, rank = D.world, D.rank
+    _cabi.lib()                                   # fail loudly now if the extension is missing
+    warm = max(3, args.warmup)
+    B = args.batch or DEFAULT_BATCH[args.workload]
+    main = measure_workload(args, D, args.workload, B, want_roofline=True, sample_clocks=True)
+
+    secondary = None
+    if not args.no_secondary and args.workload == "O" and args.precision == "bf16":
+        secondary = {}
+        weak = measure_workload(args, D, "V", DEFAULT_BATCH["V"], want_roofline=False, sample_clocks=False)
+        secondary.update(block_of(weak, world, args.steps, warm))
+        secondary["scaling"] = "weak"
+        if 128 % world == 0:
+            strong = measure_workload(args, D, "V", 128 // world, want_roofline=False, sample_clocks=False)
+            secondary["strong_scaling_global_batch_128"] = block_of(strong, world, args.steps, warm)
+            secondary["strong_scaling_global_batch_128"]["scaling"] = "strong"
 
     if rank != 0:
-        _finish(world, dev)
-        return
+        return None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -308,56 +413,153 @@ def run_ours(args):
     # for the layer shape that takes most of its time in this workload (128->128 3x3 @32x32 over B*5 = 640 images)
     traffic, traffic_note = None, None
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_conv_shapes_r01.json")))
-        top = ncu["fwd_32x32_128_128_k3"]
-        if args.workload == "O" and B == 128:
-            traffic = top["dram_bytes_read"] + top["dram_bytes_write"]
-            traffic_note = ("per launch of the 128->128 3x3 @32x32 layer (640 images): algorithmic %.1f MB, ncu tensor-pipe active %.1f %%, "
-                            "%.0f us under ncu" % (top["algorithmic_bytes"] / 1e6, top["tensor_pipe_active_pct"], top["duration_us"]))
+        for fn in ("ncu_conv_shapes_r02.json", "ncu_conv_shapes_r01.json"):
+            path = os.path.join(ROOT, "profiles", fn)
+            if os.path.exists(path):
+                top = json.load(open(path))["fwd_32x32_128_128_k3"]
+                if args.workload == "O" and B == 128:
+                    traffic = top["dram_bytes_read"] + top["dram_bytes_write"]
+                    traffic_note = ("%s: per launch of the 128->128 3x3 @32x32 layer (640 images): algorithmic %.1f MB, ncu tensor-pipe active %.1f %%, "
+                                    "%.0f us under ncu" % (fn, top["algorithmic_bytes"] / 1e6, top["tensor_pipe_active_pct"], top["duration_us"]))
+                break
     except Exception:
         pass
+    prof = main["prof"]
     tc = prof.get("tcgen05", {"flops": 0.0, "ms": 0.0, "launches": 0})
     achieved = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
     total_conv_ms = sum(v["ms"] for v in prof.values())
-    eps_total = B * world * args.steps / (ms_total * 1e-3)
-    eps_e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    ms_step = main["ms_total"] / args.steps
     line = {
-        "metric": "GIM train episodes/sec (fwd+bwd G+D)", "value": eps_total, "unit": "episodes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": main["eps"], "unit": "episodes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": desc, "episodes_per_gpu_per_step": B, "m": M_, "n": N_, "k": K_, "style_dim": STYLE, "parallelism": "dp%d" % world, "cuda_graph": graphed is not None,
-                   "cache": "working set (activations of %d images/step) >> 126 MB L2; %d rotating input batches" % (B * 45, n_pool),
-                   "algorithmic_gflop_per_episode": gflop_ep,
-                   "executed_conv_gflop_per_episode": sum(v["flops"] for v in prof.values()) / 1e9 / B,
-                   "whole_step_model_tflops": gflop_ep * 1e-3 * eps_total / world},
-        "e2e": {"value": eps_e2e, "unit": "episodes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
-        "clocks": clocks,
+        "config": config_of(args.workload, B, world),
+        "detail": {"cuda_graph": main["graph"], "executed_conv_gflop_per_episode": sum(v["flops"] for v in prof.values()) / 1e9 / B,
+                   "whole_step_model_tflops_per_gpu": main["gflop_ep"] * 1e-3 * main["eps"] / world,
+                   "whole_step_frac_of_sustained_peak": main["gflop_ep"] * 1e-3 * main["eps"] / world / peak_tf},
+        "e2e": {"value": main["eps_e2e"], "unit": "episodes/s", "h2d_bytes_per_step": main["h2d_bytes"], "d2h_bytes_per_step": 8,
+                "ms_per_step": main["ms_e2e"] / args.steps},
+        "gpu_launches": main["launches"],
+        "clocks": main["clocks"],
         "roofline": {"bound": "tensor", "kernel": "conv_fwd_tc2_kernel / conv_fwd_tc_kernel (tcgen05 implicit GEMM: conv forward + input-gradient)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": peak_src, "launches_per_step": tc["launches"], "kernel_ms_per_step": tc["ms"],
-                     "share_of_step": tc["ms"] / (ms_total / args.steps) if ms_total else None,
+                     "share_of_step": tc["ms"] / ms_step if ms_step else None,
                      "other_conv_kernels_ms_per_step": {k: v["ms"] for k, v in prof.items() if k != "tcgen05"},
                      "all_conv_ms_per_step": total_conv_ms},
     }
-    if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
-        torch.cuda.empty_cache()
-        cb, _ = time_cpu(args.workload, args.cpu_batch, 2, 1)
-        line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
-    _finish(world, dev)
+    if secondary is not None:
+        line["secondary"] = secondary
+    if world == 1:                                        # baselines are reported on rank 0 at N=1 only
+        if not args.no_gpu_baseline:
+            try:
+                gb, _ = time_reference(args.workload, B, 5, 2, device=D.dev)
+                gb["speedup_ours_over_gpu_eager"] = main["eps"] / gb["value"] if gb["value"] else None
+                line["gpu_eager_baseline"] = gb
+            except Exception as e:                        # the baseline must never take the bench line down
+                line["gpu_eager_baseline"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+            torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            cb, _ = time_reference(args.workload, args.cpu_batch, 5, 2)
+            line["cpu_baseline"] = cb
+    return line
 
 
-def _finish(world, dev):
+def run_check(args):
+    """Data-parallel correctness instead of timing (launch under torchrun, N >= 2), fp32 parity path:
+      1. the all-reduced mean of the per-rank gradients over B/N episodes each == the gradient of the global batch of B episodes,
+         computed on every rank alone (G-step and D-step), per tensor rel <= 1e-5;
+      2. after 3 graph-replayed training iterations every rank holds bit-identical parameters (checksums all-gathered)."""
+    import torch
+    import torch.distributed as dist
+    import optimalstrategiesagainstgenerativeattacks_b200 as gim
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi, ddp
+    from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_models as M
+    from optimalstrategiesagainstgenerativeattacks_b200.cuda_graph import GraphedIteration
+    from optimalstrategiesagainstgenerativeattacks_b200.gim_img_trainer import GIMImgTrainer
+    from optimalstrategiesagainstgenerativeattacks_b200.utils import DataParallelMock
+    D = Dist()
+    world, rank, dev = D.world, D.rank, D.dev
+    if world < 2:
+        raise RuntimeError("--check needs torchrun with at least 2 ranks")
+    size, ch, reg, au_lr, im_lr, map_lr = WORKLOADS[args.workload][:6]
+    B = args.batch or 4 * world
+    lo, hi = ddp.shard_range(B, rank, world)
+    gim.set_precision("fp32")
+    _cabi.set_deterministic(True)
+    leaked, real, si = synth_batch(B, ch, size, 4321, dev)
+    z = torch.randn((B, N_, STYLE), generator=torch.Generator().manual_seed(7)).to(dev)
+    real_randn = torch.randn
+    worst = {}
+
+    def grads_of(shard):
+        torch.manual_seed(1)
+        au, im = M.get_au(size, ch, STYLE).to(dev), M.get_im(size, ch, STYLE).to(dev)
+        tr = GIMImgTrainer(tempfile.mkdtemp(prefix="gim_check_"), M_, N_, K_, au, im, au_lr, im_lr, map_lr, reg_param=reg)
+        sl = slice(lo, hi) if shard else slice(0, B)
+        torch.randn = lambda *a, **k: z[sl].clone()
+        try:
+            loss, fake, _ = tr.impersonator_forward(leaked[sl], si[sl])
+        finally:
+            torch.randn = real_randn
+        loss.mean().backward()
+        g_im = [p.grad.clone() for p in im.parameters() if p.grad is not None]
+        out = tr.authenticator_forward(fake.detach(), real[sl].clone(), si[sl].clone())
+        au.zero_grad()
+        out[0].mean().backward()
+        g_au = [p.grad.clone() for p in au.parameters() if p.grad is not None]
+        return g_im, g_au
+
+    full = grads_of(False)
+    mine = grads_of(True)
+    for name, gs_full, gs_mine in (("impersonator", full[0], mine[0]), ("authenticator", full[1], mine[1])):
+        flat = torch.cat([g.flatten() for g in gs_mine])
+        dist.all_reduce(flat)
+        flat /= world
+        off, w = 0, 0.0
+        scale = max(float(g.norm()) for g in gs_full)
+        for g in gs_full:
+            d = float((flat[off:off + g.numel()] - g.flatten()).norm()) / max(float(g.norm()), 1e-6 * scale)
+            off += g.numel()
+            w = max(w, d)
+        worst[name] = w
+    # replicas stay identical through the path bench.py times (graph + NCCL all-reduce inside it)
+    gim.set_precision(args.precision)
+    _cabi.set_deterministic(False)
+    torch.manual_seed(1)
+    au, im = M.get_au(size, ch, STYLE).to(dev), M.get_im(size, ch, STYLE).to(dev)
+    tr = DataParallelMock(GIMImgTrainer(tempfile.mkdtemp(prefix="gim_check_"), M_, N_, K_, au, im, 1e-3, 1e-3, 1e-4, reg_param=reg))
+    ddp.attach(tr.module.authenticator_opt)
+    ddp.attach(tr.module.impersonator_opt)
+    torch.manual_seed(1000 + rank)
+    g = GraphedIteration(tr, leaked[lo:hi], real[lo:hi], si[lo:hi], warmup=3)
+    for _ in range(3):
+        g()
+    torch.cuda.synchronize()
+    sums = torch.tensor([float(sum(p.double().sum() for p in net.parameters())) for net in (au, im)], dtype=torch.float64, device=dev)
+    gathered = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(gathered, sums)
+    identical = all(torch.equal(gathered[0], t) for t in gathered)
+    ok = identical and all(v <= 1e-5 for v in worst.values())
+    if rank != 0:
+        return None
+    return {"check": "ok" if ok else "FAILED", "n_gpus": world, "global_batch": B, "workload": WORKLOADS[args.workload][7],
+            "sharded_vs_global_batch_gradient_max_rel_err": worst, "tolerance": 1e-5,
+            "replica_parameter_checksums_identical_after_3_graph_steps": identical,
+            "checksums": [t.tolist() for t in gathered]}
+
+
+def _finish(world):
     """Leave a multi-rank run without tearing NCCL down: destroying a communicator that CUDA graphs still reference can block
     forever, and nothing after the JSON line needs it.  Ranks meet at a last barrier, flush, and exit."""
     if world <= 1:
         return
     import torch
     import torch.distributed as dist
-    torch.cuda.synchronize(dev)
-    dist.barrier()
-    torch.cuda.synchronize(dev)
+    if dist.is_initialized():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(0)
@@ -365,10 +567,17 @@ def _finish(world, dev):
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    real_stdout = sys.stdout
+    with contextlib.redirect_stdout(sys.stderr):      # trainers print parameter counts etc.: stdout carries the JSON line only
+        if args.impl == "reference":
+            line = run_reference(args)
+        elif args.check:
+            line = run_check(args)
+        else:
+            line = run_ours(args)
+    if line is not None:
+        print(json.dumps(line), file=real_stdout, flush=True)
+    _finish(int(os.environ.get("WORLD_SIZE", "1")) if args.impl != "reference" else 1)
 
 
 if __name__ == "__main__":

@@ -40,6 +40,10 @@ int         gim_conv2d_tc_supported(int n, int h, int w, int cin, int cout, int 
 int         gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype);
 /* counts kernel launches issued through this library since the last reset (bench.py `gpu_launches`) */
 long long   gim_launch_count(int reset);
+/* Parity mode: when on, every reduction output (weight gradients, column sums, split-K GEMMs, scalar dots) is owned by ONE CTA, so
+ * results do not depend on the arrival order of fp32 atomics (slower; for tests).  Returns the previous setting.  The reference has no
+ * equivalent knob: torch's own `torch.use_deterministic_algorithms` plays this role for its cuDNN path. */
+int         gim_set_deterministic(int on);
 
 /* ---- convolution: nn.Conv2d forward / input-grad / weight-grad (model_blocks.py:497-514, 753-773, 795-865) ---- */
 /* y[n,h,w,co] = bias[co] + sum_{r,s,ci} x[n,h+r-p,w+s-p,ci] * w[r*k+s][co][ci];  x,w: dtype; y: out_dtype (fp32 accumulate

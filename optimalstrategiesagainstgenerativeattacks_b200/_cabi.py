@@ -80,7 +80,7 @@ PROTOTYPES = {
     "gim_adam_multi": "pilppfff" + "fp",
     "gim_zero_grads_multi": "pilp",
 }
-OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_launch_count")
+OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_launch_count", "gim_set_deterministic")
 
 
 
@@ -120,6 +120,8 @@ def lib():
         L.gim_conv2d_wgrad_tc_supported.restype = _I
         L.gim_launch_count.argtypes = [_I]
         L.gim_launch_count.restype = _L
+        L.gim_set_deterministic.argtypes = [_I]
+        L.gim_set_deterministic.restype = _I
         _lib = L
     return _lib
 
@@ -160,6 +162,11 @@ def call(name, *args):
 
 def launch_count(reset=False):
     return int(lib().gim_launch_count(1 if reset else 0))
+
+
+def set_deterministic(flag):
+    """Parity mode (gim_set_deterministic): no multi-CTA fp32 atomics into one output.  -> previous setting."""
+    return bool(lib().gim_set_deterministic(1 if flag else 0))
 
 
 def conv_tc_supported(n, h, w, cin, cout, k, dtype):

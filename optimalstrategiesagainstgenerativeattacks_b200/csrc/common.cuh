@@ -10,6 +10,8 @@ namespace gim {
 
 extern thread_local char g_err[512];
 extern long long g_launches;
+extern int g_deterministic;      // gim_set_deterministic(): every reduction output is owned by ONE CTA (no split-K / multi-CTA atomics)
+inline bool deterministic() { return g_deterministic != 0; }
 
 inline int fail(int code, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s", what);

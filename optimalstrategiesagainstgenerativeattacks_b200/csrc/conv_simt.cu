@@ -290,6 +290,7 @@ static int conv_wgrad_simt(const void* x, const void* gy, float* gw, int n, int 
     if (want > max_split) want = max_split;
     if (want < 1) want = 1;
     if (want > 65535) want = 65535;
+    if (deterministic()) want = 1;
     long long per = (npix + want - 1) / want;
     per = (per + BK - 1) / BK * BK;
     int splits = (int)((npix + per - 1) / per);
@@ -384,7 +385,7 @@ int gim_cast_colsum(const float* x, void* y_bf16, float* sums, long long rows, i
     const int rlanes = 256 / (c / 8);
     long long want = (rows + rlanes * 4 - 1) / (rlanes * 4);                  // >= 4 row steps per CTA
     if (want > 2LL * num_sms()) want = 2LL * num_sms();
-    if (want < 1) want = 1;
+    if (want < 1 || deterministic()) want = 1;
     cast_colsum_kernel<<<(unsigned)want, 256, 0, (cudaStream_t)s>>>(x, (bf16*)y_bf16, sums, rows, c);
     return check_launch("cast_colsum");
 }
@@ -397,7 +398,7 @@ static int colsum_launch(const void* x, float* out, long long rows, int c, int d
     long long want = ((long long)num_sms() * 4 + cchunks - 1) / cchunks;
     long long maxc = (rows + 63) / 64;
     if (want > maxc) want = maxc;
-    if (want < 1) want = 1;
+    if (want < 1 || deterministic()) want = 1;
     long long per = (rows + want - 1) / want;
     dim3 grid((unsigned)((rows + per - 1) / per), cchunks), block(32, 8);
     GIM_DISPATCH_DTYPE(dtype, (colsum_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)x, out, rows, c, per)));

@@ -1240,6 +1240,7 @@ static int conv_wgrad_tc3(const void* x, const void* gy, float* gw, int n, int h
     if (want > max_split) want = max_split;
     if (want < 1) want = 1;
     if (want > 65535) want = 65535;
+    if (deterministic()) want = 1;
     p.tiles_per_split = (int)((total + want - 1) / want);
     const int splits = (int)((total + p.tiles_per_split - 1) / p.tiles_per_split);
     CUtensorMap map_gy, map_x;
@@ -1298,6 +1299,7 @@ int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd
     if (want > max_split) want = max_split;
     if (want < 1) want = 1;
     if (want > 65535) want = 65535;
+    if (deterministic()) want = 1;
     p.tiles_per_split = (int)((total + want - 1) / want);
     const int splits = (int)((total + p.tiles_per_split - 1) / p.tiles_per_split);
     CUtensorMap map_gy, map_x;

@@ -5,6 +5,7 @@ namespace gim {
 
 thread_local char g_err[512] = "";
 long long g_launches = 0;
+int g_deterministic = 0;
 
 template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
 
@@ -1046,6 +1047,11 @@ long long gim_launch_count(int reset) {
     if (reset) g_launches = 0;
     return v;
 }
+int gim_set_deterministic(int on) {
+    int old = g_deterministic;
+    g_deterministic = on ? 1 : 0;
+    return old;
+}
 
 int gim_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, gim_stream_t s) {
     GIM_DISPATCH_DTYPE(dtype, return (launch_map<T, 1>(x, nullptr, nullptr, y, n, (cudaStream_t)s, LreluF{slope}, "lrelu_fwd")));
@@ -1075,6 +1081,7 @@ int gim_dot(const void* x, const void* y, float* out, long long n, int dtype, gi
     if (n <= 0) return GIM_OK;
     int grid = ew_grid(n, 256, 16);
     if (grid > 2 * num_sms()) grid = 2 * num_sms();
+    if (deterministic()) grid = 1;
     GIM_DISPATCH_DTYPE(dtype, (dot_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)y, out, n)));
     return check_launch("dot");
 }
@@ -1211,6 +1218,7 @@ int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_p
         if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
         int grid = per_sm * num_sms();
         if (grid > bands) grid = bands;
+        if (deterministic()) { grid = 1; replicas = 1; }
         if (c == 1) first_block_wgrad_mma_kernel<1><<<grid, 256, smem_mma, st>>>(x, (const bf16*)gt_bf16, gy_pooled, scratch, replicas, n, h, wd, cout, slope);
         else first_block_wgrad_mma_kernel<3><<<grid, 256, smem_mma, st>>>(x, (const bf16*)gt_bf16, gy_pooled, scratch, replicas, n, h, wd, cout, slope);
         int rc = check_launch("first_block_wgrad_mma");
@@ -1231,6 +1239,7 @@ int gim_first_block_wgrad(const float* x, const void* gt_bf16, const float* gy_p
     const int per_sm = smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1);
     int grid = per_sm * num_sms();
     if (grid > bands) grid = bands;
+    if (deterministic()) grid = 1;
     if (c == 1) first_block_wgrad_kernel<1><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
     else first_block_wgrad_kernel<3><<<grid, 256, smem, st>>>(x, (const bf16*)gt_bf16, gy_pooled, gw_r1, gw_l1, n, h, wd, cout, slope);
     return check_launch("first_block_wgrad");

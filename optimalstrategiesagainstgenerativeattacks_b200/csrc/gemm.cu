@@ -323,7 +323,7 @@ int gim_gemm_strided_bf16(const void* A, int dtA, long long sAb, long long sAm, 
     const int m_tiles = (m + TBM - 1) / TBM, n_tiles = (n + TBN - 1) / TBN;
     const long long ctas = (long long)m_tiles * n_tiles * batch;
     int splits = 1;
-    if (dtC == GIM_F32 && beta == 0.f && k >= 8 * TBK && ctas < num_sms()) {       // few output tiles, long K: split K over the chip
+    if (dtC == GIM_F32 && beta == 0.f && k >= 8 * TBK && ctas < num_sms() && !deterministic()) {       // few output tiles, long K: split K over the chip
         long long want = (2LL * num_sms() + ctas - 1) / ctas, most = k / (4 * TBK);
         splits = (int)(want < most ? want : most);
         if (splits < 1) splits = 1;

@@ -370,7 +370,7 @@ int gim_sn_forward(const float* weight_orig, float* u, float* v, int power_iter,
         int col_blocks = (J + 31) / 32;
         int splits = (2 * num_sms() + col_blocks - 1) / col_blocks;          // enough CTAs to cover the chip ~2x
         if (splits > (cout + 31) / 32) splits = (cout + 31) / 32;
-        if (splits < 1) splits = 1;
+        if (splits < 1 || deterministic()) splits = 1;
         int rows_per_split = (cout + splits - 1) / splits;
         sn_wtu_kernel<<<dim3(col_blocks, (cout + rows_per_split - 1) / rows_per_split), dim3(32, 8), 0, st>>>(weight_orig, u, t, cout, J, rows_per_split);
         if ((rc = check_launch("sn_wtu")) != GIM_OK) return rc;
@@ -393,7 +393,7 @@ int gim_sn_backward(const float* g_w_sn, const float* weight_orig, const float* 
     int taps = ksize * ksize;
     long long total = (long long)taps * cout * cin;
     if (cudaMemsetAsync(scratch, 0, sizeof(float), st) != cudaSuccess) return fail(GIM_E_CUDA, "sn_backward memset");
-    int grid = ew_grid(total, 256, 8);
+    int grid = deterministic() ? 1 : ew_grid(total, 256, 8);
     sn_bwd_dot_kernel<<<grid, 256, 0, st>>>(g_w_sn, weight_orig, scratch, cout, cin, taps);
     int rc = check_launch("sn_bwd_dot");
     if (rc != GIM_OK) return rc;

@@ -253,6 +253,7 @@ int gim_rows_sqsum(const void* x, float* out, int b, long long l, int dtype, gim
     if (l <= 0) return GIM_OK;
     int gx = (int)((l + 256 * 16 - 1) / (256 * 16));
     if (gx > 64) gx = 64;
+    if (deterministic()) gx = 1;
     dim3 grid(gx, b);
     GIM_DISPATCH_DTYPE(dtype, (rows_sqsum_kernel<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)x, out, l)));
     return check_launch("rows_sqsum");

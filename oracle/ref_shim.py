@@ -9,11 +9,23 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("GIM_REFERENCE_ROOT", "/root/reference")
+ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference.zip")
 
 
-def install(reference_root=REFERENCE_ROOT):
-    if not os.path.isdir(reference_root):
-        raise RuntimeError("reference tree not present at %s" % reference_root)
+def available():
+    """Where the unmodified reference can be imported from: its source tree (build container) or the archive packed by
+    oracle/build_ref.py (GPU box), else None."""
+    if os.path.isdir(REFERENCE_ROOT):
+        return REFERENCE_ROOT
+    if os.path.exists(ARCHIVE):
+        return ARCHIVE
+    return None
+
+
+def install(reference_root=None):
+    reference_root = reference_root or available()
+    if reference_root is None or not os.path.exists(reference_root):
+        raise RuntimeError("reference not present (neither %s nor %s)" % (REFERENCE_ROOT, ARCHIVE))
     if "colorama" not in sys.modules:
         c = types.ModuleType("colorama")
 
