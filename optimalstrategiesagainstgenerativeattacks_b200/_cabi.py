@@ -146,7 +146,13 @@ def ptr(t):
         raise RuntimeError("libgim_b200: tensor is on %s; the GIM hot path runs on CUDA only (no CPU fallback)" % t.device)
     if not t.is_contiguous():
         raise RuntimeError("libgim_b200: tensor must be contiguous")
+    if t.device.index != _current_device():
+        raise RuntimeError("libgim_b200: tensor lives on %s but the current CUDA device is %d -- kernels launch on the current device's "
+                           "stream; call torch.cuda.set_device() (utils.get_device does) or run one process per GPU" % (t.device, _current_device()))
     return t.data_ptr()
+
+
+_current_device = torch.cuda.current_device
 
 
 def stream():

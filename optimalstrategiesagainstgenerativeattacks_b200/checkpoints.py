@@ -20,7 +20,10 @@ def _to_host(obj):
     if torch.is_tensor(obj):
         return obj.detach().to("cpu", copy=True)
     if isinstance(obj, dict):
-        return type(obj)((k, _to_host(v)) for k, v in obj.items())
+        out = type(obj)((k, _to_host(v)) for k, v in obj.items())
+        if hasattr(obj, "_metadata"):                  # nn.Module.state_dict() versions (e.g. spectral_norm's weight.version)
+            out._metadata = obj._metadata
+        return out
     if isinstance(obj, (list, tuple)):
         return type(obj)(_to_host(v) for v in obj)
     return obj
@@ -32,6 +35,7 @@ class CheckpointIO:
         self.module_dict = dict(named_objects)          # name -> anything with state_dict() / load_state_dict()
         self.async_save = async_save
         self._writer = None
+        self._writer_error = None
         os.makedirs(checkpoint_dir, exist_ok=True)
 
     def register_modules(self, **named_objects):
@@ -41,15 +45,24 @@ class CheckpointIO:
 
     # -- writing -------------------------------------------------------------------------------------------------
     def _write(self, payload, path):
-        tmp = path + ".tmp"
+        tmp = "%s.tmp.%d" % (path, os.getpid())        # unique per process: two writers never share a temporary file
         torch.save(payload, tmp)
         os.replace(tmp, path)
 
+    def _write_bg(self, payload, path):
+        try:
+            self._write(payload, path)
+        except BaseException as e:                     # surfaced by wait() on the training thread
+            self._writer_error = e
+
     def wait(self):
-        """Block until a background save (if any) has reached the disk."""
+        """Block until a background save (if any) has reached the disk; re-raises the writer's exception if it failed."""
         writer, self._writer = self._writer, None
         if writer is not None:
             writer.join()
+        err, self._writer_error = getattr(self, "_writer_error", None), None
+        if err is not None:
+            raise RuntimeError("background checkpoint write failed: %r" % (err,)) from err
 
     def save(self, global_step, last_epoch, filename):
         self.wait()
@@ -58,7 +71,7 @@ class CheckpointIO:
             payload[name] = _to_host(obj.state_dict())
         path = os.path.join(self.checkpoint_dir, filename)
         if self.async_save:
-            self._writer = threading.Thread(target=self._write, args=(payload, path), daemon=False)
+            self._writer = threading.Thread(target=self._write_bg, args=(payload, path), daemon=False)
             self._writer.start()
         else:
             self._write(payload, path)

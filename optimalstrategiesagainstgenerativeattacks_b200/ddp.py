@@ -36,18 +36,43 @@ class FlatGradBucket:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
+    def covers(self, params):
+        """True if exactly the parameters re-homed here carry a gradient (a parameter whose first gradient appears later would
+        otherwise be stepped with an un-reduced gradient and the replicas would drift apart silently)."""
+        with_grad = [p for p in params if p.grad is not None]
+        return len(with_grad) == len(self.params) and all(a is b for a, b in zip(with_grad, self.params))
+
+
+def broadcast_module_state(module, src=0, group=None):
+    """Every rank adopts rank `src`'s parameters and buffers (spectral-norm u/v included): replica consistency no longer depends on
+    the caller seeding every process identically before building the networks."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+
 
 def attach(optimizer, group=None):
     """Make `optimizer.step()` all-reduce its gradients first and apply the mean (grad_scale = 1/world)."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     optimizer.grad_scale = 1.0 / world
+    if world > 1:                                    # replicas start from rank 0's parameters
+        with torch.no_grad():
+            for g in optimizer.param_groups:
+                for p in g["params"]:
+                    dist.broadcast(p.data, src=0, group=group)
     inner_step = optimizer.step
     state = {"bucket": None}
 
     def step(closure=None):
         if world > 1:
+            params = [p for g in optimizer.param_groups for p in g["params"]]
             if state["bucket"] is None:
-                state["bucket"] = FlatGradBucket([p for g in optimizer.param_groups for p in g["params"]])
+                state["bucket"] = FlatGradBucket(params)
+            elif not torch.cuda.is_current_stream_capturing() and not state["bucket"].covers(params):
+                raise RuntimeError("ddp: the set of parameters that receive gradients changed after the first optimizer step "
+                                   "(flat gradient bucket is frozen) -- re-attach the optimizer")
             state["bucket"].all_reduce(group)
         return inner_step(closure)
 

@@ -151,8 +151,8 @@ def train_epoch(device, logger, epoch, trainer, train_ds, val_ds, train_batch_si
 
         if fake_sample is not None and global_step % tb_log_enc_every == 0:
             _log_encodings(trainer, logger, real_sample, si_sample, fake_sample, global_step)
-        if global_step % save_every == 0 and (not dist.is_initialized() or dist.get_rank() == 0):
-            trainer.module.save(epoch=epoch)
+        if global_step % save_every == 0:
+            _save_rank0(trainer, epoch)
         if global_step % eval_every == 0 and val_ds is not None:
             eval_step(device=device, trainer=trainer, ds=val_ds, logger=logger, batch_size=val_batch_size)
 
@@ -172,6 +172,7 @@ def train_gim_imgs(device_name, device_ids, outdir, train_ds, val_ds, authentica
         trainer.resume_from_ckpt(ckpt_path=resume_from_ckpt)
         trainer.to(device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        ddp.broadcast_module_state(trainer)            # replicas start from rank 0's parameters and spectral-norm u/v
         ddp.attach(trainer.authenticator_opt)
         ddp.attach(trainer.impersonator_opt)
     trainer = DataParallelMock(trainer)
@@ -183,7 +184,16 @@ def train_gim_imgs(device_name, device_ids, outdir, train_ds, val_ds, authentica
                         train_eval_indices=train_eval_indices, val_eval_indices=val_eval_indices, n_au_steps=n_au_steps, dbg=dbg,
                         use_cuda_graph=use_cuda_graph)
         except KeyboardInterrupt:
-            trainer.module.save(epoch=ep)
+            _save_rank0(trainer, ep)
             raise
-    trainer.module.save(epoch=n_epochs - 1)
+    _save_rank0(trainer, n_epochs - 1)
     return trainer, logger
+
+
+def _save_rank0(trainer, epoch):
+    """Checkpoints are written by rank 0 only (replicas are identical); the other ranks wait until the file is complete."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if not multi or dist.get_rank() == 0:
+        trainer.module.save(epoch=epoch)
+    if multi:
+        dist.barrier()

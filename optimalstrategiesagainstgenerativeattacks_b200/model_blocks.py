@@ -80,6 +80,12 @@ class MLP(nn.Module):
         return x
 
 
+def _sn_state_dict_hook(module, state_dict, prefix, local_metadata):
+    """torch.nn.utils.spectral_norm's SpectralNormStateDictHook: the entry its load pre-hook reads to tell a current-format
+    (weight_orig / weight_u / weight_v) state dict from a legacy one, so files written here load in the reference's modules."""
+    local_metadata.setdefault('spectral_norm', {})['weight.version'] = 1
+
+
 class SNConv2d(nn.Module):
     """nn.utils.spectral_norm(nn.Conv2d(cin, cout, k, padding=(k-1)//2)) -- parameters `bias`, `weight_orig`, buffers
     `weight_u`, `weight_v`, initialised with the same RNG draws as torch (Conv2d.reset_parameters, then u, v)."""
@@ -98,6 +104,7 @@ class SNConv2d(nn.Module):
         self.register_buffer('weight_u', u)
         self.register_buffer('weight_v', v)
         self._prepared = None
+        self._register_state_dict_hook(_sn_state_dict_hook)
 
     def effective_weight(self):
         """Packed fp32 [k*k, cout, cin] weight W/sigma; runs the power iteration when self.training (unless sn_prepare_module already

@@ -44,7 +44,11 @@ def get_device(device_type, device_ids, verbose=True):
     name = "cuda:{}".format(min(device_ids)) if device_ids else "cuda"
     if verbose:
         print('Using device {}'.format(name))
-    return torch.device(name)
+    device = torch.device(name)
+    # one process drives ONE GPU: every kernel of libgim_b200 is launched on the current device's current stream, so the device the
+    # tensors live on must be the current one (the reference's nn.DataParallel over device_ids is replaced by one process per GPU)
+    torch.cuda.set_device(device)
+    return device
 
 
 def num_parameters(parameter_list):

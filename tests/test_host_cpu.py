@@ -130,3 +130,60 @@ def test_cat_params_direct_accumulation_and_merged_rows():
     g = torch.randn(1, 5, 4)
     ga, gb = torch.autograd.grad((merged * g).sum(), parts)
     assert torch.equal(ga, g[:, :2]) and torch.equal(gb, g[:, 2:])
+
+
+def test_checkpoint_keeps_spectral_norm_metadata_and_cross_loads(tmp_path):
+    """State dicts keep nn.Module's `_metadata` through the host snapshot, SNConv2d publishes spectral_norm's `weight.version`, and
+    its state dict loads (strict) into torch.nn.utils.spectral_norm(nn.Conv2d) -- the module the reference builds
+    (models/model_blocks.py:492-495) -- with the same effective weight state."""
+    from optimalstrategiesagainstgenerativeattacks_b200 import model_blocks as mb
+    from optimalstrategiesagainstgenerativeattacks_b200.checkpoints import CheckpointIO, _to_host
+    torch.manual_seed(3)
+    blk = torch.nn.Sequential(mb.SNConv2d(4, 6, 3, padding=1))
+    sd = blk.state_dict()
+    assert sd._metadata["0"]["spectral_norm"] == {"weight.version": 1}
+    host = _to_host(sd)
+    assert host._metadata["0"]["spectral_norm"] == {"weight.version": 1}
+    io = CheckpointIO(str(tmp_path), net=blk)
+    path = io.save(global_step=0, last_epoch=0, filename="m.pt")
+    stored = torch.load(path, map_location="cpu", weights_only=False)
+    ref = torch.nn.Sequential(torch.nn.utils.spectral_norm(torch.nn.Conv2d(4, 6, 3, padding=1)))
+    ref.load_state_dict(stored["net"], strict=True)
+    for k in ("0.weight_orig", "0.weight_u", "0.weight_v", "0.bias"):
+        assert torch.equal(ref.state_dict()[k], sd[k]), k
+    # and the other way round: a state dict written by the reference's module loads here
+    blk2 = torch.nn.Sequential(mb.SNConv2d(4, 6, 3, padding=1))
+    blk2.load_state_dict(ref.state_dict(), strict=True)
+    assert torch.equal(blk2[0].weight_orig, blk[0].weight_orig)
+
+
+def test_checkpoint_background_writer_errors_surface(tmp_path):
+    from optimalstrategiesagainstgenerativeattacks_b200.checkpoints import CheckpointIO
+
+    class Unpicklable:
+        def state_dict(self):
+            return {"f": lambda: None}                   # torch.save cannot pickle a lambda
+
+        def load_state_dict(self, d):
+            pass
+    io = CheckpointIO(str(tmp_path), async_save=True, bad=Unpicklable())
+    io.save(global_step=0, last_epoch=0, filename="m.pt")
+    import pytest
+    with pytest.raises(RuntimeError, match="background checkpoint write failed"):
+        io.wait()
+    io.wait()                                            # the error is reported once
+
+
+def test_reference_archive_is_importable_when_built():
+    """oracle/build_ref.py packs the unmodified reference into oracle/_ref/reference.zip (git-ignored); zipimport finds the packages."""
+    import os
+    import zipfile
+    from oracle import build_ref
+    path = build_ref.build()
+    if path is None:
+        import pytest
+        pytest.skip("neither /root/reference nor a prebuilt archive is present")
+    names = zipfile.ZipFile(path).namelist()
+    assert "training/gim_img_trainer.py" in names and "models/gim_img_models.py" in names
+    assert not [n for n in names if not n.endswith(".py")]
+    assert os.path.getsize(path) < 1 << 20
