@@ -77,6 +77,46 @@ def grad_summary(module):
     return np.asarray(rows, dtype=np.float64)
 
 
+N_SAMPLES = 128          # gradient elements stored per parameter tensor
+FULL_LIMIT = 20000       # parameters up to this size may be stored in full (see grad_full)
+
+
+def sample_index(numel, j):
+    """The element positions stored for the j-th parameter tensor (shared with tests/conftest.py: `grad_sample_index`)."""
+    if numel <= N_SAMPLES:
+        return np.arange(numel)
+    return np.sort(np.random.RandomState(7919 + j).choice(numel, N_SAMPLES, replace=False))
+
+
+def grad_samples(module):
+    """[n_params, N_SAMPLES] float64: actual gradient ELEMENTS at seeded positions of every parameter (NaN rows: no gradient; short
+    tensors are NaN-padded).  Unlike (sum, norm) summaries these see a permuted / transposed gradient."""
+    rows = np.full((len(list(module.parameters())), N_SAMPLES), np.nan)
+    for j, (_, prm) in enumerate(module.named_parameters()):
+        if prm.grad is None:
+            continue
+        g = prm.grad.detach().double().reshape(-1).numpy()
+        idx = sample_index(g.size, j)
+        rows[j, :idx.size] = g[idx]
+    return rows
+
+
+def grad_full(module, prefix, count=10):
+    """{prefix + name: float32 gradient} for `count` whole tensors spread over the sub-networks: the largest that fit FULL_LIMIT."""
+    named = [(n, p) for n, p in module.named_parameters() if p.grad is not None and 256 <= p.numel() <= FULL_LIMIT]
+    by_top = {}
+    for n, p in named:
+        by_top.setdefault(n.split(".")[0], []).append((n, p))
+    picked, tops = [], sorted(by_top)
+    for lst in by_top.values():
+        lst.sort(key=lambda np_: -np_[1].numel())
+    while len(picked) < count and any(by_top.values()):
+        for t in tops:
+            if by_top[t] and len(picked) < count:
+                picked.append(by_top[t].pop(0))
+    return {prefix + n: p.grad.detach().float().numpy() for n, p in picked}
+
+
 def param_summary(module):
     return np.asarray([[v.double().sum().item(), v.double().norm().item()] for v in module.state_dict().values()],
                       dtype=np.float64)
@@ -96,7 +136,8 @@ def case_au(size, ch, sd_dim, b, n, k, seed, with_grads=True):
     if with_grads:
         loss = torch.nn.functional.binary_cross_entropy_with_logits(out, torch.ones_like(out), reduction="none").mean()
         loss.backward()
-        res.update(loss=npy(loss), grads=grad_summary(au), g_test=npy(test.grad), g_si=npy(si.grad),
+        res.update(grad_full(au, "gfull."))
+        res.update(loss=npy(loss), grads=grad_summary(au), gsamp=grad_samples(au), g_test=npy(test.grad), g_si=npy(si.grad),
                    g_mlp_last=npy(au.dis.mlp.model[4].weight.grad),
                    u_after=npy(au.src_encoder.down_blocks[0].conv_r1.weight_u),
                    v_after=npy(au.src_encoder.down_blocks[0].conv_r1.weight_v))
@@ -118,6 +159,8 @@ def case_im(size, ch, sd_dim, b, m, n, seed, with_grads=True):
         probe = seeded(tuple(fake.shape), seed + 4)
         (fake * probe).sum().backward()
         res["grads"] = grad_summary(im)
+        res["gsamp"] = grad_samples(im)
+        res.update(grad_full(im, "gfull."))
         res["g_noise_last"] = npy(im.env_noise_mapper.model[6].weight.grad)
     return res
 
@@ -148,7 +191,42 @@ def case_img_steps(size, ch, sd_dim, b, m, n, k, reg, iters, seed, lrs=(1e-3, 1e
     return res
 
 
-def case_gauss(d, b, m, n, k, iters, seed, reg=0.0):
+def case_step_grads(size, ch, sd_dim, b, m, n, k, reg, seed, lrs=(1e-4, 1e-4, 1e-6)):
+    """ONE full training iteration (G-step, D-step; R1 when reg > 0) of the reference trainer at full network width, batch b:
+    losses, the generated images and the gradients both optimizers consumed (element samples of every tensor + a dozen whole tensors)."""
+    au = load(ref_img.get_au(size, ch, sd_dim), seed)
+    im = load(ref_img.get_im(size, ch, sd_dim), seed + 10)
+    tr = DataParallelMock(GIMImgTrainer("/tmp/gim_golden_out", m, n, k, au, im, lrs[0], lrs[1], lrs[2], reg_param=reg))
+    leaked = seeded((b, m, ch, size, size), seed + 1, 0.5, 1.0)
+    real = seeded((b, n, ch, size, size), seed + 2, 0.5, 1.0)
+    si = seeded((b, k, ch, size, size), seed + 3, 0.5, 1.0)
+    z = seeded((b, n, sd_dim), seed + 4)
+    tr.module.do_global_step()
+    tr.module.update_learning_rate()
+    with inject_randn([z]):
+        im_loss, fake, au_out = ref_img_loop.im_train_step(tr, leaked, si)
+    res = {"im_loss": npy(im_loss), "fake": npy(fake).astype(np.float32), "g_au_out": npy(au_out),
+           "im_grads": grad_summary(im), "im_gsamp": grad_samples(im)}
+    res.update(grad_full(im, "im_gfull."))
+    o = ref_img_loop.au_train_step(tr, real, fake, si)
+    res.update(au_loss=npy(o[0]), loss_real=npy(o[1]), loss_fake=npy(o[2]), reg=npy(o[3]), out_real=npy(o[4]), out_fake=npy(o[5]),
+               au_grads=grad_summary(au), au_gsamp=grad_samples(au))
+    res.update(grad_full(au, "au_gfull."))
+    return res
+
+
+def state_samples(module):
+    """[n_entries, N_SAMPLES] float64 element samples of every state-dict tensor (same positions rule as grad_samples)."""
+    vals = list(module.state_dict().values())
+    rows = np.full((len(vals), N_SAMPLES), np.nan)
+    for j, v in enumerate(vals):
+        a = v.detach().double().reshape(-1).numpy()
+        idx = sample_index(a.size, j)
+        rows[j, :idx.size] = a[idx]
+    return rows
+
+
+def case_gauss(d, b, m, n, k, iters, seed, reg=0.0, compact=False):
     au = load(ref_gauss.get_au(d), seed)
     im = load(ref_gauss.get_im(d), seed + 10)
     real = seeded((b, n, d), seed + 1)
@@ -159,7 +237,7 @@ def case_gauss(d, b, m, n, k, iters, seed, reg=0.0):
     real_g = real.clone().requires_grad_()
     out = au(real_g, si)
     out.sum().backward()
-    res.update(au_out=npy(out), au_g_real=npy(real_g.grad), au_grads=grad_summary(au))
+    res.update(au_out=npy(out), au_g_real=npy(real_g.grad), au_grads=grad_summary(au), au_gsamp=grad_samples(au))
     au.zero_grad()
     with inject_randn([z]):
         fake = im(leaked, n, True)
@@ -179,6 +257,10 @@ def case_gauss(d, b, m, n, k, iters, seed, reg=0.0):
         rec["au_loss"].append(o[0].item())
         rec["reg"].append(o[3].item())
     res.update({key: np.asarray(v) for key, v in rec.items()})
+    if compact:          # wide models: element samples instead of whole tensors
+        res["au_final_samp"], res["im_final_samp"] = state_samples(au), state_samples(im)
+        res["au_g_real"], res["fake"] = res["au_g_real"].astype(np.float32), res["fake"].astype(np.float32)
+        return res
     for key, v in au.state_dict().items():
         res["au_final." + key] = npy(v)
     for key, v in im.state_dict().items():
@@ -230,7 +312,7 @@ def main():
             "im_params": [k for k, _ in im.named_parameters()],
             "im_groups": optimizer_groups(im),
         }
-    for d in (10,):
+    for d in (10, 1000):
         schemas["gauss%d" % d] = {"au": schema_of(ref_gauss.get_au(d)), "im": schema_of(ref_gauss.get_im(d))}
     # init parity: the product must reproduce the reference's own initialisation under the same seed
     torch.manual_seed(1)
@@ -250,6 +332,9 @@ def main():
         "im_O": lambda: case_im(32, 1, 512, 1, 1, 1, 61, with_grads=False),
         "au_V": lambda: case_au(64, 3, 512, 1, 1, 1, 71, with_grads=False),
         "im_V": lambda: case_im(64, 3, 512, 1, 1, 1, 81, with_grads=False),
+        "step_O": lambda: case_step_grads(32, 1, 512, 2, 2, 2, 2, 0.0, 151),
+        "step_V": lambda: case_step_grads(64, 3, 512, 2, 1, 2, 1, 10.0, 171),
+        "gauss_d1000": lambda: case_gauss(1000, 8, 1, 5, 10, 2, 191, compact=True),
         "gauss_d10": lambda: case_gauss(10, 16, 1, 5, 10, 3, 91),
         "gauss_d10_r1": lambda: case_gauss(10, 16, 2, 3, 4, 2, 95, reg=1.0),
         "sn_steps": lambda: case_sn_steps(5),

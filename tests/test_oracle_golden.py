@@ -7,7 +7,7 @@ in tests/test_parity_gpu.py, where it sets the tolerance for ill-conditioned qua
 import numpy as np
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import load_golden, rel_err, sample_errs, sample_rows
 from oracle import gim_oracle as O
 from oracle.fill import fill_state_dict
 from oracle.fill import seeded as _seeded32
@@ -47,6 +47,16 @@ def check_rows(got, want, tol):
     assert (np.abs(got[~nan, 0] - want[~nan, 0]) / (scale * 30)).max() < tol
 
 
+def check_samples(p, names, gold, samp_key, full_prefix, tol=GTOL):
+    """Element-level pin: the sampled gradient elements of EVERY tensor and the whole tensors stored in the golden."""
+    err = sample_errs(sample_rows([p[n].grad for n in names]), gold[samp_key])
+    assert np.nanmax(err) < tol, [(names[j], err[j]) for j in np.argsort(-np.nan_to_num(err))[:4]]
+    full = [k for k in gold if k.startswith(full_prefix)]
+    assert len(full) >= 8
+    for k in full:
+        assert rel_err(p[k[len(full_prefix):]].grad, gold[k]) < 1e-6, k        # stored as float32
+
+
 def test_spectral_norm_steps():
     g = load_golden("sn_steps")
     p = fill_state_dict([("c.bias", [8]), ("c.weight_orig", [8, 6, 3, 3]), ("c.weight_u", [8]), ("c.weight_v", [54])], 5)
@@ -71,6 +81,7 @@ def test_authenticator_small(schemas):
     assert rel_err(loss, g["loss"]) < TOL
     assert rel_err(test.grad, g["g_test"]) < GTOL and rel_err(si.grad, g["g_si"]) < GTOL
     check_rows(grad_rows(p, s["au_params"]), g["grads"], GTOL)
+    check_samples(p, s["au_params"], g, "gsamp", "gfull.")
     assert rel_err(p["dis.mlp.model.4.weight"].grad, g["g_mlp_last"]) < GTOL
     assert rel_err(p["src_encoder.down_blocks.0.conv_r1.weight_u"], g["u_after"]) < TOL
     with torch.no_grad():
@@ -88,6 +99,7 @@ def test_impersonator_small(schemas):
     assert rel_err(fake, g["fake"]) < TOL
     (fake * seeded(tuple(fake.shape), 25)).sum().backward()
     check_rows(grad_rows(p, s["im_params"]), g["grads"], GTOL)
+    check_samples(p, s["im_params"], g, "gsamp", "gfull.")
     assert rel_err(p["env_noise_mapper.model.6.weight"].grad, g["g_noise_last"]) < GTOL
 
 
@@ -199,6 +211,68 @@ def test_gaussian(schemas):
             assert rel_err(pa[x], g["au_final." + x]) < GTOL, x
         for x in i_names:
             assert rel_err(pi[x], g["im_final." + x]) < GTOL, x
+
+
+def test_full_width_training_step_gradients(schemas):
+    """One G-step + D-step of the reference trainer at full width (Omniglot-shaped, batch 2): losses, generated images and the
+    gradients both optimizers consume, element by element.  (The VoxCeleb2-shaped twin with R1, step_V, is checked on the GPU box.)"""
+    g = load_golden("step_O")
+    s = schemas["O"]
+    seed, b, m, n, k, size, ch = 151, 2, 2, 2, 2, 32, 1
+    pa, pi = params_of(s["au"], seed), params_of(s["im"], seed + 10)
+    leaked = seeded((b, m, ch, size, size), seed + 1, 0.5, 1.0)
+    real = seeded((b, n, ch, size, size), seed + 2, 0.5, 1.0)
+    si = seeded((b, k, ch, size, size), seed + 3, 0.5, 1.0)
+    z = seeded((b, n, 512), seed + 4)
+    fake = O.impersonator(pi, leaked, n, z)
+    loss = O.gan_loss(O.authenticator(pa, fake, si), 1.0).mean()
+    loss.backward()
+    assert rel_err(fake, g["fake"]) < 1e-6 and rel_err(loss, g["im_loss"]) < GTOL
+    check_rows(grad_rows(pi, s["im_params"]), g["im_grads"], 10 * GTOL)
+    check_samples(pi, s["im_params"], g, "im_gsamp", "im_gfull.", 10 * GTOL)
+    for v in pa.values():
+        v.grad = None
+    o = O.img_authenticator_forward(pa, fake.detach(), real, si, 0.0)
+    o[0].mean().backward()
+    assert rel_err(o[0].mean(), g["au_loss"]) < GTOL
+    check_samples(pa, s["au_params"], g, "au_gsamp", "au_gfull.", 10 * GTOL)
+
+
+def test_gaussian_d1000(schemas):
+    """BASELINE configs[3] width: forward, input gradient, two training iterations (sampled post-Adam parameters)."""
+    g = load_golden("gauss_d1000")
+    d, b, (m, n, k), seed = 1000, 8, (1, 5, 10), 191
+    pa, pi = params_of(schemas["gauss1000"]["au"], seed), params_of(schemas["gauss1000"]["im"], seed + 10)
+    real = seeded((b, n, d), seed + 1).requires_grad_()
+    si = seeded((b, k, d), seed + 2)
+    out = O.gaussian_authenticator(pa, real, si)
+    out.sum().backward()
+    assert rel_err(out, g["au_out"]) < TOL and rel_err(real.grad, g["au_g_real"]) < 1e-6
+    a_names, i_names = list(pa.keys()), list(pi.keys())
+    err = sample_errs(sample_rows([pa[x].grad for x in a_names]), g["au_gsamp"])
+    assert np.nanmax(err) < GTOL
+    st_a = {"step": 0, "m": [torch.zeros_like(pa[x]) for x in a_names], "v": [torch.zeros_like(pa[x]) for x in a_names]}
+    st_i = {"step": 0, "m": [torch.zeros_like(pi[x]) for x in i_names], "v": [torch.zeros_like(pi[x]) for x in i_names]}
+    for it in range(2):
+        real = seeded((b, n, d), seed + 100 * it + 1)
+        si = seeded((b, k, d), seed + 100 * it + 2)
+        leaked = seeded((b, m, d), seed + 100 * it + 5)
+        z = seeded((b, n, d), seed + 100 * it + 3)
+        for v in list(pa.values()) + list(pi.values()):
+            v.grad = None
+        fake = O.gaussian_impersonator(pi, leaked, n, z)
+        loss = O.gan_loss(O.gaussian_authenticator(pa, fake, si), 1.0).mean()
+        loss.backward()
+        assert abs(loss.item() - g["im_loss"][it]) < GTOL * max(1, abs(g["im_loss"][it]))
+        O.adam_step([pi[x] for x in i_names], [pi[x].grad for x in i_names], st_i, 1e-2, 0.9, 0.999)
+        for v in pa.values():
+            v.grad = None
+        o = O.gaussian_authenticator_forward(pa, fake.detach(), real, si, 0.0)
+        o[0].mean().backward()
+        assert abs(o[0].mean().item() - g["au_loss"][it]) < GTOL * max(1, abs(g["au_loss"][it]))
+        O.adam_step([pa[x] for x in a_names], [pa[x].grad for x in a_names], st_a, 1e-2, 0.9, 0.999)
+    assert np.nanmax(sample_errs(sample_rows([pa[x] for x in a_names]), g["au_final_samp"], 0.0)) < 1e-6
+    assert np.nanmax(sample_errs(sample_rows([pi[x] for x in i_names]), g["im_final_samp"], 0.0)) < 1e-6
 
 
 def test_episode_indices(schemas):
