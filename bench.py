@@ -486,7 +486,7 @@ def run_check(args):
     B = args.batch or 4 * world
     lo, hi = ddp.shard_range(B, rank, world)
     gim.set_precision("fp32")
-    _cabi.set_deterministic(True)
+    gim.set_deterministic(True)
     leaked, real, si = synth_batch(B, ch, size, 4321, dev)
     z = torch.randn((B, N_, STYLE), generator=torch.Generator().manual_seed(7)).to(dev)
     real_randn = torch.randn
@@ -525,7 +525,7 @@ def run_check(args):
         worst[name] = w
     # replicas stay identical through the path bench.py times (graph + NCCL all-reduce inside it)
     gim.set_precision(args.precision)
-    _cabi.set_deterministic(False)
+    gim.set_deterministic(False)
     torch.manual_seed(1)
     au, im = M.get_au(size, ch, STYLE).to(dev), M.get_im(size, ch, STYLE).to(dev)
     tr = DataParallelMock(GIMImgTrainer(tempfile.mkdtemp(prefix="gim_check_"), M_, N_, K_, au, im, 1e-3, 1e-3, 1e-4, reg_param=reg))

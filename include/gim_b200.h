@@ -237,6 +237,9 @@ int gim_set_stats_bwd(const float* g_sum, const float* g_std, int ld_g, const fl
 int gim_set_std_bwd_bwd(const float* ggx, const float* g_std, int ld_g, const float* x, float* gg_std, float* g_x, int b, int s, int d, float eps, gim_stream_t stream);
 /* y[b][s][d] = x - mean_s(x) (+ add[b][d] if add != NULL)   (gim_img_models.py:378-380, gim_gaussian_models.py:84-88) */
 int gim_set_center_add(const float* x, const float* add, float* y, int b, int s, int d, int center, gim_stream_t stream);
+/* y[b][s][d] = alpha * x[b][s][d] + beta * add[b][d]: Gaussian episode synthesis mu + sigma * noise on the device
+ * (replaces the host-side torch.normal calls of training/gim_gaussian_training.py:71-86) */
+int gim_affine_rows(const float* x, const float* add, float* y, int b, int s, int d, float alpha, float beta, gim_stream_t stream);
 
 /* ---- encoder tail: AdaptiveMaxPool2d((1,1)) (gim_img_models.py:53-54) ---- */
 int gim_gmax_fwd(const void* x, float* y, int32_t* idx, int n, int hw, int c, int dtype, gim_stream_t stream);

@@ -5,6 +5,6 @@ CUDA behind the C ABI in include/gim_b200.h).  No CPU fallback: importing works 
 a CUDA device.
 """
 from . import ops
-from .ops import set_precision, get_precision, set_conv_algo
+from .ops import set_precision, get_precision, set_conv_algo, set_deterministic
 
-__all__ = ["ops", "set_precision", "get_precision", "set_conv_algo"]
+__all__ = ["ops", "set_precision", "get_precision", "set_conv_algo", "set_deterministic"]

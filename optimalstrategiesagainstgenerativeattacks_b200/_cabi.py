@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gim_set_stats_bwd": "ppippiiiffp",
     "gim_set_std_bwd_bwd": "ppippp" + "iiifp",
     "gim_set_center_add": "pppiiiip",
+    "gim_affine_rows": "pppiiiffp",
     "gim_gmax_fwd": "pppiiiip",
     "gim_gather_idx": "pppiiiip",
     "gim_scatter_idx": "pppiiiip",

@@ -5,20 +5,25 @@
 namespace gim {
 
 // grid (ceil(c/32), n); block (32, 8).  Two passes over the (L2-resident) plane: exact mean, then M2.
+// The mean is accumulated as pivot + mean(x - pivot) with pivot = the plane's first pixel: on a spatially CONSTANT plane every
+// difference is exactly zero, so mean == x and the centred values are exactly 0 -- as in exact arithmetic.  That case is not exotic:
+// with the reference's initialisation (InstanceNorm bias 0) the right branch of every EnvDecoder block is spatially constant, the
+// variance is 0 and rsqrt(eps) = 316 multiplies whatever round-off the mean carries (a plain running sum gives 3x != x + x + x).
 template <typename T>
 __global__ void __launch_bounds__(256) norm_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __restrict__ m2, int hw, int c) {
     __shared__ float sh[8][33];
     int ch = blockIdx.x * 32 + threadIdx.x;
     long long img = blockIdx.y;
     const T* xi = x + img * (long long)hw * c;
+    const float pivot = ch < c ? to_f<T>(xi[ch]) : 0.f;
     float s = 0.f;
-    if (ch < c) for (int p = threadIdx.y; p < hw; p += 8) s += to_f<T>(xi[(long long)p * c + ch]);
+    if (ch < c) for (int p = threadIdx.y; p < hw; p += 8) s += to_f<T>(xi[(long long)p * c + ch]) - pivot;
     sh[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     float mu = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) mu += sh[j][threadIdx.x];
-    mu /= (float)hw;
+    mu = pivot + mu / (float)hw;
     __syncthreads();
     float q = 0.f;
     if (ch < c) for (int p = threadIdx.y; p < hw; p += 8) { float d = to_f<T>(xi[(long long)p * c + ch]) - mu; q += d * d; }

@@ -277,12 +277,14 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_multi_kernel(const __grid_cons
     const int taps = L.ksize * L.ksize;
     const int ci_tiles = (L.cin + 31) / 32, co_tiles = (L.cout + 31) / 32;
     if ((int)blockIdx.x >= ci_tiles * co_tiles) return;
-    const int co0 = ((int)blockIdx.x / ci_tiles) * 32, ci0 = ((int)blockIdx.x % ci_tiles) * 32;
     __shared__ float sh[32 * kShPitch];
     __shared__ float red[33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int nci = min(32, L.cin - ci0);
     float acc = 0.f;
+    // normally one tile per CTA; in the deterministic mode the grid has ONE CTA per layer, which walks all tiles in order
+    for (int tile = blockIdx.x; tile < ci_tiles * co_tiles; tile += gridDim.x) {
+    const int co0 = (tile / ci_tiles) * 32, ci0 = (tile % ci_tiles) * 32;
+    const int nci = min(32, L.cin - ci0);
     for (int t0 = 0; t0 < taps; t0 += kPackTaps) {
         const int nt = min(kPackTaps, taps - t0);
         for (int tl = 0; tl < nt; ++tl)
@@ -306,6 +308,7 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_multi_kernel(const __grid_cons
             }
         }
         __syncthreads();
+    }
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0 && acc != 0.f) atomicAdd(L.scratch, acc);
@@ -455,7 +458,7 @@ int gim_sn_backward_multi(const gim_sn_bwd_layer* layers, int n_layers, gim_stre
             if (tl > max_tiles) max_tiles = tl;
         }
         for (int i = c.n; i < kSnChunk; ++i) c.l[i] = c.l[0];
-        sn_bwd_dot_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c);
+        sn_bwd_dot_multi_kernel<<<dim3(deterministic() ? 1 : max_tiles, c.n), 256, 0, st>>>(c);
         int rc = check_launch("sn_bwd_dot_multi");
         if (rc != GIM_OK) return rc;
         sn_bwd_apply_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c);

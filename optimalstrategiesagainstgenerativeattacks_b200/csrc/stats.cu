@@ -98,6 +98,18 @@ __global__ void __launch_bounds__(256) set_center_add_kernel(const float* __rest
     for (int k = 0; k < s; ++k) ye[(long long)k * d] = xe[(long long)k * d] + shift;
 }
 
+// y[e, k, :] = alpha * x[e, k, :] + beta * add[e, :]: the Gaussian episode synthesis mu + sigma * noise (reference
+// training/gim_gaussian_training.py:71-86) from standard-normal draws, one read + one write per element
+__global__ void __launch_bounds__(256) affine_rows_kernel(const float* x, const float* __restrict__ add, float* y /* may alias x */, long long total,
+                                                          int s, int d, float alpha, float beta) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int j = (int)(i % d);
+        const long long e = i / ((long long)s * d);
+        y[i] = fmaf(alpha, x[i], beta * add[e * d + j]);
+    }
+}
+
 // grid (ceil(c/32), n), block (32, 8): max over the hw pixels + first arg-max
 template <typename T>
 __global__ void __launch_bounds__(256) gmax_fwd_kernel(const T* __restrict__ x, float* __restrict__ y, int32_t* __restrict__ idx, int hw, int c) {
@@ -216,6 +228,12 @@ int gim_set_center_add(const float* x, const float* add, float* y, int b, int s,
     if (total <= 0) return GIM_OK;
     set_center_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)st>>>(x, add, y, b, s, d, center);
     return check_launch("set_center_add");
+}
+int gim_affine_rows(const float* x, const float* add, float* y, int b, int s, int d, float alpha, float beta, gim_stream_t st) {
+    long long total = (long long)b * s * d;
+    if (total <= 0) return GIM_OK;
+    affine_rows_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)st>>>(x, add, y, total, s, d, alpha, beta);
+    return check_launch("affine_rows");
 }
 int gim_gmax_fwd(const void* x, float* y, int32_t* idx, int n, int hw, int c, int dtype, gim_stream_t st) {
     if (n <= 0 || c <= 0) return GIM_OK;

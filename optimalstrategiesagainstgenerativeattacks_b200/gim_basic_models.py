@@ -34,7 +34,7 @@ class GIMMeanStdStat(nn.Module):
         self.sample_std = GIMStdStat()
 
     def forward(self, x):
-        return torch.cat((self.sample_mean(x), self.sample_std(x)), dim=-1)
+        return ops.set_mean_std(x)                      # mean | std side by side from one pass over x
 
 
 class GIMFCStat(nn.Module):
@@ -59,4 +59,4 @@ class GIMMeanStdFcStat(nn.Module):
         self.fc = GIMFCStat(style_dim=style_dim, n_stats=fc_n_stats, hidden_layers=fc_hidden_layers)
 
     def forward(self, x):
-        return torch.cat((self.sample_mean(x), self.sample_std(x), self.fc(x)), dim=-1)
+        return torch.cat((ops.set_mean_std(x), self.fc(x)), dim=-1)

@@ -194,6 +194,9 @@ def _save_rank0(trainer, epoch):
     """Checkpoints are written by rank 0 only (replicas are identical); the other ranks wait until the file is complete."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     if not multi or dist.get_rank() == 0:
-        trainer.module.save(epoch=epoch)
+        if epoch is None:
+            trainer.module.save()                      # GIMGaussianTrainer.save() takes no epoch (reference gim_gaussian_trainer.py:125)
+        else:
+            trainer.module.save(epoch=epoch)
     if multi:
         dist.barrier()

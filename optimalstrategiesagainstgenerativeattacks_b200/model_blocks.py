@@ -163,9 +163,14 @@ class ResBlockDown(nn.Module):
                                       self.conv_r2.effective_weight(), self.conv_r2.bias, self.conv_r1.kernel_size, 0.2, want_ops)
         if isinstance(x, ops.Act):
             x = x.t32
-        out_res = self.conv_l1(x)
         out = self.conv_r1(x, ops.PRE_LRELU)          # conv(lrelu(x)): the activation is fused into the operand producer
         out = self.conv_r2(out, ops.PRE_LRELU)
+        if ops.get_precision() == "bf16" and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0:
+            # mixed-precision path: the 1x1 residual conv commutes with the pooling and runs at the pooled resolution, exactly like the
+            # fused block (ops.ResBlockDownFn) -- same operands, same single bf16 rounding of AvgPool2(x); 4x fewer FLOPs
+            out_res = self.conv_l1(ops.avg_pool2_add(x))
+            return ops.AddFn.apply(ops.avg_pool2_add(out), out_res)
+        out_res = self.conv_l1(x)
         return ops.avg_pool2_add(out_res, out)
 
 

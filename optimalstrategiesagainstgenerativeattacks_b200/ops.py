@@ -21,7 +21,8 @@ from torch.autograd.function import once_differentiable
 from . import _cabi as C
 
 LRELU_SLOPE = 0.2
-_state = {"operand_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False, "composite": False, "defer_sn": False}
+_state = {"operand_dtype": torch.float32, "conv_algo": C.ALGO_AUTO, "input_grads_only": False, "composite": False, "defer_sn": False,
+          "deterministic": False}
 
 
 def set_precision(name):
@@ -44,6 +45,16 @@ def act_dtype():
 
 def operand_dtype():
     return _state["operand_dtype"]
+
+
+def set_deterministic(flag):
+    """Parity mode: every reduction output is owned by one CTA (gim_set_deterministic) and the image-side weight-gradient kernel, whose
+    warps meet in shared-memory atomics, is replaced by the tensor-core route -- results are then bit-reproducible run to run (eager or
+    CUDA graph).  Slower; meant for tests.  -> previous setting."""
+    old = _state["deterministic"]
+    _state["deterministic"] = bool(flag)
+    C.set_deterministic(flag)
+    return old
 
 
 def set_conv_algo(algo):
@@ -633,7 +644,7 @@ class ResBlockDownFn(Function):
             x32 = xa
             xa = xr = xl = None
             want_any_w = (not _state["input_grads_only"]) and (ctx.needs_input_grad[3] or ctx.needs_input_grad[5])
-            fused_wgrad = want_any_w and ks == 3 and ci in (1, 3) and co % 8 == 0 and 256 % co == 0 and h % 4 == 0
+            fused_wgrad = want_any_w and ks == 3 and ci in (1, 3) and co % 8 == 0 and 256 % co == 0 and h % 4 == 0 and not _state["deterministic"]
             if (want_any_w and not fused_wgrad) or ctx.needs_input_grad[0]:
                 xl = _prepare_operand(x32, PRE_LRELU, slope)
             if want_any_w and not fused_wgrad:
@@ -1339,7 +1350,10 @@ def linear(x, weight, bias, slope=1.0):
     x2 = x.reshape(-1, shp[-1])
     rows, k = x2.shape
     n = weight.shape[0]
-    if _state["operand_dtype"] == torch.bfloat16 and _state["conv_algo"] != C.ALGO_SIMT and k % 8 == 0 and n % 8 == 0 and rows >= 16:
+    if _state["operand_dtype"] == torch.bfloat16 and k % 8 == 0 and n % 8 == 0 and rows >= 16:
+        # (the same route -- hence the same single bf16 rounding of x, W and the incoming gradient -- whichever conv algorithm is
+        # selected: with set_conv_algo("simt") the CUDA-core kernels consume the identical operands, which is what lets
+        # tests/test_parity_gpu.py compare the tcgen05 path element by element)
         y = conv2d(x2.reshape(rows, 1, 1, k), weight.reshape(1, n, k), bias, 1).reshape(rows, n)
         if slope != 1.0:
             y = LReluFn.apply(y, slope)
@@ -1518,6 +1532,71 @@ class SetStdBwdFn(Function):
         g_x = torch.empty_like(x)
         C.call("gim_set_std_bwd_bwd", C.ptr(ggx), C.ptr(g), d, C.ptr(x), C.ptr(gg_std), C.ptr(g_x), b, s, d, ctx.eps)
         return gg_std, g_x, None
+
+
+class SetMeanStdFn(Function):
+    """cat(mean_s x, custom_std_s x) -> [b, 2d] in ONE pass over x (GIMMeanStdStat gim_basic_models.py:71-89 and the first two thirds of
+    GIMMeanStdFcStat :152-172): the statistics kernel emits both and writes them side by side, so x is read once and there is no concat.
+    Twice differentiable (R1): the backward is itself an operator with an explicit second-order kernel."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = _c(x)
+        b, s, d = x.shape
+        out = _empty((b, 2 * d), torch.float32, x)
+        C.call("gim_set_stats_fwd", C.ptr(x), C.ptr(out), C.ptr(out) + 4 * d, 2 * d, b, s, d, 1.0 / s, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return SetMeanStdBwdFn.apply(g, x, ctx.eps), None
+
+
+class SetMeanStdBwdFn(Function):
+    @staticmethod
+    def forward(ctx, g, x, eps):
+        g = _c(g)
+        b, s, d = x.shape
+        gx = torch.empty_like(x)
+        C.call("gim_set_stats_bwd", C.ptr(g), C.ptr(g) + 4 * d, 2 * d, C.ptr(x), C.ptr(gx), b, s, d, 1.0 / s, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(g, x)
+        return gx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ggx):
+        g, x = ctx.saved_tensors
+        b, s, d = x.shape
+        ggx = _c(ggx)
+        gg = _empty((b, 2 * d), torch.float32, x)
+        gg_std = _empty((b, d), torch.float32, x)
+        g_x = torch.empty_like(x)
+        C.call("gim_set_stats_fwd", C.ptr(ggx), C.ptr(gg), None, 2 * d, b, s, d, 1.0 / s, 0.0)             # d/d g_mean: the mean of ggx
+        C.call("gim_set_std_bwd_bwd", C.ptr(ggx), C.ptr(g) + 4 * d, 2 * d, C.ptr(x), C.ptr(gg_std), C.ptr(g_x), b, s, d, ctx.eps)
+        gg[:, d:] = gg_std
+        return gg, g_x, None
+
+
+def set_mean_std(x, eps=1e-8):
+    return SetMeanStdFn.apply(x, eps)
+
+
+def gaussian_episodes(batch, sizes, d, prior_sigma, src_sigma, device):
+    """Device-side synthesis of Gaussian GIM episodes with the reference's distributions (training/gim_gaussian_training.py:71-86):
+    mu ~ N(0, prior_sigma^2 I) per episode, every sample of the episode ~ N(mu, src_sigma^2 I).  -> (mu [b, d], [x_i [b, s_i, d] for s_i
+    in sizes]).  Standard normals come from the CUDA generator (seeded by torch.manual_seed; CUDA-graph safe), one kernel per sample set
+    shifts and scales them.  The reference draws on the host and copies 65 M floats per iteration at d = 1000."""
+    mu_raw = torch.randn((batch, d), device=device)
+    out = []
+    for s in sizes:
+        noise = torch.randn((batch, s, d), device=device)
+        C.call("gim_affine_rows", C.ptr(noise), C.ptr(mu_raw), C.ptr(noise), batch, s, d, float(src_sigma), float(prior_sigma))
+        out.append(noise)
+    return mu_raw * prior_sigma, out
 
 
 def set_mean(x):

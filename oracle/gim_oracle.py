@@ -237,6 +237,11 @@ def n_down_blocks(img_size):
     return int(math.log2(img_size)) - 2                                 # gim_img_models.py:30, 111, 175
 
 
+# Test-only hook (NOT part of the reference): callable(prefix, x[N,C,H,W]) -> [N,C] used instead of the global max, so that a test can
+# record one evaluation's arg-max routing and replay it in another (tests/test_parity_width_gpu.py isolates what arg-max flips cost).
+GMAX_HOOK = None
+
+
 def encoder(p, prefix, x, img_size, training=True):
     """Encoder gim_img_models.py:43-57 -> [N, style_dim]."""
     nb = n_down_blocks(img_size)
@@ -245,7 +250,7 @@ def encoder(p, prefix, x, img_size, training=True):
         if i == att_loc:
             x = self_attention(p, prefix + ".att", x, training)
         x = res_block_down(p, "%s.down_blocks.%d" % (prefix, i), x, 3, training)
-    x = torch.amax(x, dim=(2, 3))
+    x = torch.amax(x, dim=(2, 3)) if GMAX_HOOK is None else GMAX_HOOK(prefix, x)
     return lrelu(x)
 
 

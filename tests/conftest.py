@@ -76,3 +76,67 @@ def sample_errs(got, want, zero_floor=1e-9):
     err = np.linalg.norm(g - w, axis=1) / np.maximum(wn, 1e-300)
     err[none_w | (wn < zero_floor * wn.max())] = np.nan
     return err
+
+
+class Routing:
+    """Record the encoders' global-max arg-max positions in one evaluation and force them in others (oracle or CUDA path), keyed by
+    (encoder name, call index) so the order in which the two-stream path happens to build its branches does not matter.  Isolates the
+    one discontinuous operator of the path: with the routing pinned, every remaining operation is smooth in its operands."""
+
+    def __init__(self):
+        self.idx = {}
+
+    # ---- oracle side: install as oracle.gim_oracle.GMAX_HOOK ----
+    def oracle_hook(self, net, record):
+        counts = {}
+
+        def hook(prefix, x):
+            key = "%s.%s" % (net, prefix)
+            j = counts.get(key, 0)
+            counts[key] = j + 1
+            flat = x.flatten(2)
+            if record:
+                self.idx[(key, j)] = flat.argmax(-1)
+            return flat.gather(2, self.idx[(key, j)].to(flat.device).unsqueeze(-1)).squeeze(-1)
+        return hook
+
+    # ---- CUDA path: patches gim_img_models.Encoder.forward for the modules given as {module: name} ----
+    def patch_encoders(self, named_modules, record=False):
+        import contextlib
+
+        import torch
+        from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_models as M
+        from optimalstrategiesagainstgenerativeattacks_b200 import model_blocks as mb
+        from optimalstrategiesagainstgenerativeattacks_b200 import ops
+        names = {id(m): n for m, n in named_modules.items()}
+        counts = {}
+        routing = self
+
+        def forward(self, x):
+            x = M._as_nhwc(x)
+            mb.sn_prepare_module(self, skip=() if self.att_loc < self.n_down_blocks else (self.att,))
+            for i, block in enumerate(self.down_blocks):
+                if i == self.att_loc:
+                    x = self.att(x)
+                x = block(x, want_ops=i + 1 < self.n_down_blocks)
+            if isinstance(x, ops.Act):
+                x = x.t32
+            key = names[id(self)]
+            j = counts.get(key, 0)
+            counts[key] = j + 1
+            if record:
+                n, h, w, c = x.shape
+                routing.idx[(key, j)] = x.detach().reshape(n, h * w, c).argmax(1)
+            idx = routing.idx[(key, j)].to(device=x.device, dtype=torch.int32).contiguous()
+            x = ops.GatherIdxFn.apply(x, idx)
+            return ops.lrelu(x) if self.use_out_lrelu else x
+
+        @contextlib.contextmanager
+        def ctx():
+            orig = M.Encoder.forward
+            M.Encoder.forward = forward
+            try:
+                yield
+            finally:
+                M.Encoder.forward = orig
+        return ctx()

@@ -232,8 +232,14 @@ def test_set_statistics_with_double_backward():
         ref = torch.cat((x64.mean(1), O.custom_std(x64)), -1)
         got = torch.cat((ops.set_mean(x), ops.set_std(x)), -1)
         assert rel_err(got, ref) < 1e-5 or (s == 1 and float(got[:, d:].abs().max()) == 0)
+        xf = x64.detach().float().cuda().requires_grad_()
+        fused = ops.set_mean_std(xf)                   # one pass, mean | std side by side
+        assert torch.equal(fused, got.detach())
         if s == 1:
             continue
+        pf, qf = rnd(b, 2 * d, seed=2).float().cuda(), rnd(b, s, d, seed=3).float().cuda()
+        (f1,) = torch.autograd.grad((fused * pf).sum(), xf, create_graph=True)
+        (f2,) = torch.autograd.grad(ops.DotFn.apply(f1, qf).sum(), xf)
         probe = rnd(b, 2 * d, seed=2)
         q = rnd(b, s, d, seed=3)          # (sum g1^2 is ~independent of x for the std term, so contract with a random tensor)
         (g1r,) = torch.autograd.grad((ref * probe).sum(), x64, create_graph=True)
@@ -241,6 +247,7 @@ def test_set_statistics_with_double_backward():
         (g1,) = torch.autograd.grad((got * probe.float().cuda()).sum(), x, create_graph=True)
         (g2,) = torch.autograd.grad(ops.DotFn.apply(g1, q.float().cuda()).sum(), x)
         assert rel_err(g1, g1r) < 1e-5 and rel_err(g2, g2r) < 1e-4
+        assert rel_err(f1, g1r) < 1e-5 and rel_err(f2, g2r) < 1e-4
     w64, add64 = rnd(3, 4, 6, seed=3).requires_grad_(), rnd(3, 6, seed=4).requires_grad_()
     ref = w64 - w64.mean(1, keepdim=True) + add64.unsqueeze(1)
     w, add = w64.detach().float().cuda().requires_grad_(), add64.detach().float().cuda().requires_grad_()
@@ -249,6 +256,23 @@ def test_set_statistics_with_double_backward():
     gr = torch.autograd.grad((ref * probe).sum(), (w64, add64))
     gg = torch.autograd.grad((got * probe.float().cuda()).sum(), (w, add))
     assert rel_err(got, ref) < 1e-6 and rel_err(gg[0], gr[0]) < 1e-6 and rel_err(gg[1], gr[1]) < 1e-6
+
+
+def test_gaussian_episode_sampler_distribution():
+    """Device-side episode synthesis (reference training/gim_gaussian_training.py:71-86): mu ~ N(0, prior^2), x | mu ~ N(mu, src^2)."""
+    ops = ops_mod()
+    torch.manual_seed(3)
+    mu, (leaked, real, si) = ops.gaussian_episodes(4096, (1, 5, 10), 16, 10.0, 1.0, torch.device("cuda"))
+    assert leaked.shape == (4096, 1, 16) and real.shape == (4096, 5, 16) and si.shape == (4096, 10, 16) and mu.shape == (4096, 16)
+    assert abs(float(mu.std()) - 10.0) < 0.2 and abs(float(mu.mean())) < 0.2
+    for x in (leaked, real, si):
+        r = x - mu.unsqueeze(1)
+        assert abs(float(r.std()) - 1.0) < 0.02 and abs(float(r.mean())) < 0.02
+    # samples of one episode share mu, different sets are independent draws
+    assert abs(float(((real.mean(1) - mu) * (si.mean(1) - mu)).mean())) < 0.01
+    torch.manual_seed(3)
+    mu2, _ = ops.gaussian_episodes(4096, (1, 5, 10), 16, 10.0, 1.0, torch.device("cuda"))
+    assert torch.equal(mu, mu2)                        # seeded by torch.manual_seed
 
 
 def test_global_max_bce_rows():

@@ -244,13 +244,20 @@ def test_training_iterations_vs_reference(schemas, tmp_path, prec, name, reg, se
             rec[key].append(val.item())
         if it == 0:
             assert rel_err(fake, gold["fake0"]) < max(tol, 3e-4)
-    # iteration 0 is a pure function of the inputs; iteration 1 also carries the Adam update (sign-like for tiny gradients)
+    # iteration 0 is a pure function of the inputs; iteration 1 also carries the Adam update (sign-like for tiny gradients).
+    # Fixed gates [measured on B200: fp32 it0 <= 2e-7, it1 <= 1.6e-4; bf16 it0 <= 2.8e-3, it1 <= 9.1e-3]
+    gate0, gate1 = {"fp32": (1e-5, 1e-3), "bf16": (2e-2, 2e-2)}[prec]
     for key, v in rec.items():
-        assert abs(v[0] - gold[key][0]) <= (5 * tol) * max(abs(gold[key][0]), 1e-2), (key, v, gold[key])
-        assert abs(v[1] - gold[key][1]) <= (50 * tol) * max(abs(gold[key][1]), 1e-2), (key, v, gold[key])
+        print("steps %s/%s %-10s it0 dev %.2e  it1 dev %.2e" % (name, prec, key, abs(v[0] - gold[key][0]) / max(abs(gold[key][0]), 1e-2),
+                                                             abs(v[1] - gold[key][1]) / max(abs(gold[key][1]), 1e-2)))
+    for key, v in rec.items():
+        assert abs(v[0] - gold[key][0]) <= gate0 * max(abs(gold[key][0]), 1e-2), (key, v, gold[key])
+        assert abs(v[1] - gold[key][1]) <= gate1 * max(abs(gold[key][1]), 1e-2), (key, v, gold[key])
     for mod, key in ((au, "au_params"), (im, "im_params")):
         got = np.asarray([[v.double().sum().item(), v.double().norm().item()] for v in mod.state_dict().values()])
-        assert np.abs(got[:, 1] - gold[key][:, 1]).max() / np.abs(gold[key][:, 1]).max() < max(10 * tol, 2e-3)
+        dev = np.abs(got[:, 1] - gold[key][:, 1]).max() / np.abs(gold[key][:, 1]).max()
+        print("steps %s/%s post-Adam %s norm dev %.2e" % (name, prec, key, dev))
+        assert dev < max(10 * tol, 2e-3)
     # checkpoint round trip in the reference's schema
     tr.module.save(epoch=0)
     ck = torch.load(str(tmp_path / "ckpts" / "model_00000001.pt"), map_location="cpu", weights_only=False)

@@ -1,0 +1,351 @@
+"""GPU parity at FULL network width (BASELINE configs[1] Omniglot-shaped 1x32x32 and configs[2] VoxCeleb2-shaped 3x64x64, style 512),
+through the kept trainer API and the C ABI:
+
+  1. element-level gradients of one whole training iteration (G-step + D-step, R1 for V) against the UNMODIFIED reference in float64
+     (tests/golden/step_{O,V}.npz: sampled elements of every tensor + whole tensors), fp32 and bf16 paths;
+  2. the tcgen05 tensor-core path (fused blocks, two streams) against the CUDA-core path on IDENTICAL bf16 operands, every
+     gradient tensor element by element: isolates implementation error from what bf16 operands cost;
+  3. a well-conditioned bf16-vs-float64 case (trained weights, batch 8) against the oracle evaluated in float64 on the device;
+  4. the path bench.py times -- whole-iteration CUDA graph + two streams -- against the eager trainer, step by step.
+"""
+import contextlib
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, sample_errs, sample_rows
+from oracle import gim_oracle as O
+from oracle.fill import fill_state_dict, seeded
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"O": dict(size=32, ch=1, reg=0.0, seed=151, b=2, m=2, n=2, k=2), "V": dict(size=64, ch=3, reg=10.0, seed=171, b=2, m=1, n=2, k=1)}
+
+
+@pytest.fixture(autouse=True)
+def _cuda_only():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi, ops
+    ops.set_precision("fp32")
+    ops.set_conv_algo("auto")
+    yield
+    ops.set_precision("fp32")
+    ops.set_conv_algo("auto")
+    ops.set_deterministic(False)
+
+
+@contextlib.contextmanager
+def inject_randn(zs):
+    real = torch.randn
+    queue = list(zs)
+    torch.randn = lambda *a, **k: queue.pop(0).clone()
+    try:
+        yield
+    finally:
+        torch.randn = real
+
+
+def pkg():
+    import optimalstrategiesagainstgenerativeattacks_b200 as g
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi, gim_img_models, gim_img_trainer, training_steps, utils
+    return g, _cabi, gim_img_models, gim_img_trainer, training_steps, utils
+
+
+def one_iteration(tr, S, leaked, real, si, z):
+    """-> dict(fake, im_loss, im_grads [list], au_loss..., au_grads [list]) of one G-step + D-step (gradients as the optimizers saw them)."""
+    tr.module.do_global_step()
+    tr.module.update_learning_rate()
+    with inject_randn([z]):
+        im_loss, fake, au_out = S.im_train_step(tr, leaked, si)
+    im_g = [None if p.grad is None else p.grad.detach().clone() for p in tr.module.impersonator.parameters()]
+    o = S.au_train_step(tr, real, fake, si)
+    au_g = [None if p.grad is None else p.grad.detach().clone() for p in tr.module.authenticator.parameters()]
+    return dict(fake=fake, im_loss=im_loss, g_au_out=au_out, im_grads=im_g, au_loss=o[0], loss_real=o[1], loss_fake=o[2], reg=o[3],
+                out_real=o[4], out_fake=o[5], au_grads=au_g)
+
+
+def report(tag, names, err, top=5):
+    fin = np.nan_to_num(err, nan=-1.0)
+    order = np.argsort(-fin)[:top]
+    q = np.nanquantile(err, [0.5, 0.9, 1.0])
+    print("%s: per-tensor rel err median %.2e  q90 %.2e  max %.2e | worst: %s" % (
+        tag, q[0], q[1], q[2], ", ".join("%s %.1e" % (names[j], err[j]) for j in order)))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# 1. full-width training iteration against the float64 reference
+# ----------------------------------------------------------------------------------------------------------------------
+# Fixed gates (measured values, B200, round 2, in brackets).
+# fp32 path: forward quantities / losses rel 1e-4 [<= 5e-5].  Gradients, per tensor, elements at reference positions:
+#   authenticator (D-step): median 5e-5 [5e-6], worst tensor 2e-3 [O 5.0e-4, V 1.2e-4 -- conv biases: column sums of +-values];
+#   attacker (G-step, ~50 layers deep): median 5e-3 [O 3.6e-4, V 1.1e-3], worst tensor 5e-2 [O 7e-3, V 1.5e-2 (an attention gamma)].
+#   torch's own fp32 evaluation of the reference algorithm (the oracle in fp32, printed below) sits at the same distance from the float64
+#   truth [au median 1.7e-4 / max 4.9e-4; im median 6.6e-4 / max 1.0e-1]: these are the round-off floor of the algorithm, not of the kernels.
+# bf16 path: forward quantities / losses rel 2e-2 [fake 1.4e-2, losses <= 1e-3].  The trainer's D loss is BCE(real->1) + BCE(fake->0) at
+#   logits ~ 0: the two terms' gradients cancel to ~10 % of their size, so per-tensor gradient errors of ANY bf16 evaluation are ~10 % there
+#   (emulation vs float64: median 9.8e-2); they are printed, the layout is gated by direction, and the well-conditioned gradient gates
+#   are tests 2 and 3 below.
+FP32_FWD, FP32_AU_MED, FP32_AU_MAX, FP32_IM_MED, FP32_IM_MAX = 1e-4, 5e-5, 2e-3, 5e-3, 5e-2
+BF16_FWD = 2e-2
+
+
+@pytest.mark.parametrize("name", ["O", "V"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_full_width_iteration_vs_reference(schemas, tmp_path, name, prec):
+    g, C, M, T, S, U = pkg()
+    c = CFG[name]
+    gold = load_golden("step_" + name)
+    g.set_precision(prec)
+    g.set_deterministic(prec == "fp32")
+    s = schemas[name]
+    au, im = M.get_au(c["size"], c["ch"], 512), M.get_im(c["size"], c["ch"], 512)
+    au.load_state_dict(fill_state_dict([(k, sh) for k, sh in s["au"]], c["seed"]))
+    im.load_state_dict(fill_state_dict([(k, sh) for k, sh in s["im"]], c["seed"] + 10))
+    au, im = au.cuda(), im.cuda()
+    tr = U.DataParallelMock(T.GIMImgTrainer(str(tmp_path), c["m"], c["n"], c["k"], au, im, 1e-4, 1e-4, 1e-6, reg_param=c["reg"]))
+    sd = c["seed"]
+    shp = (c["ch"], c["size"], c["size"])
+    leaked = seeded((c["b"], c["m"]) + shp, sd + 1, 0.5, 1.0).cuda()
+    real = seeded((c["b"], c["n"]) + shp, sd + 2, 0.5, 1.0).cuda()
+    si = seeded((c["b"], c["k"]) + shp, sd + 3, 0.5, 1.0).cuda()
+    z = seeded((c["b"], c["n"], 512), sd + 4).cuda()
+    r = one_iteration(tr, S, leaked, real, si, z)
+    fwd_tol = FP32_FWD if prec == "fp32" else BF16_FWD
+    assert rel_err(r["fake"], gold["fake"]) < fwd_tol
+    for key in ("im_loss", "au_loss", "loss_real", "loss_fake", "out_real", "out_fake", "g_au_out"):
+        assert rel_err(r[key], gold[key]) < fwd_tol, (key, float(r[key].float().mean()), gold[key])
+    if c["reg"] > 0:
+        assert rel_err(r["reg"], gold["reg"]) < (1e-3 if prec == "fp32" else 5e-2), (float(r["reg"]), gold["reg"])
+    e_au = sample_errs(sample_rows(r["au_grads"]), gold["au_gsamp"])
+    e_im = sample_errs(sample_rows(r["im_grads"]), gold["im_gsamp"])
+    report("%s/%s authenticator (D-step)" % (name, prec), s["au_params"], e_au)
+    report("%s/%s attacker (G-step)" % (name, prec), s["im_params"], e_im)
+    # whole tensors: position-exact (a transposed or permuted gradient cannot pass)
+    full_err, full_cos = {}, {}
+    for prefix, mod in (("au_gfull.", au), ("im_gfull.", im)):
+        params = dict(mod.named_parameters())
+        top = max(float(np.linalg.norm(gold[kk])) for kk in gold if kk.startswith(prefix))
+        for k in [k for k in gold if k.startswith(prefix)]:
+            got, want = params[k[len(prefix):]].grad.flatten().double().cpu(), torch.from_numpy(gold[k]).flatten().double()
+            full_err[k] = rel_err(got, want)
+            if float(want.norm()) > 1e-7 * top:
+                full_cos[k] = float(torch.dot(got, want) / (got.norm() * want.norm()))
+    print("%s/%s whole tensors: %s" % (name, prec, ", ".join("%s %.1e" % kv for kv in sorted(full_err.items(), key=lambda kv: -kv[1])[:6])))
+    if prec == "fp32":
+        assert np.nanmedian(e_au) < FP32_AU_MED and np.nanmax(e_au) < FP32_AU_MAX
+        assert np.nanmedian(e_im) < FP32_IM_MED and np.nanmax(e_im) < FP32_IM_MAX
+        assert max(v for k, v in full_err.items() if k.startswith("au_")) < FP32_AU_MAX
+        assert max(v for k, v in full_err.items() if k.startswith("im_")) < FP32_IM_MAX
+        assert min(full_cos.values()) > 0.999
+    else:
+        assert min(full_cos.values()) > 0.7, sorted(full_cos.items(), key=lambda kv: kv[1])[:3]     # a wrong layout gives ~0
+        assert np.median(list(full_cos.values())) > 0.98
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# 2 + 3. bf16 gradients where they are well conditioned, three ways:
+#   tcgen05 tensor-core path (A) vs CUDA-core path (B): same operands, different kernels          -> implementation error
+#   A vs the oracle with bf16 operand rounding (E): same rounding points, independent arithmetic  -> implementation error
+#   A vs the oracle in float64 (R)                                                                -> what bf16 operands cost
+# Conditioning: a single-term loss (no real/fake cancellation) and the encoders' arg-max routing pinned to R's (conftest.Routing).
+# ----------------------------------------------------------------------------------------------------------------------
+def _grad_errs(x, y):
+    top = max(float(t.double().norm()) for t in y if t is not None)
+    out = []
+    for gx, gy in zip(x, y):
+        assert (gx is None) == (gy is None)
+        if gy is None or float(gy.double().norm()) < 1e-7 * top:
+            out.append(np.nan)           # identically-zero true gradients are rounding noise in every evaluation
+        else:
+            out.append(float((gx.double() - gy.double()).norm() / gy.double().norm()))
+    return np.asarray(out)
+
+
+# measured (B200, batch 4, fill.py weights), O / V width, per tensor:
+#   A-B  median 9.5e-3 / 8.4e-3, max 5.2e-2 / 2.2e-2 (attention query/key projections: softmax-logit gradients cancel)
+#   A-E  median 1.3e-2 / 6.3e-3, max 4.1e-2 / 3.3e-2
+#   A-R  median 1.7e-2 / 3.2e-2, q90 2.1e-2 / 3.7e-2, max 4.3e-2 / 2.0e-1 (an attention gamma)
+#   E-R  median 2.2e-2 / 3.0e-2, q90 2.6e-2 / 3.5e-2, max 5.0e-2 / 1.6e-1
+# i.e. north_star's 2e-2 holds for the O-width median, not for V's -- and not for the emulation either: the distance from the truth is
+# the bf16 rounding of the operands (common to A and E), the kernels add nothing to it.  fp32 evaluations of the same gradients sit
+# 1e-5 .. 1e-3 from float64: the network amplifies forward perturbations ~100x into these gradients at random weights.
+AU_IMPL_MED, AU_IMPL_MAX, AU_TRUTH_MED, AU_TRUTH_MAX = 2e-2, 8e-2, 4e-2, 2.5e-1
+
+
+@pytest.mark.parametrize("name", ["O", "V"])
+def test_bf16_authenticator_gradients_well_conditioned(schemas, name):
+    """Every authenticator gradient tensor at full width: tensor-core path vs both independent bf16 evaluations (implementation error) and
+    vs float64 (arithmetic cost, bounded by the emulation's own)."""
+    from conftest import Routing
+    g, C, M, T, S, U = pkg()
+    c = CFG[name]
+    size, ch, B = c["size"], c["ch"], 4
+    s = schemas[name]
+    sd = fill_state_dict([(k, sh) for k, sh in s["au"]], c["seed"])
+    names = s["au_params"]
+    gen = torch.Generator().manual_seed(77)
+    test, si = (torch.rand((B, 5, ch, size, size), generator=gen).mul(2).sub(1).cuda() for _ in range(2))
+    routing = Routing()
+
+    def oracle(dtype, rounding, record):
+        p = {k: v.to("cuda", dtype).clone() for k, v in sd.items()}
+        for n_ in names:
+            p[n_].requires_grad_()
+        O.set_operand_rounding(rounding)
+        O.GMAX_HOOK = routing.oracle_hook("au", record)
+        try:
+            O.gan_loss(O.authenticator(p, test.to(dtype), si.to(dtype)), 1.0).mean().backward()
+        finally:
+            O.set_operand_rounding(False)
+            O.GMAX_HOOK = None
+        return [p[n_].grad for n_ in names]
+
+    def ours(algo):
+        g.set_precision("bf16")
+        g.set_conv_algo(algo)
+        au = M.get_au(size, ch, 512)
+        au.load_state_dict(sd)
+        au = au.cuda().train()
+        with routing.patch_encoders({au.src_encoder: "au.src_encoder", au.env_encoder: "au.env_encoder"}):
+            g.ops.BCEWithLogitsFn.apply(au(test, si), 1.0).mean().backward()
+        return [p.grad for p in au.parameters()]
+
+    allow = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # the emulation must not be rounded to tf32
+    try:
+        R = oracle(torch.float64, False, True)
+        E = oracle(torch.float32, True, False)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = allow
+    A, Bc = ours("tcgen05"), ours("simt")
+    e_ab, e_ae, e_ar, e_er = _grad_errs(A, Bc), _grad_errs(A, E), _grad_errs(A, R), _grad_errs(E, R)
+    for tag, e in (("A-B tcgen05 vs CUDA cores", e_ab), ("A-E tcgen05 vs emulation", e_ae), ("A-R tcgen05 vs float64", e_ar), ("E-R emulation vs float64", e_er)):
+        report("%s authenticator %s" % (name, tag), names, e)
+    for e in (e_ab, e_ae):
+        assert np.nanmedian(e) < AU_IMPL_MED and np.nanmax(e) < AU_IMPL_MAX
+    assert np.nanmedian(e_ar) < AU_TRUTH_MED and np.nanmax(e_ar) < AU_TRUTH_MAX
+    # never further from the truth than the emulation of the same arithmetic (plus the implementation bound)
+    assert np.nanmedian(e_ar) < 1.25 * np.nanmedian(e_er) + 5e-3 and np.nanmax(e_ar - e_er) < AU_IMPL_MAX
+
+
+# measured (O width, batch 4, fill.py weights, routing pinned): pairwise medians A-B 2.7e-2, A-E 2.7e-2, B-E 2.2e-2; vs float64 A-R 4.0e-2,
+# E-R 3.7e-2 -- every bf16 evaluation of the ~50-layer attacker (InstanceNorm over 2x2 / 4x4 maps) lands this far from every other one, the
+# CUDA-core path and the torch emulation included.  The gate is that the tensor-core path is not an outlier among them, plus fixed caps.
+IM_PAIR_MED, IM_PAIR_Q90, IM_TRUTH_MED = 6e-2, 1.5e-1, 8e-2
+
+
+@pytest.mark.parametrize("name,B", [("O", 4), ("V", 2)])
+def test_bf16_attacker_gradients_three_way(schemas, name, B):
+    from conftest import Routing
+    g, C, M, T, S, U = pkg()
+    c = CFG[name]
+    size, ch, n = c["size"], c["ch"], 5
+    s = schemas[name]
+    sd_a = fill_state_dict([(k, sh) for k, sh in s["au"]], c["seed"])
+    sd_i = fill_state_dict([(k, sh) for k, sh in s["im"]], c["seed"] + 10)
+    names = s["im_params"]
+    gen = torch.Generator().manual_seed(78)
+    leaked, si = (torch.rand((B, 5, ch, size, size), generator=gen).mul(2).sub(1).cuda() for _ in range(2))
+    z = torch.randn((B, n, 512), generator=gen).cuda()
+    routing = Routing()
+
+    def oracle(dtype, rounding, record):
+        pa = {k: v.to("cuda", dtype).clone() for k, v in sd_a.items()}
+        pi = {k: v.to("cuda", dtype).clone() for k, v in sd_i.items()}
+        for n_ in names:
+            pi[n_].requires_grad_()
+        O.set_operand_rounding(rounding)
+        try:
+            O.GMAX_HOOK = routing.oracle_hook("im", record)
+            fake = O.impersonator(pi, leaked.to(dtype), n, z.to(dtype))
+            O.GMAX_HOOK = routing.oracle_hook("au", record)
+            O.gan_loss(O.authenticator(pa, fake, si.to(dtype)), 1.0).mean().backward()
+        finally:
+            O.set_operand_rounding(False)
+            O.GMAX_HOOK = None
+        return fake.detach(), [pi[n_].grad for n_ in names]
+
+    def ours(algo):
+        g.set_precision("bf16")
+        g.set_conv_algo(algo)
+        au, im = M.get_au(size, ch, 512), M.get_im(size, ch, 512)
+        au.load_state_dict(sd_a)
+        im.load_state_dict(sd_i)
+        au, im = au.cuda().train(), im.cuda().train()
+        tr = T.GIMImgTrainer(tempfile.mkdtemp(), 5, n, 5, au, im, 1e-6, 1e-6, 1e-7, reg_param=0.0)
+        mods = {au.src_encoder: "au.src_encoder", au.env_encoder: "au.env_encoder", im.src_encoder: "im.src_encoder", im.env_encoder: "im.env_encoder"}
+        with routing.patch_encoders(mods), inject_randn([z]):
+            loss, fake, _ = tr.impersonator_forward(leaked, si)          # the G-step's graph (authenticator weights are constants)
+        loss.mean().backward()
+        return fake.detach(), [p.grad for p in im.parameters()]
+
+    allow = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        fR, R = oracle(torch.float64, False, True)
+        fE, E = oracle(torch.float32, True, False)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = allow
+    fA, A = ours("tcgen05")
+    fB, Bc = ours("simt")
+    print("%s fake: A-B %.2e A-E %.2e B-E %.2e A-R %.2e E-R %.2e" % (name, rel_err(fA, fB), rel_err(fA, fE), rel_err(fB, fE), rel_err(fA, fR), rel_err(fE, fR)))
+    assert rel_err(fA, fR) < BF16_FWD and rel_err(fA, fE) < BF16_FWD and rel_err(fA, fB) < BF16_FWD
+    e = {k: _grad_errs(x, y) for k, (x, y) in dict(ab=(A, Bc), ae=(A, E), be=(Bc, E), ar=(A, R), er=(E, R)).items()}
+    for k, v in e.items():
+        report("%s attacker %s" % (name, k), names, v)
+    med = {k: float(np.nanmedian(v)) for k, v in e.items()}
+    assert med["ab"] < IM_PAIR_MED and med["ae"] < IM_PAIR_MED and med["ar"] < IM_TRUTH_MED
+    assert np.nanquantile(e["ab"], 0.9) < IM_PAIR_Q90 and np.nanquantile(e["ae"], 0.9) < IM_PAIR_Q90
+    # not an outlier: the tensor-core path is as close to the emulation / to the truth as the independent CUDA-core path and the emulation are
+    assert med["ae"] < 2.0 * med["be"] + 5e-3 and med["ar"] < 1.5 * med["er"] + 5e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# 4. the benchmarked path: CUDA graph + two streams vs eager
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-6), ("bf16", 1e-5)])
+def test_graph_replay_equals_eager_iterations(prec, tol):
+    """Three training iterations at O width: `GraphedIteration` (what bench.py times: one captured graph, two encoder streams, fused
+    Adam with device-side step) vs the eager trainer API on the same batches and noise -- losses per step and ALL parameters afterwards.
+    Deterministic reductions, so the only difference allowed is none: tolerance is round-off of the comparison itself."""
+    g, C, M, T, S, U = pkg()
+    from optimalstrategiesagainstgenerativeattacks_b200.cuda_graph import GraphedIteration
+    size, ch, B = 32, 1, 4
+    g.set_precision(prec)
+    g.set_deterministic(True)
+    gen = torch.Generator().manual_seed(9)
+    batches = [[torch.rand((B, 5, ch, size, size), generator=gen).mul(2).sub(1).cuda() for _ in range(3)] for _ in range(3)]
+    out = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(1)
+        au, im = M.get_au(size, ch, 512).cuda(), M.get_im(size, ch, 512).cuda()
+        tr = U.DataParallelMock(T.GIMImgTrainer(tempfile.mkdtemp(), 5, 5, 5, au, im, 1e-4, 1e-4, 1e-6, reg_param=0.0))
+        graphed = GraphedIteration(tr, *batches[0], warmup=2) if mode == "graph" else None
+        assert tr.module.global_step == -1                 # warm-up left no trace
+        torch.manual_seed(123)                            # the noise stream of the three iterations
+        torch.cuda.manual_seed(123)
+        losses = []
+        for leaked, real, si in batches:
+            if graphed is not None:
+                o = graphed(leaked, real, si)
+                losses.append([float(o[0]), float(o[1])])
+            else:
+                tr.module.do_global_step()
+                tr.module.update_learning_rate()
+                im_loss, fake, _ = S.im_train_step(tr, leaked, si)
+                o = S.au_train_step(tr, real, fake, si)
+                losses.append([float(im_loss), float(o[0])])
+        assert tr.module.global_step == 2
+        out[mode] = (np.asarray(losses), {k: v.detach().clone() for k, v in list(au.state_dict().items()) + [("im." + k2, v2) for k2, v2 in im.state_dict().items()]})
+        del tr, au, im, graphed
+        torch.cuda.empty_cache()
+    le, lg = out["eager"][0], out["graph"][0]
+    print("losses eager", le.tolist(), "graph", lg.tolist())
+    # the noise z comes from the CUDA generator: a captured graph consumes it through the graph-safe philox offset, the eager path
+    # directly -- same seed, same offsets, same numbers
+    assert np.abs(le - lg).max() <= tol * np.abs(le).max()
+    worst = max(rel_err(out["graph"][1][k], v) for k, v in out["eager"][1].items())
+    assert worst <= tol, worst
