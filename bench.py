@@ -13,8 +13,10 @@ Rank 0 prints ONE JSON line on stdout (everything else goes to stderr):
   value            whole-job episodes/s, inputs resident in HBM
   e2e              the same through the public API with pinned-host inputs copied in and the losses read back every step
   roofline         the dominant kernel (tcgen05 implicit-GEMM conv forward/input-gradient) against the measured bf16 peak
-  secondary        BASELINE configs[2] (VoxCeleb2-shaped 3x64x64, R1 reg=10): weak scaling at 32 episodes/GPU and strong scaling
-                   at the published global batch of 128 episodes (128/N per GPU), same timing rules
+  secondary        BASELINE configs[2] (VoxCeleb2-shaped 3x64x64, R1 reg=10): weak scaling at 128 episodes/GPU and strong scaling
+                   at the reference's global batch of 128 episodes (128/N per GPU) -- SURVEY.md section 8d config 3 --, same timing rules
+  other_configs    BASELINE configs[0]/[3] (Gaussian GIM d = 10 / 1000, batch sweep, device-side episode synthesis) at every N, and the
+                   authenticator-only forward+backward at 1x105x105 (N = 1)
   cpu_baseline     the reference's own trainer (oracle/_ref, kind "reference"; else the oracle port, kind "port") on this box's
                    host cores: B=8, 2 warm-up + 5 timed iterations; N=1 only
   gpu_eager_baseline  the same unmodified reference code with device='cuda' (eager PyTorch/cuDNN, default fp32 flags) at the
@@ -43,7 +45,7 @@ WORKLOADS = {
     "O": (32, 1, 0.0, 1e-6, 1e-5, 1e-7, 281.0, "GIM Omniglot-shaped 1x32x32 m=n=k=5 reg=0 (BASELINE configs[1] at the reference's Omniglot resolution)"),
     "V": (64, 3, 10.0, 1e-4, 1e-4, 1e-6, 494.0, "GIM VoxCeleb2-shaped 3x64x64 m=n=k=5 R1 reg=10 (BASELINE configs[2])"),
 }
-DEFAULT_BATCH = {"O": 128, "V": 32}
+DEFAULT_BATCH = {"O": 128, "V": 128}
 M_, N_, K_ = 5, 5, 5
 STYLE = 512
 METRIC = "GIM train episodes/sec (fwd+bwd G+D)"
@@ -56,7 +58,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="O", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="episodes per GPU per step (default 128 for O, 32 for V)")
+    ap.add_argument("--batch", type=int, default=0, help="episodes per GPU per step (default 128)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -370,6 +372,71 @@ def measure_workload(args, D, workload, B, want_roofline, sample_clocks):
     return res
 
 
+def measure_gaussian(args, D, d, batch):
+    """BASELINE configs[0] / configs[3]: Gaussian GIM training (m=1, n=5, k=10, prior sigma 10, source sigma 1, lr 1e-4), episodes
+    synthesised on the device, the whole iteration (synthesis + G-step + D-step + both Adam updates) one CUDA-graph replay."""
+    import torch
+    import optimalstrategiesagainstgenerativeattacks_b200 as gim
+    from optimalstrategiesagainstgenerativeattacks_b200 import ddp, ops
+    from optimalstrategiesagainstgenerativeattacks_b200 import gim_gaussian_models as GM
+    from optimalstrategiesagainstgenerativeattacks_b200.gim_gaussian_trainer import GIMGaussianTrainer
+    from optimalstrategiesagainstgenerativeattacks_b200.gim_gaussian_training import _GraphedGaussianIteration
+    from optimalstrategiesagainstgenerativeattacks_b200.utils import DataParallelMock
+    m, n, k = 1, 5, 10
+    gim.set_precision(args.precision)
+    torch.manual_seed(1)
+    au, im = GM.get_au(d).to(D.dev), GM.get_im(d).to(D.dev)
+    tr = DataParallelMock(GIMGaussianTrainer(tempfile.mkdtemp(prefix="gim_bench_"), m, n, k, au, im, 1e-4, 1e-4, reg_param=0.0))
+    if D.world > 1:
+        ddp.attach(tr.module.authenticator_opt)
+        ddp.attach(tr.module.impersonator_opt)
+    torch.manual_seed(1000 + D.rank)
+
+    def sample():
+        mu, (real, leaked, si) = ops.gaussian_episodes(batch, (n, m, k), d, 10.0, 1.0, D.dev)
+        return mu, (leaked, real, si)
+    graphed = _GraphedGaussianIteration(tr, sample, warmup=2)
+    for _ in range(3):
+        graphed()
+    steps = max(args.steps, 20)
+    ms = D.timed(lambda s: graphed(), steps)
+    out = {"workload": "Gaussian GIM d=%d m=1 n=5 k=10" % d, "episodes_per_gpu_per_step": batch, "value": batch * D.world * steps / (ms * 1e-3), "unit": "episodes/s",
+           "ms_per_step": ms / steps, "steps": steps, "statistics_bytes_read_per_D_forward": batch * (n + k) * d * 4}
+    del graphed, tr, au, im
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_authenticator_105(args, D, batch=32):
+    """SURVEY.md section 8d config 2's second number: authenticator-only forward + backward at the native Omniglot resolution 1x105x105
+    (the reference Impersonator cannot run there), n = k = 5, 282.5 GFLOP per episode.  Odd stage sizes (105, 52, 26, 13, 6)."""
+    import torch
+    import optimalstrategiesagainstgenerativeattacks_b200 as gim
+    from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_models as M
+    from optimalstrategiesagainstgenerativeattacks_b200 import ops
+    gim.set_precision(args.precision)
+    torch.manual_seed(1)
+    au = M.get_au(105, 1, STYLE).to(D.dev).train()
+    g = torch.Generator().manual_seed(99)
+    test, si = ((torch.rand((batch, 5, 1, 105, 105), generator=g) * 2 - 1).to(D.dev) for _ in range(2))
+
+    def step(_):
+        au.zero_grad(set_to_none=True)
+        loss = ops.BCEWithLogitsFn.apply(au(test, si), 1.0).mean()
+        with ops.deferred_weight_grads():
+            loss.backward()
+    for s in range(3):
+        step(s)
+    steps = min(args.steps, 10)
+    ms = D.timed(step, steps)
+    eps = batch * D.world * steps / (ms * 1e-3)
+    out = {"workload": "GIMFaceAuthenticator forward+backward, 1x105x105, n=k=5 (eager launches, no graph)", "episodes_per_gpu_per_step": batch, "value": eps,
+           "unit": "episodes/s", "ms_per_step": ms / steps, "algorithmic_gflop_per_episode": 282.5, "model_tflops_per_gpu": 282.5e-3 * eps / D.world}
+    del au
+    torch.cuda.empty_cache()
+    return out
+
+
 def block_of(res, world, steps, warmup):
     return {"workload": res["desc"], "value": res["eps"], "unit": "episodes/s", "ms_per_step": res["ms_total"] / steps, "episodes_per_gpu_per_step": res["B"],
             "global_batch": res["B"] * world, "steps": steps, "warmup": warmup, "cuda_graph": res["graph"],
@@ -395,10 +462,18 @@ def run_ours(args):
         weak = measure_workload(args, D, "V", DEFAULT_BATCH["V"], want_roofline=False, sample_clocks=False)
         secondary.update(block_of(weak, world, args.steps, warm))
         secondary["scaling"] = "weak"
-        if 128 % world == 0:
+        if world == 1:
+            secondary["strong_scaling_global_batch_128"] = dict(secondary, scaling="strong")      # at N = 1 the two rows coincide
+        elif 128 % world == 0:
             strong = measure_workload(args, D, "V", 128 // world, want_roofline=False, sample_clocks=False)
             secondary["strong_scaling_global_batch_128"] = block_of(strong, world, args.steps, warm)
             secondary["strong_scaling_global_batch_128"]["scaling"] = "strong"
+
+    extra = None
+    if not args.no_secondary and args.workload == "O" and args.precision == "bf16":
+        extra = {"gaussian": [measure_gaussian(args, D, d, b) for d, b in ((10, 4096), (1000, 4096), (1000, 16384), (1000, 65536))]}
+        if world == 1:
+            extra["authenticator_105x105"] = measure_authenticator_105(args, D)
 
     if rank != 0:
         return None
@@ -450,6 +525,8 @@ def run_ours(args):
     }
     if secondary is not None:
         line["secondary"] = secondary
+    if extra is not None:
+        line["other_configs"] = extra
     if world == 1:                                        # baselines are reported on rank 0 at N=1 only
         if not args.no_gpu_baseline:
             try:

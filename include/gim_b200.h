@@ -241,8 +241,17 @@ int gim_set_center_add(const float* x, const float* add, float* y, int b, int s,
  * (replaces the host-side torch.normal calls of training/gim_gaussian_training.py:71-86) */
 int gim_affine_rows(const float* x, const float* add, float* y, int b, int s, int d, float alpha, float beta, gim_stream_t stream);
 
+/* ---- ImgAttention blend (model_blocks.py:596-608): per pixel s_i = <q_i, k_i> over the c channels, (a1, a2) = softmax(s1, s2),
+ * out = a1 * x1 + a2 * v2; all tensors NHWC fp32 [pixels][c], att [pixels][2].  Backward: gx1 may be NULL (x1 is an input image). ---- */
+int gim_img_att_blend_fwd(const float* q1, const float* k1, const float* q2, const float* k2, const float* x1, const float* v2, float* out, float* att,
+                          long long pixels, int c, gim_stream_t stream);
+int gim_img_att_blend_bwd(const float* g, const float* q1, const float* k1, const float* q2, const float* k2, const float* x1, const float* v2,
+                          const float* att, float* gq1, float* gk1, float* gq2, float* gk2, float* gx1, float* gv2, long long pixels, int c,
+                          gim_stream_t stream);
+
 /* ---- encoder tail: AdaptiveMaxPool2d((1,1)) (gim_img_models.py:53-54) ---- */
-int gim_gmax_fwd(const void* x, float* y, int32_t* idx, int n, int hw, int c, int dtype, gim_stream_t stream);
+/* y[n][c] = LeakyReLU_slope(max_p x[n][p][c]), idx = first arg-max (slope 1: plain max) -- the encoder tail in one pass */
+int gim_gmax_fwd(const void* x, float* y, int32_t* idx, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
 int gim_gather_idx(const void* x, const int32_t* idx, float* y, int n, int hw, int c, int dtype, gim_stream_t stream);
 int gim_scatter_idx(const float* g, const int32_t* idx, void* gx, int n, int hw, int c, int dtype, gim_stream_t stream);
 

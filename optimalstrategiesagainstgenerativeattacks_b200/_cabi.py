@@ -70,8 +70,10 @@ PROTOTYPES = {
     "gim_set_stats_bwd": "ppippiiiffp",
     "gim_set_std_bwd_bwd": "ppippp" + "iiifp",
     "gim_set_center_add": "pppiiiip",
+    "gim_img_att_blend_fwd": "pppppppplip",
+    "gim_img_att_blend_bwd": "pppppppppppppplip",
     "gim_affine_rows": "pppiiiffp",
-    "gim_gmax_fwd": "pppiiiip",
+    "gim_gmax_fwd": "pppiiifip",
     "gim_gather_idx": "pppiiiip",
     "gim_scatter_idx": "pppiiiip",
     "gim_bce_logits_fwd": "pfplp",

@@ -110,9 +110,48 @@ __global__ void __launch_bounds__(256) affine_rows_kernel(const float* x, const 
     }
 }
 
+// ImgAttention blend (reference models/model_blocks.py:596-608), one thread per pixel, c = image channels (1 or 3):
+//   s1 = <q1, k1>, s2 = <q2, k2> over channels; (a1, a2) = softmax(s1, s2); out = a1 * x1 + a2 * v2
+__global__ void __launch_bounds__(256) img_att_blend_fwd_kernel(const float* __restrict__ q1, const float* __restrict__ k1, const float* __restrict__ q2,
+                                                                const float* __restrict__ k2, const float* __restrict__ x1, const float* __restrict__ v2,
+                                                                float* __restrict__ out, float* __restrict__ att, long long pixels, int c) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pixels) return;
+    const long long o = p * c;
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < c; ++j) { s1 = fmaf(q1[o + j], k1[o + j], s1); s2 = fmaf(q2[o + j], k2[o + j], s2); }
+    const float m = fmaxf(s1, s2), e1 = expf(s1 - m), e2 = expf(s2 - m), inv = 1.f / (e1 + e2);
+    const float a1 = e1 * inv, a2 = e2 * inv;
+    att[2 * p] = a1;
+    att[2 * p + 1] = a2;
+    for (int j = 0; j < c; ++j) out[o + j] = a1 * x1[o + j] + a2 * v2[o + j];
+}
+// d a1 = <g, x1>, d a2 = <g, v2>;  d s1 = a1 (d a1 - (a1 d a1 + a2 d a2)), d s2 likewise;  d q1 = d s1 k1, ...;  d x1 = a1 g, d v2 = a2 g
+__global__ void __launch_bounds__(256) img_att_blend_bwd_kernel(const float* __restrict__ g, const float* __restrict__ q1, const float* __restrict__ k1,
+                                                                const float* __restrict__ q2, const float* __restrict__ k2, const float* __restrict__ x1,
+                                                                const float* __restrict__ v2, const float* __restrict__ att, float* __restrict__ gq1,
+                                                                float* __restrict__ gk1, float* __restrict__ gq2, float* __restrict__ gk2,
+                                                                float* __restrict__ gx1, float* __restrict__ gv2, long long pixels, int c) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pixels) return;
+    const long long o = p * c;
+    const float a1 = att[2 * p], a2 = att[2 * p + 1];
+    float d1 = 0.f, d2 = 0.f;
+    for (int j = 0; j < c; ++j) { d1 = fmaf(g[o + j], x1[o + j], d1); d2 = fmaf(g[o + j], v2[o + j], d2); }
+    const float dot = a1 * d1 + a2 * d2, ds1 = a1 * (d1 - dot), ds2 = a2 * (d2 - dot);
+    for (int j = 0; j < c; ++j) {
+        gq1[o + j] = ds1 * k1[o + j];
+        gk1[o + j] = ds1 * q1[o + j];
+        gq2[o + j] = ds2 * k2[o + j];
+        gk2[o + j] = ds2 * q2[o + j];
+        if (gx1) gx1[o + j] = a1 * g[o + j];
+        gv2[o + j] = a2 * g[o + j];
+    }
+}
+
 // grid (ceil(c/32), n), block (32, 8): max over the hw pixels + first arg-max
 template <typename T>
-__global__ void __launch_bounds__(256) gmax_fwd_kernel(const T* __restrict__ x, float* __restrict__ y, int32_t* __restrict__ idx, int hw, int c) {
+__global__ void __launch_bounds__(256) gmax_fwd_kernel(const T* __restrict__ x, float* __restrict__ y, int32_t* __restrict__ idx, int hw, int c, float slope) {
     __shared__ float shv[8][33];
     __shared__ int shi[8][33];
     int ch = blockIdx.x * 32 + threadIdx.x;
@@ -135,7 +174,7 @@ __global__ void __launch_bounds__(256) gmax_fwd_kernel(const T* __restrict__ x, 
             int p = shi[j][threadIdx.x];
             if (v > best || (v == best && p < bi)) { best = v; bi = p; }
         }
-        y[img * c + ch] = best;
+        y[img * c + ch] = lrelu_f(best, slope);          // the encoder's output LeakyReLU (gim_img_models.py:55-56) rides along; slope 1 = none
         idx[img * c + ch] = bi;
     }
 }
@@ -235,11 +274,23 @@ int gim_affine_rows(const float* x, const float* add, float* y, int b, int s, in
     affine_rows_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)st>>>(x, add, y, total, s, d, alpha, beta);
     return check_launch("affine_rows");
 }
-int gim_gmax_fwd(const void* x, float* y, int32_t* idx, int n, int hw, int c, int dtype, gim_stream_t st) {
+int gim_img_att_blend_fwd(const float* q1, const float* k1, const float* q2, const float* k2, const float* x1, const float* v2, float* out, float* att,
+                          long long pixels, int c, gim_stream_t st) {
+    if (pixels <= 0 || c <= 0) return GIM_OK;
+    img_att_blend_fwd_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, (cudaStream_t)st>>>(q1, k1, q2, k2, x1, v2, out, att, pixels, c);
+    return check_launch("img_att_blend_fwd");
+}
+int gim_img_att_blend_bwd(const float* g, const float* q1, const float* k1, const float* q2, const float* k2, const float* x1, const float* v2,
+                          const float* att, float* gq1, float* gk1, float* gq2, float* gk2, float* gx1, float* gv2, long long pixels, int c, gim_stream_t st) {
+    if (pixels <= 0 || c <= 0) return GIM_OK;
+    img_att_blend_bwd_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, (cudaStream_t)st>>>(g, q1, k1, q2, k2, x1, v2, att, gq1, gk1, gq2, gk2, gx1, gv2, pixels, c);
+    return check_launch("img_att_blend_bwd");
+}
+int gim_gmax_fwd(const void* x, float* y, int32_t* idx, int n, int hw, int c, float slope, int dtype, gim_stream_t st) {
     if (n <= 0 || c <= 0) return GIM_OK;
     GIM_REQUIRE(hw >= 1 && n <= 65535, "gmax: bad shape");
     dim3 grid((c + 31) / 32, n), block(32, 8);
-    GIM_DISPATCH_DTYPE(dtype, (gmax_fwd_kernel<T><<<grid, block, 0, (cudaStream_t)st>>>((const T*)x, y, idx, hw, c)));
+    GIM_DISPATCH_DTYPE(dtype, (gmax_fwd_kernel<T><<<grid, block, 0, (cudaStream_t)st>>>((const T*)x, y, idx, hw, c, slope)));
     return check_launch("gmax_fwd");
 }
 int gim_gather_idx(const void* x, const int32_t* idx, float* y, int n, int hw, int c, int dtype, gim_stream_t st) {

@@ -61,8 +61,7 @@ class Encoder(nn.Module):
             x = block(x, want_ops=i + 1 < self.n_down_blocks)       # the next consumer reads the bf16 operands
         if isinstance(x, ops.Act):
             x = x.t32
-        x = ops.GlobalMaxFn.apply(x)
-        return ops.lrelu(x) if self.use_out_lrelu else x
+        return ops.GlobalMaxFn.apply(x, 0.2 if self.use_out_lrelu else 1.0)      # global max + LeakyReLU in one pass
 
 
 class EnvDecoder(nn.Module):
@@ -257,8 +256,8 @@ class GIMFaceImpersonator(nn.Module, _EncodeMixin):
         exp_nhwc = ops.to_nhwc(expanded_img.reshape(batch_size * n, img_channels, img_size, img_size))
         x = self.generate_img(env_img=NHWC(ops.CatChannelsFn.apply(env_img, exp_nhwc)), src=src, n=n)
 
-        if self.use_img_att:
-            x = self.img_att(x1=expanded_img.reshape(batch_size * n, *expanded_img.size()[2:]), x2=x.view(batch_size * n, *x.size()[2:]))
+        if self.use_img_att:                               # reference :392-396 (non-default)
+            x = ops.from_nhwc(self.img_att(x1=exp_nhwc, x2=ops.to_nhwc(x.reshape(batch_size * n, *x.size()[2:]))))
             x = x.view(batch_size, n, *x.size()[1:])
         return x
 

@@ -9,8 +9,11 @@ Changed for a GPU that runs > 2000 episodes/s:
     iterations (the reference calls `.item()` a dozen times per iteration in its Gaussian loop and per log interval here);
   * with `use_cuda_graph=True` (and n_au_steps == 1) the whole G+D iteration is one CUDA-graph replay (`cuda_graph.GraphedIteration`);
   * several GPUs = one process per GPU under torchrun (`ddp.attach`), not nn.DataParallel: `device_ids` lists the local device only;
-  * the image grids of `sample_and_save_imgs` (:34-73, PIL / tensorboard) are not produced.
-`logger` is anything with `add_scalar(category=, k=, v=, global_step=)`; `ScalarLog` below keeps the values in memory.
+  * the image grids of `sample_and_save_imgs` (:34-73) go to `logger.add_imgs` (kept signature); `ScalarLog` tiles them into one
+    grid and, given an `img_dir`, writes `<img_dir>/<category>/<k>/<step>.png` like the reference's Logger -- with a 30-line PNG
+    encoder instead of torchvision / PIL, from one device-to-host copy per grid.
+`logger` is anything with `add_scalar(category=, k=, v=, global_step=)` (+ `add_imgs` for the grids); `ScalarLog` below keeps the
+values in memory.
 """
 import itertools
 import os
@@ -25,14 +28,83 @@ from .training_steps import au_eval_step, au_train_step, im_eval_step, im_train_
 from .utils import DataParallelMock, get_device
 
 
-class ScalarLog:
-    """Minimal stand-in for the reference's Logger (training/logger.py): records add_scalar calls."""
+def make_grid(imgs, nrow=5, padding=2):
+    """[n, C, H, W] in [0, 1] -> one [C, rows*(H+pad)+pad, cols*(W+pad)+pad] tile image (torchvision.utils.make_grid's layout, which
+    the reference's Logger.add_imgs uses, training/logger.py:43-52)."""
+    imgs = imgs.detach().float().cpu()
+    n, c, h, w = imgs.shape
+    cols = min(nrow, n)
+    rows = (n + cols - 1) // cols
+    grid = torch.zeros((c, rows * (h + padding) + padding, cols * (w + padding) + padding))
+    for i in range(n):
+        r, q = divmod(i, cols)
+        y0, x0 = padding + r * (h + padding), padding + q * (w + padding)
+        grid[:, y0:y0 + h, x0:x0 + w] = imgs[i]
+    return grid
 
-    def __init__(self):
+
+def write_png(path, img):
+    """Minimal PNG encoder (8-bit gray or RGB, no dependencies): img [C, H, W] float in [0, 1], C in (1, 3)."""
+    import struct
+    import zlib
+    c, h, w = img.shape
+    if c not in (1, 3):
+        raise ValueError("write_png: 1 or 3 channels")
+    data = (img.clamp(0, 1) * 255.0 + 0.5).to(torch.uint8).permute(1, 2, 0).contiguous().numpy()
+    raw = b"".join(b"\x00" + data[y].tobytes() for y in range(h))
+
+    def chunk(tag, payload):
+        body = tag + payload
+        return struct.pack(">I", len(payload)) + body + struct.pack(">I", zlib.crc32(body) & 0xffffffff)
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0 if c == 1 else 2, 0, 0, 0)) + \
+        chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(png)
+
+
+class ScalarLog:
+    """Minimal stand-in for the reference's Logger (training/logger.py): records add_scalar / add_imgs calls; with `img_dir` the image
+    grids are also written as PNG files in the reference's directory layout."""
+
+    def __init__(self, img_dir=None):
         self.scalars = {}
+        self.images = {}
+        self.img_dir = img_dir
 
     def add_scalar(self, category, k, v, global_step):
         self.scalars.setdefault((category, k), []).append((int(global_step), float(v)))
+
+    def add_imgs(self, imgs, category, k, global_step, nrow=5):
+        grid = make_grid(imgs, nrow=nrow)
+        self.images[(category, k)] = (int(global_step), grid)
+        if self.img_dir is not None:
+            outdir = os.path.join(self.img_dir, category, k)
+            os.makedirs(outdir, exist_ok=True)
+            write_png(os.path.join(outdir, '%08d.png' % global_step), grid)
+
+
+def save_imgs(logger, img_sample, category, k, global_step):
+    """Reference :21-31: the first episode's images, [-1, 1] -> [0, 1], as one grid."""
+    imgs_for_save = (img_sample[0].clamp(-1, 1) + 1) / 2.0
+    logger.add_imgs(imgs=imgs_for_save, category=category, k=k, global_step=global_step)
+
+
+def sample_and_save_imgs(device, logger, trainer, ds, ds_prefix, indices, dbg=False):
+    """Reference :34-73: for the listed episodes, the leaked sample and what the attacker makes of it (plus real / si when dbg)."""
+    if ds is None or not hasattr(logger, "add_imgs"):
+        return
+    with torch.no_grad():
+        global_step = trainer.module.get_global_step()
+        for idx in indices:
+            data = ds[idx]
+            category = "{} imgs_{:04}".format(ds_prefix, idx)
+            leaked_sample = data["leaked_sample"].unsqueeze(0).to(device)
+            fake_sample = trainer.forward(mode='impersonator_sample', leaked_sample=leaked_sample)
+            save_imgs(logger=logger, img_sample=leaked_sample, category=category, k="leaked", global_step=global_step)
+            save_imgs(logger=logger, img_sample=fake_sample, category=category, k="impersonator", global_step=global_step)
+            if dbg:
+                save_imgs(logger=logger, img_sample=data["real_sample"].unsqueeze(0).to(device), category=category, k="real", global_step=global_step)
+                save_imgs(logger=logger, img_sample=data["si_sample"].unsqueeze(0).to(device), category=category, k="si", global_step=global_step)
 
 
 def _batches(ds, batch_size, shuffle, num_workers, drop_last=True):
@@ -153,6 +225,9 @@ def train_epoch(device, logger, epoch, trainer, train_ds, val_ds, train_batch_si
             _log_encodings(trainer, logger, real_sample, si_sample, fake_sample, global_step)
         if global_step % save_every == 0:
             _save_rank0(trainer, epoch)
+        if global_step % save_imgs_every == 0:
+            sample_and_save_imgs(device=device, logger=logger, trainer=trainer, ds=train_ds, ds_prefix='train', indices=train_eval_indices, dbg=dbg)
+            sample_and_save_imgs(device=device, logger=logger, trainer=trainer, ds=val_ds, ds_prefix='val', indices=val_eval_indices, dbg=dbg)
         if global_step % eval_every == 0 and val_ds is not None:
             eval_step(device=device, trainer=trainer, ds=val_ds, logger=logger, batch_size=val_batch_size)
 

@@ -222,8 +222,8 @@ class ImgAttConvBlock(nn.Module):
 
 
 class ImgAttention(nn.Module):
-    """Reference model_blocks.py:583-608.  The CLI default is use_img_att=False (train_gim_on_imgs.py); the blend itself
-    (channel dot products + 2-way softmax) is not on the north-star path and is not implemented."""
+    """Reference model_blocks.py:583-608 (use_img_att=True; the CLI default is False): five ImgAttConvBlocks produce two queries, two
+    keys and a value image, a per-pixel 2-way softmax over the channel dot products blends the leaked image x1 with the value image."""
 
     def __init__(self, img1_channels, img2_channels):
         super().__init__()
@@ -234,7 +234,12 @@ class ImgAttention(nn.Module):
         self.v2conv = ImgAttConvBlock(img2_channels, img1_channels)
 
     def forward(self, x1, x2):
-        raise NotImplementedError("use_img_att=True is outside the hot path this build covers (SURVEY.md section 2)")
+        """x1, x2: NHWC fp32 activations [n, h, w, c1], [n, h, w, c2] -> [n, h, w, c1]."""
+        sn_prepare_module(self)
+        x = ops.CatChannelsFn.apply(x1, x2)
+        q1, q2 = self.q1conv(x), self.q2conv(x)
+        k1, k2, v2 = self.k1conv(x1), self.k2conv(x2), self.v2conv(x2)
+        return ops.ImgAttBlendFn.apply(q1, k1, q2, k2, x1, v2)
 
 
 class ResBlockUp(nn.Module):

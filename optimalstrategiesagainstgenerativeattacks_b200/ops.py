@@ -1205,6 +1205,34 @@ class CatChannelsFn(Function):
         return ga, gb
 
 
+class ImgAttBlendFn(Function):
+    """ImgAttention's blend (reference model_blocks.py:596-608) on NHWC fp32 tensors [n, h, w, c]: per pixel the two channel dot products
+    <q1, k1>, <q2, k2>, their 2-way softmax and out = a1 * x1 + a2 * v2 -- one kernel forward, one backward (first order: attacker only)."""
+
+    @staticmethod
+    def forward(ctx, q1, k1, q2, k2, x1, v2):
+        q1, k1, q2, k2, x1, v2 = (_c(t) for t in (q1, k1, q2, k2, x1, v2))
+        c = x1.shape[-1]
+        pixels = x1.numel() // c
+        out = torch.empty_like(x1)
+        att = _empty(x1.shape[:-1] + (2,), torch.float32, x1)
+        C.call("gim_img_att_blend_fwd", C.ptr(q1), C.ptr(k1), C.ptr(q2), C.ptr(k2), C.ptr(x1), C.ptr(v2), C.ptr(out), C.ptr(att), pixels, c)
+        ctx.save_for_backward(q1, k1, q2, k2, x1, v2, att)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        q1, k1, q2, k2, x1, v2, att = ctx.saved_tensors
+        g = _c(g)
+        c = x1.shape[-1]
+        gq1, gk1, gq2, gk2, gv2 = (torch.empty_like(x1) for _ in range(5))
+        gx1 = torch.empty_like(x1) if ctx.needs_input_grad[4] else None
+        C.call("gim_img_att_blend_bwd", C.ptr(g), C.ptr(q1), C.ptr(k1), C.ptr(q2), C.ptr(k2), C.ptr(x1), C.ptr(v2), C.ptr(att),
+               C.ptr(gq1), C.ptr(gk1), C.ptr(gq2), C.ptr(gk2), C.ptr(gx1), C.ptr(gv2), x1.numel() // c, c)
+        return gq1, gk1, gq2, gk2, gx1, gv2
+
+
 # ------------------------------------------------------------------------------------------------------------
 # InstanceNorm2d / ada_in (attacker only: first order)
 # ------------------------------------------------------------------------------------------------------------
@@ -1633,23 +1661,30 @@ class SetCenterAddFn(Function):
 # encoder tail, losses
 # ------------------------------------------------------------------------------------------------------------
 class GlobalMaxFn(Function):
-    """AdaptiveMaxPool2d((1,1)) + flatten (gim_img_models.py:53-54): NHWC activation -> fp32 [n, c]."""
+    """AdaptiveMaxPool2d((1,1)) + flatten (+ the encoder's output LeakyReLU when slope != 1) -- gim_img_models.py:53-56 -- in one pass:
+    NHWC activation -> fp32 [n, c].  The backward is built from differentiable operators (mask, scatter), so it stays twice differentiable."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, slope=1.0):
         x = _c(x)
         n, h, w, c = x.shape
         y = _empty((n, c), torch.float32, x)
         idx = _empty((n, c), torch.int32, x)
-        C.call("gim_gmax_fwd", C.ptr(x), C.ptr(y), C.ptr(idx), n, h * w, c, C.dtype_code(x))
+        C.call("gim_gmax_fwd", C.ptr(x), C.ptr(y), C.ptr(idx), n, h * w, c, float(slope), C.dtype_code(x))
         ctx.shape = x.shape
         ctx.dtype = x.dtype
         ctx.idx = idx
+        ctx.slope = float(slope)
+        if slope != 1.0:
+            ctx.save_for_backward(y)
         return y
 
     @staticmethod
     def backward(ctx, g):
-        return ScatterIdxFn.apply(g, ctx.idx, ctx.shape, ctx.dtype)
+        if ctx.slope != 1.0:
+            (y,) = ctx.saved_tensors
+            g = LReluBwdFn.apply(g, y.detach(), ctx.slope)
+        return ScatterIdxFn.apply(g, ctx.idx, ctx.shape, ctx.dtype), None
 
 
 class ScatterIdxFn(Function):

@@ -147,8 +147,8 @@ def case_au(size, ch, sd_dim, b, n, k, seed, with_grads=True):
     return res
 
 
-def case_im(size, ch, sd_dim, b, m, n, seed, with_grads=True):
-    im = load(ref_img.get_im(size, ch, sd_dim), seed)
+def case_im(size, ch, sd_dim, b, m, n, seed, with_grads=True, use_img_att=False):
+    im = load(ref_img.get_im(size, ch, sd_dim, use_img_att=use_img_att), seed)
     im.train()
     leaked = seeded((b, m, ch, size, size), seed + 1, 0.5, 1.0)
     z = seeded((b, n, sd_dim), seed + 3)
@@ -326,6 +326,7 @@ def main():
     cases = {
         "au_s16": lambda: case_au(16, 3, 64, 2, 3, 2, 11),
         "im_s16": lambda: case_im(16, 3, 64, 2, 2, 3, 21),
+        "im_s16_att": lambda: case_im(16, 3, 64, 2, 2, 3, 221, use_img_att=True),
         "steps_s16_r1": lambda: case_img_steps(16, 3, 64, 2, 2, 3, 2, 10.0, 2, 31),
         "steps_s16_noreg": lambda: case_img_steps(16, 3, 64, 2, 2, 3, 2, 0.0, 2, 41),
         "au_O": lambda: case_au(32, 1, 512, 1, 2, 2, 51, with_grads=False),

@@ -187,3 +187,32 @@ def test_reference_archive_is_importable_when_built():
     assert "training/gim_img_trainer.py" in names and "models/gim_img_models.py" in names
     assert not [n for n in names if not n.endswith(".py")]
     assert os.path.getsize(path) < 1 << 20
+
+
+def test_image_grid_and_png_writer(tmp_path):
+    """sample_and_save_imgs' host side (reference training/gim_img_training.py:21-73, logger.py:43-52): grid layout and a valid PNG."""
+    import struct
+    import zlib
+    from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_training as T
+    imgs = torch.rand(7, 3, 6, 5)
+    grid = T.make_grid(imgs, nrow=5, padding=2)
+    assert grid.shape == (3, 2 * 8 + 2, 5 * 7 + 2)
+    assert torch.equal(grid[:, 2:8, 2:7], imgs[0]) and torch.equal(grid[:, 10:16, 9:14], imgs[6]) and float(grid[:, :2].abs().max()) == 0
+    log = T.ScalarLog(img_dir=str(tmp_path))
+    T.save_imgs(log, (imgs * 2 - 1).unsqueeze(0), "train imgs_0003", "leaked", 12)
+    path = tmp_path / "train imgs_0003" / "leaked" / "00000012.png"
+    raw = path.read_bytes()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, {}
+    while pos < len(raw):
+        n, tag = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xffffffff
+        chunks[tag] = body
+        pos += 12 + n
+    w, h, depth, ctype = struct.unpack(">IIBB", chunks[b"IHDR"][:10])
+    assert (w, h, depth, ctype) == (37, 18, 8, 2)
+    rows = zlib.decompress(chunks[b"IDAT"])
+    pix = np.frombuffer(rows, dtype=np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
+    want = (log.images[("train imgs_0003", "leaked")][1].clamp(0, 1) * 255 + 0.5).to(torch.uint8).permute(1, 2, 0).numpy()
+    assert np.array_equal(pix, want) and np.abs(want[2:8, 2:7].astype(float) / 255 - imgs[0].permute(1, 2, 0).numpy()).max() < 3e-3

@@ -283,15 +283,20 @@ def test_global_max_bce_rows():
     got = ops.lrelu(ops.GlobalMaxFn.apply(x))
     assert rel_err(got, ref) < 1e-6
     probe = rnd(3, 40, seed=2)
+    # the one-pass encoder tail (max + LeakyReLU in the same kernel) gives the same values, first and second order
+    xf = to_dev_nhwc(x64.detach(), torch.float32)
+    fused = ops.GlobalMaxFn.apply(xf, 0.2)
+    assert torch.equal(fused, got.detach())
+    (gf,) = torch.autograd.grad((fused * probe.float().cuda()).sum(), xf, create_graph=True)
     (gr,) = torch.autograd.grad((ref * probe).sum(), x64)
     (gg,) = torch.autograd.grad((got * probe.float().cuda()).sum(), x, create_graph=True)
-    assert rel_err(nchw(gg), gr) < 1e-6
+    assert rel_err(nchw(gg), gr) < 1e-6 and rel_err(nchw(gf), gr) < 1e-6
     # second order: scatter's backward is a gather of the same indices
     x64b = x64.detach().clone().requires_grad_()
     xb = to_dev_nhwc(x64b.detach(), torch.float32)
     (g1r,) = torch.autograd.grad(F.leaky_relu(torch.amax(x64b, dim=(2, 3)), 0.2).pow(2).sum(), x64b, create_graph=True)
     (g2r,) = torch.autograd.grad((g1r * x64b).sum(), x64b)
-    (g1,) = torch.autograd.grad(ops.lrelu(ops.GlobalMaxFn.apply(xb)).pow(2).sum(), xb, create_graph=True)
+    (g1,) = torch.autograd.grad(ops.GlobalMaxFn.apply(xb, 0.2).pow(2).sum(), xb, create_graph=True)
     (g2,) = torch.autograd.grad(ops.DotFn.apply(g1, xb).sum(), xb)
     assert rel_err(nchw(g1), g1r) < 1e-6 and rel_err(nchw(g2), g2r) < 1e-6
     z64 = rnd(11, 1, seed=3).requires_grad_()

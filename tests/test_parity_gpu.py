@@ -402,8 +402,8 @@ def test_training_loop_runs_logs_saves_and_resumes(schemas, tmp_path):
     classes = D.synthetic_classes(3, 8, 3, 16, seed=5) * 0.5
     mk = lambda seed: D.ResidentGIMDataSet(classes, m=2, n=2, k=2, example_cnt_per_class=2, device="cuda", seed=seed)
     common = dict(device_name="cuda", device_ids=[0], m=2, n=2, k=2, remove_noise_mean=True, au_lr=1e-4, im_lr=1e-4, beta1=0.0, beta2=0.99,
-                  env_noise_mapping_lr=1e-6, lr_gamma=0.3, milestones=(), batch_size=2, num_workers=0, save_every=2, eval_every=2, save_imgs_every=10 ** 9,
-                  train_eval_indices=[], val_eval_indices=[], n_au_steps=1)
+                  env_noise_mapping_lr=1e-6, lr_gamma=0.3, milestones=(), batch_size=2, num_workers=0, save_every=2, eval_every=2, save_imgs_every=3,
+                  train_eval_indices=[0, 4], val_eval_indices=[1], n_au_steps=1)
     torch.manual_seed(3)
     out = str(tmp_path / "run")
     trainer, log = T.train_gim_imgs(outdir=out, train_ds=mk(1), val_ds=mk(2), authenticator=M.get_au(16, 3, 64), impersonator=M.get_im(16, 3, 64),
@@ -412,6 +412,10 @@ def test_training_loop_runs_logs_saves_and_resumes(schemas, tmp_path):
     for key in (("train_losses", "dis_loss"), ("train_losses", "dis_reg"), ("train losses", "gen loss"), ("train_accuracy", "dis_acc"), ("lr", "au"),
                 ("eval losses", "dis loss"), ("eval accuracy", "dis acc"), ("train-au_src_std", "fake"), ("train-au_env_mean", "abs[fake-si]")):
         assert key in log.scalars and all(np.isfinite(v) for _, v in log.scalars[key]), key
+    # image grids of sample_and_save_imgs (reference :34-73): leaked sample + the attacker's output for the listed episodes
+    for key in (("train imgs_0000", "leaked"), ("train imgs_0004", "impersonator"), ("val imgs_0001", "impersonator")):
+        step, grid = log.images[key]
+        assert step == 3 and grid.shape[0] == 3 and grid.shape[1] == 16 + 4 and torch.isfinite(grid).all() and float(grid.max()) <= 1.0
     ckpts = sorted(os.listdir(os.path.join(out, "ckpts")))
     assert ckpts and ckpts[-1].endswith(".pt")
     # resume: the step counter and the weights come back
@@ -429,3 +433,104 @@ def test_training_loop_runs_logs_saves_and_resumes(schemas, tmp_path):
                   tb_log_enc_every=10 ** 9, n_au_steps=1, use_cuda_graph=True)
     vals = [v for _, v in log3.scalars[("train_losses", "dis_loss")]]
     assert len(vals) == 3 and all(np.isfinite(v) for v in vals) and tr3.module.global_step > step0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_impersonator_with_image_attention_vs_reference(schemas, prec):
+    """use_img_att=True (reference gim_img_models.py:392-396, model_blocks.py:551-608): five ImgAttConvBlocks + the per-pixel 2-way softmax
+    blend, against the unmodified reference in float64 -- generated images and every gradient tensor (img_att's included)."""
+    from conftest import sample_errs, sample_rows
+    g, M = pkg()[0], pkg()[1]
+    g.set_precision(prec)
+    gold = load_golden("im_s16_att")
+    s = schemas["s16"]
+    im = load(M.get_im(16, 3, 64, use_img_att=True), s["im"], 221).train()
+    leaked = seeded((2, 2, 3, 16, 16), 222, 0.5, 1.0).cuda()
+    z = seeded((2, 3, 64), 224).cuda()
+    with inject_randn([z]):
+        fake = im(leaked, 3, True)
+    assert fake.shape == (2, 3, 3, 16, 16) and rel_err(fake, gold["fake"]) < (2e-4 if prec == "fp32" else 2e-2)
+    (fake * seeded(tuple(fake.shape), 225).cuda()).sum().backward()
+    assert all(prm.grad is not None for prm in im.img_att.parameters())
+    err = sample_errs(sample_rows([p.grad for p in im.parameters()]), gold["gsamp"])
+    names = s["im_params"]
+    att = np.asarray([n_.startswith("img_att.") for n_ in names])
+    print("img_att %s: img_att tensors median %.2e max %.2e; all tensors median %.2e" % (prec, np.nanmedian(err[att]), np.nanmax(err[att]), np.nanmedian(err)))
+    if prec == "fp32":
+        assert np.nanmax(err[att]) < 2e-3 and np.nanmedian(err) < 2e-3
+    else:
+        assert np.nanmedian(err[att]) < 5e-2
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_gaussian_d1000_vs_reference(schemas, tmp_path, prec):
+    """BASELINE configs[3] width (d = 1000: the Linear layers run on the tcgen05 kernels in bf16): forward, input gradient, parameter
+    gradients (element samples) and two training iterations against the unmodified reference in float64."""
+    from conftest import sample_errs, sample_rows
+    g, _, GM, _, GT, S, U = pkg()
+    g.set_precision(prec)
+    tol = TOLS[prec]
+    gold = load_golden("gauss_d1000")
+    d, b, (m, n, k), seed = 1000, 8, (1, 5, 10), 191
+    au = load(GM.get_au(d), schemas["gauss1000"]["au"], seed)
+    im = load(GM.get_im(d), schemas["gauss1000"]["im"], seed + 10)
+    real = seeded((b, n, d), seed + 1).cuda().requires_grad_()
+    si = seeded((b, k, d), seed + 2).cuda()
+    out = au(real, si)
+    out.sum().backward()
+    assert rel_err(out, gold["au_out"]) < tol and rel_err(real.grad, gold["au_g_real"]) < (1e-4 if prec == "fp32" else tol)
+    err = sample_errs(sample_rows([p.grad for p in au.parameters()]), gold["au_gsamp"])
+    print("gauss d=1000 %s: parameter-gradient tensors rel err %s" % (prec, np.array2string(err, precision=2)))
+    assert np.nanmax(err) < (1e-4 if prec == "fp32" else tol)
+    au.zero_grad(set_to_none=True)
+    with inject_randn([seeded((b, n, d), seed + 3).cuda()]):
+        fake = im(seeded((b, m, d), seed + 5).cuda(), n, True)
+    assert rel_err(fake, gold["fake"]) < (1e-5 if prec == "fp32" else tol)
+    tr = U.DataParallelMock(GT.GIMGaussianTrainer(str(tmp_path), m, n, k, au, im, 1e-2, 1e-2, reg_param=0.0))
+    for it in range(2):
+        real = seeded((b, n, d), seed + 100 * it + 1).cuda()
+        si = seeded((b, k, d), seed + 100 * it + 2).cuda()
+        leaked = seeded((b, m, d), seed + 100 * it + 5).cuda()
+        tr.module.do_global_step()
+        with inject_randn([seeded((b, n, d), seed + 100 * it + 3).cuda()]):
+            im_loss, fake, _ = S.im_train_step(tr, leaked, si)
+        o = S.au_train_step(tr, real, fake, si)
+        ltol = 2e-4 if prec == "fp32" else tol
+        assert abs(im_loss.item() - gold["im_loss"][it]) < ltol * max(1.0, abs(gold["im_loss"][it])), (it, im_loss.item(), gold["im_loss"][it])
+        assert abs(o[0].item() - gold["au_loss"][it]) < ltol * max(1.0, abs(gold["au_loss"][it])), (it, o[0].item(), gold["au_loss"][it])
+    if prec == "fp32":
+        perr = sample_errs(sample_rows(list(au.state_dict().values())), gold["au_final_samp"], 0.0)
+        assert np.nanmax(perr) < 1e-3, perr
+
+
+def test_gaussian_training_loop_device_sampler_and_deferred_logging(tmp_path):
+    """`train_gim_gaussian` (reference training/gim_gaussian_training.py:50-232) with episodes synthesised on
+    the device, the iteration as one CUDA graph and the per-iteration scalars delivered in batches: every iteration is logged under the
+    reference's keys with its own global step, eager and graph modes see the same noise stream and produce the same curves."""
+    g, _, GM, _, _, _, _ = pkg()
+    from optimalstrategiesagainstgenerativeattacks_b200 import gim_gaussian_training as GT
+    g.set_precision("fp32")
+    g.set_deterministic(True)
+    curves = {}
+    try:
+        for mode in (False, True):
+            torch.manual_seed(1)
+            au, im = GM.get_au(10), GM.get_im(10)
+            torch.manual_seed(7)
+            torch.cuda.manual_seed(7)
+            tr, log = GT.train_gim_gaussian(device_name="cuda", device_ids=[0], outdir=str(tmp_path / ("g%d" % mode)), authenticator=au, impersonator=im, m=1, n=5, k=10,
+                                            src_dim=10, src_sigma=1.0, prior_sigma=10.0, reg_param=0.0, remove_noise_mean=True, au_lr=1e-3, im_lr=1e-3,
+                                            resume_from_ckpt=None, n_iters=12, batch_size=256, save_every=10, save_stats_every=5, use_cuda_graph=mode, log_every=5)
+            assert tr.module.global_step == 11
+            for key in GT.SCALARS:
+                steps = [s_ for s_, _ in log.scalars[key]]
+                assert steps == list(range(12)), (key, steps)
+            assert [s_ for s_, _ in log.scalars[("im distances", "l1_dist_from_gt_sample_mean")]] == [0, 5, 10]
+            import os
+            assert sorted(os.listdir(tmp_path / ("g%d" % mode) / "ckpts")) == ["model_00000000.pt", "model_00000010.pt"]
+            curves[mode] = np.asarray([[v for _, v in log.scalars[key]] for key in GT.SCALARS])
+            acc = curves[mode][7]
+            assert ((0.0 <= acc) & (acc <= 1.0)).all()
+    finally:
+        g.set_deterministic(False)
+    assert np.allclose(curves[False], curves[True], rtol=1e-5, atol=1e-6), np.abs(curves[False] - curves[True]).max()
