@@ -776,6 +776,7 @@ def deferred_weight_grads():
         if _side["used"] and _side["stream"] is not None:
             # kernels of the side branch's backward wrote into .grad directly (bias sums): the optimizer on this stream must see them
             torch.cuda.current_stream().wait_stream(_side["stream"])
+        _side["used"] = False          # (the next forward that forks sets it again; a model without branches never touches the side stream)
 
 
 def _defer_sn_backward(ctx, g, w, aux):
