@@ -284,7 +284,7 @@ def measure_workload(args, D, workload, B, want_roofline, sample_clocks):
     from optimalstrategiesagainstgenerativeattacks_b200 import _cabi, ddp, ops
     from optimalstrategiesagainstgenerativeattacks_b200 import gim_img_models as M
     from optimalstrategiesagainstgenerativeattacks_b200.gim_img_trainer import GIMImgTrainer
-    from optimalstrategiesagainstgenerativeattacks_b200.training_steps import au_train_step, im_train_step
+    from optimalstrategiesagainstgenerativeattacks_b200.training_steps import au_train_step, finish_deferred_steps, im_train_step
     from optimalstrategiesagainstgenerativeattacks_b200.utils import DataParallelMock
 
     world, rank, dev = D.world, D.rank, D.dev
@@ -296,7 +296,7 @@ def measure_workload(args, D, workload, B, want_roofline, sample_clocks):
     trainer = DataParallelMock(GIMImgTrainer(outdir, M_, N_, K_, au, im, au_lr, im_lr, map_lr, reg_param=reg))
     if world > 1:
         ddp.attach(trainer.module.authenticator_opt)
-        ddp.attach(trainer.module.impersonator_opt)
+        ddp.attach(trainer.module.impersonator_opt, defer=not os.environ.get("GIM_DDP_NO_OVERLAP"))     # G's all-reduce under the D-step
     torch.manual_seed(1000 + rank)                # per-rank noise stream for z
 
     n_pool = 2
@@ -309,6 +309,7 @@ def measure_workload(args, D, workload, B, want_roofline, sample_clocks):
         trainer.module.update_learning_rate()
         im_loss, fake, _ = im_train_step(trainer, leaked, si)
         o = au_train_step(trainer, real, fake, si)
+        finish_deferred_steps(trainer)
         return im_loss, o[0]
 
     graphed = None
@@ -389,7 +390,7 @@ def measure_gaussian(args, D, d, batch):
     tr = DataParallelMock(GIMGaussianTrainer(tempfile.mkdtemp(prefix="gim_bench_"), m, n, k, au, im, 1e-4, 1e-4, reg_param=0.0))
     if D.world > 1:
         ddp.attach(tr.module.authenticator_opt)
-        ddp.attach(tr.module.impersonator_opt)
+        ddp.attach(tr.module.impersonator_opt, defer=True)
     torch.manual_seed(1000 + D.rank)
 
     def sample():
@@ -607,7 +608,7 @@ def run_check(args):
     au, im = M.get_au(size, ch, STYLE).to(dev), M.get_im(size, ch, STYLE).to(dev)
     tr = DataParallelMock(GIMImgTrainer(tempfile.mkdtemp(prefix="gim_check_"), M_, N_, K_, au, im, 1e-3, 1e-3, 1e-4, reg_param=reg))
     ddp.attach(tr.module.authenticator_opt)
-    ddp.attach(tr.module.impersonator_opt)
+    ddp.attach(tr.module.impersonator_opt, defer=True)
     torch.manual_seed(1000 + rank)
     g = GraphedIteration(tr, leaked[lo:hi], real[lo:hi], si[lo:hi], warmup=3)
     for _ in range(3):

@@ -16,7 +16,7 @@ import copy
 import torch
 
 from . import _cabi
-from .training_steps import au_train_step, im_train_step
+from .training_steps import au_train_step, finish_deferred_steps, im_train_step
 
 
 class _TrainingState:
@@ -87,6 +87,7 @@ class GraphedIteration:
         leaked, real, si = self.static_in
         im_loss, fake, _ = im_train_step(self.trainer, leaked, si)
         out = au_train_step(self.trainer, real, fake, si)
+        finish_deferred_steps(self.trainer)              # data parallel: G's all-reduce ran underneath the D-step; its Adam update goes here
         return (im_loss,) + tuple(out[:6])
 
     def _capture(self, warmup):

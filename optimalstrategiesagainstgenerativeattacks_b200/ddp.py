@@ -53,28 +53,78 @@ def broadcast_module_state(module, src=0, group=None):
             dist.broadcast(t.data, src=src, group=group)
 
 
-def attach(optimizer, group=None):
-    """Make `optimizer.step()` all-reduce its gradients first and apply the mean (grad_scale = 1/world)."""
+_comm = {"stream": None}
+
+
+def _comm_stream(device):
+    if _comm["stream"] is None or _comm["stream"].device != device:
+        _comm["stream"] = torch.cuda.Stream(device=device)
+    return _comm["stream"]
+
+
+def attach(optimizer, group=None, defer=False):
+    """Make `optimizer.step()` all-reduce its gradients first and apply the mean (grad_scale = 1/world).
+
+    defer=True -- overlap: `step()` only LAUNCHES the all-reduce, on a communication stream, and returns; the Adam update runs at
+    `optimizer.flush()` (also triggered by the next zero_grad / step / state_dict), after that stream has finished.  The training
+    loops attach the attacker's optimizer this way and flush it at the end of the iteration: the authenticator step that follows the
+    attacker step never reads the attacker's parameters (it consumes the already generated `fake_sample`), so the 246 MB all-reduce
+    of G's gradients travels over NVLink underneath D's forward and backward and the result is bit-identical to stepping immediately.
+    Inside a captured CUDA graph the communication stream becomes a parallel branch of the graph."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    optimizer.grad_scale = 1.0 / world
+    in_kernel = getattr(type(optimizer), "FOLDS_GRAD_SCALE", False)      # FusedAdam multiplies by 1/world inside its update kernel
+    if in_kernel:
+        optimizer.grad_scale = 1.0 / world
     if world > 1:                                    # replicas start from rank 0's parameters
         with torch.no_grad():
             for g in optimizer.param_groups:
                 for p in g["params"]:
                     dist.broadcast(p.data, src=0, group=group)
-    inner_step = optimizer.step
-    state = {"bucket": None}
+    inner_step, inner_zero, inner_sd = optimizer.step, optimizer.zero_grad, optimizer.state_dict
+    state = {"bucket": None, "pending": False}
+
+    def reduce_now():
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        if state["bucket"] is None:
+            state["bucket"] = FlatGradBucket(params)
+        elif not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()) and not state["bucket"].covers(params):
+            raise RuntimeError("ddp: the set of parameters that receive gradients changed after the first optimizer step "
+                               "(flat gradient bucket is frozen) -- re-attach the optimizer")
+        state["bucket"].all_reduce(group)
+        if not in_kernel and world > 1:
+            state["bucket"].flat.mul_(1.0 / world)   # a stock optimizer sees the mean gradient
+
+    def flush():
+        """Finish a deferred step: wait for the communication stream, then run the (fused) Adam update."""
+        if not state["pending"]:
+            return None
+        state["pending"] = False
+        torch.cuda.current_stream().wait_stream(_comm_stream(state["bucket"].flat.device))
+        return inner_step()
 
     def step(closure=None):
-        if world > 1:
-            params = [p for g in optimizer.param_groups for p in g["params"]]
-            if state["bucket"] is None:
-                state["bucket"] = FlatGradBucket(params)
-            elif not torch.cuda.is_current_stream_capturing() and not state["bucket"].covers(params):
-                raise RuntimeError("ddp: the set of parameters that receive gradients changed after the first optimizer step "
-                                   "(flat gradient bucket is frozen) -- re-attach the optimizer")
-            state["bucket"].all_reduce(group)
-        return inner_step(closure)
+        if closure is not None:
+            raise RuntimeError("ddp: closures are not supported")
+        flush()
+        if world <= 1:
+            return inner_step()
+        if not (defer and state["bucket"] is not None and state["bucket"].flat.is_cuda):
+            reduce_now()                             # (the first step builds the bucket: gradients move into it)
+            return inner_step()
+        comm, cur = _comm_stream(state["bucket"].flat.device), torch.cuda.current_stream()
+        comm.wait_stream(cur)                        # gradients are complete on the compute stream
+        with torch.cuda.stream(comm):
+            reduce_now()
+        state["pending"] = True
+        return None
 
-    optimizer.step = step
+    def zero_grad(*a, **k):
+        flush()
+        return inner_zero(*a, **k)
+
+    def state_dict(*a, **k):
+        flush()
+        return inner_sd(*a, **k)
+
+    optimizer.step, optimizer.flush, optimizer.zero_grad, optimizer.state_dict = step, flush, zero_grad, state_dict
     return optimizer

@@ -17,6 +17,8 @@ class _AdamTensor(ctypes.Structure):
 
 
 class FusedAdam(torch.optim.Adam):
+    FOLDS_GRAD_SCALE = True        # ddp.attach: the 1/world of the gradient mean is applied inside the update kernel (self.grad_scale)
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, lr=lr, betas=betas, eps=eps)
         self._table_key = None

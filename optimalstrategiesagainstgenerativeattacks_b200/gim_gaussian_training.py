@@ -22,7 +22,7 @@ from . import ddp, ops
 from . import model_blocks as mb
 from .gim_gaussian_trainer import GIMGaussianTrainer
 from .gim_img_training import ScalarLog, _save_rank0
-from .training_steps import au_train_step, im_train_step   # noqa: F401  (re-exported under the reference's names)
+from .training_steps import au_train_step, finish_deferred_steps, im_train_step   # noqa: F401  (the step functions are re-exported under the reference's names)
 from .utils import DataParallelMock, get_device
 
 # (category, key) of the per-iteration scalars, in the order the reference logs them (:93-112)
@@ -91,6 +91,7 @@ class _GraphedGaussianIteration:
         mu, (leaked, real, si) = self.sample()
         im_loss, fake, _ = im_train_step(self.trainer, leaked, si)
         au_out = au_train_step(self.trainer, real, fake, si)
+        finish_deferred_steps(self.trainer)
         return _iteration_scalars(im_loss, au_out), mu, leaked, real, au_out[8]
 
     def __call__(self):
@@ -121,6 +122,7 @@ def train(device, trainer, logger, n_iters, batch_size, src_dim, src_sigma, prio
                 mu, (leaked_sample, real_sample, si_sample) = sample()
                 im_loss, fake_sample, _ = im_train_step(trainer=trainer, leaked_sample=leaked_sample, si_sample=si_sample)
                 au_out = au_train_step(trainer=trainer, real_sample=real_sample, fake_sample=fake_sample, si_sample=si_sample)
+                finish_deferred_steps(trainer)
                 vec, fake_sample = _iteration_scalars(im_loss, au_out), au_out[8]
             scalars.put(global_step, vec)
 
@@ -156,7 +158,7 @@ def train_gim_gaussian(device_name, device_ids, outdir, authenticator, impersona
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         ddp.broadcast_module_state(trainer)
         ddp.attach(trainer.authenticator_opt)
-        ddp.attach(trainer.impersonator_opt)
+        ddp.attach(trainer.impersonator_opt, defer=True)
     trainer = DataParallelMock(trainer)
     os.makedirs(outdir, exist_ok=True)
     try:

@@ -24,7 +24,7 @@ import torch.distributed as dist
 from . import ddp
 from . import model_blocks as mb
 from .gim_img_trainer import GIMImgTrainer
-from .training_steps import au_eval_step, au_train_step, im_eval_step, im_train_step
+from .training_steps import au_eval_step, au_train_step, finish_deferred_steps, im_eval_step, im_train_step
 from .utils import DataParallelMock, get_device
 
 
@@ -196,6 +196,7 @@ def train_epoch(device, logger, epoch, trainer, train_ds, val_ds, train_batch_si
                 im_loss, fake_sample, _ = im_eval_step(trainer=trainer, leaked_sample=leaked_sample, si_sample=si_sample)
             (au_loss, au_loss_on_real, au_loss_on_fake, au_reg, au_out_on_real, au_out_on_fake, au_pred_on_real, au_pred_on_fake, fake_sample) = au_train_step(
                 trainer=trainer, real_sample=real_sample, fake_sample=fake_sample, si_sample=si_sample)
+            finish_deferred_steps(trainer)
         for k, v in zip(names, (au_loss, au_loss_on_real, au_loss_on_fake, au_reg, au_out_on_real, au_out_on_fake, im_loss)):
             buf[k].append(v)
         if au_pred_on_real is not None:
@@ -249,7 +250,7 @@ def train_gim_imgs(device_name, device_ids, outdir, train_ds, val_ds, authentica
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         ddp.broadcast_module_state(trainer)            # replicas start from rank 0's parameters and spectral-norm u/v
         ddp.attach(trainer.authenticator_opt)
-        ddp.attach(trainer.impersonator_opt)
+        ddp.attach(trainer.impersonator_opt, defer=True)      # G's all-reduce overlaps the D-step (flushed at the end of the iteration)
     trainer = DataParallelMock(trainer)
     os.makedirs(outdir, exist_ok=True)
     for ep in range(n_epochs):

@@ -30,6 +30,15 @@ def au_train_step(trainer, real_sample, fake_sample, si_sample):
             pred_on_real.detach(), pred_on_fake.detach(), fake_sample.detach())
 
 
+def finish_deferred_steps(trainer):
+    """Data parallel with overlapped communication (ddp.attach(..., defer=True)): apply the optimizer steps whose gradient all-reduce was
+    launched asynchronously.  Called once at the end of an iteration; a no-op otherwise."""
+    for opt in (trainer.module.impersonator_opt, trainer.module.authenticator_opt):
+        flush = getattr(opt, "flush", None)
+        if flush is not None:
+            flush()
+
+
 def im_eval_step(trainer, leaked_sample, si_sample):
     trainer.module.impersonator.eval()
     with torch.no_grad():
