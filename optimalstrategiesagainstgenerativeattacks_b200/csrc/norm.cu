@@ -4,37 +4,40 @@
 
 namespace gim {
 
-// grid (ceil(c/32), n); block (32, 8).  Two passes over the (L2-resident) plane: exact mean, then M2.
-// The mean is accumulated as pivot + mean(x - pivot) with pivot = the plane's first pixel: on a spatially CONSTANT plane every
-// difference is exactly zero, so mean == x and the centred values are exactly 0 -- as in exact arithmetic.  That case is not exotic:
-// with the reference's initialisation (InstanceNorm bias 0) the right branch of every EnvDecoder block is spatially constant, the
-// variance is 0 and rsqrt(eps) = 316 multiplies whatever round-off the mean carries (a plain running sum gives 3x != x + x + x).
+// grid (ceil(c/32), n); block (32, 8).  ONE pass over the plane with pivot-shifted sums, pivot = the plane's first pixel:
+//   d = x - pivot,  mean = pivot + sum(d)/hw,  M2 = sum(d^2) - sum(d)^2/hw
+// (the shift keeps the subtraction in M2 benign -- d is of the order of the spread, not of the mean -- and halves the DRAM traffic of
+// the two-pass form, whose second pass missed L2: ncu measured 1.92x the algorithmic bytes).  On a spatially CONSTANT plane every d is
+// exactly zero, so mean == x, M2 == 0 and the centred values are exactly 0 -- as in exact arithmetic.  That case is not exotic: with the
+// reference's initialisation (InstanceNorm bias 0) the right branch of every EnvDecoder block is spatially constant, the variance is
+// 0 and rsqrt(eps) = 316 multiplies whatever round-off the mean carries (a plain running sum gives 3x != x + x + x).
 template <typename T>
 __global__ void __launch_bounds__(256) norm_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __restrict__ m2, int hw, int c) {
-    __shared__ float sh[8][33];
+    __shared__ float sh[8][33], sh2[8][33];
     int ch = blockIdx.x * 32 + threadIdx.x;
     long long img = blockIdx.y;
     const T* xi = x + img * (long long)hw * c;
     const float pivot = ch < c ? to_f<T>(xi[ch]) : 0.f;
-    float s = 0.f;
-    if (ch < c) for (int p = threadIdx.y; p < hw; p += 8) s += to_f<T>(xi[(long long)p * c + ch]) - pivot;
+    float s = 0.f, q = 0.f;
+    if (ch < c) {
+        int p = threadIdx.y;
+        for (; p + 24 < hw; p += 32) {                     // four independent loads in flight per thread
+            const float d0 = to_f<T>(xi[(long long)p * c + ch]) - pivot, d1 = to_f<T>(xi[(long long)(p + 8) * c + ch]) - pivot;
+            const float d2 = to_f<T>(xi[(long long)(p + 16) * c + ch]) - pivot, d3 = to_f<T>(xi[(long long)(p + 24) * c + ch]) - pivot;
+            s += (d0 + d1) + (d2 + d3);
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+        for (; p < hw; p += 8) { const float d = to_f<T>(xi[(long long)p * c + ch]) - pivot; s += d; q += d * d; }
+    }
     sh[threadIdx.y][threadIdx.x] = s;
-    __syncthreads();
-    float mu = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mu += sh[j][threadIdx.x];
-    mu = pivot + mu / (float)hw;
-    __syncthreads();
-    float q = 0.f;
-    if (ch < c) for (int p = threadIdx.y; p < hw; p += 8) { float d = to_f<T>(xi[(long long)p * c + ch]) - mu; q += d * d; }
-    sh[threadIdx.y][threadIdx.x] = q;
+    sh2[threadIdx.y][threadIdx.x] = q;
     __syncthreads();
     if (threadIdx.y == 0 && ch < c) {
-        float t = 0.f;
+        float ts = 0.f, tq = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
-        mean[img * c + ch] = mu;
-        m2[img * c + ch] = t;
+        for (int j = 0; j < 8; ++j) { ts += sh[j][threadIdx.x]; tq += sh2[j][threadIdx.x]; }
+        mean[img * c + ch] = pivot + ts / (float)hw;
+        m2[img * c + ch] = fmaxf(tq - ts * ts / (float)hw, 0.f);
     }
 }
 
@@ -48,6 +51,49 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x
         long long k = (i / plane) * c + ch;
         float v = a[k] * (to_f<T>(x[i]) - mean[k]) + b[k];      // centred form: exact for the degenerate 1x1 map
         y[i] = from_f<T>(lrelu_f(v, slope));
+    }
+}
+
+// fp32, c % 4 == 0: grid (chunks of the plane, n); one float4 of adjacent channels per thread and step
+__global__ void __launch_bounds__(256) affine_act_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ mean, const float4* __restrict__ a,
+                                                              const float4* __restrict__ b, float4* __restrict__ y, int plane4, int c4, float slope) {
+    const long long base = (long long)blockIdx.y * plane4;
+    const float4* mi = mean + (long long)blockIdx.y * c4;
+    const float4* ai = a + (long long)blockIdx.y * c4;
+    const float4* bi = b + (long long)blockIdx.y * c4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane4; i += gridDim.x * blockDim.x) {
+        const int k = i % c4;
+        const float4 xv = __ldg(x + base + i), m = __ldg(mi + k), av = __ldg(ai + k), bv = __ldg(bi + k);
+        float4 o;
+        o.x = lrelu_f(av.x * (xv.x - m.x) + bv.x, slope);
+        o.y = lrelu_f(av.y * (xv.y - m.y) + bv.y, slope);
+        o.z = lrelu_f(av.z * (xv.z - m.z) + bv.z, slope);
+        o.w = lrelu_f(av.w * (xv.w - m.w) + bv.w, slope);
+        y[base + i] = o;
+    }
+}
+__global__ void __launch_bounds__(256) norm_bwd_apply_vec4_kernel(const float4* __restrict__ gy, const float4* __restrict__ x, const float4* __restrict__ y,
+                                                                  const float4* __restrict__ mean, const float4* __restrict__ A, const float4* __restrict__ B,
+                                                                  const float4* __restrict__ C, float4* __restrict__ gx, int plane4, int c4, float slope) {
+    const long long base = (long long)blockIdx.y * plane4;
+    const long long kb = (long long)blockIdx.y * c4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane4; i += gridDim.x * blockDim.x) {
+        const int k = i % c4;
+        float4 g = __ldg(gy + base + i);
+        const float4 xv = __ldg(x + base + i), m = __ldg(mean + kb + k), av = __ldg(A + kb + k), bv = __ldg(B + kb + k), cv = __ldg(C + kb + k);
+        if (y != nullptr) {
+            const float4 yv = __ldg(y + base + i);
+            if (!(yv.x > 0.f)) g.x *= slope;
+            if (!(yv.y > 0.f)) g.y *= slope;
+            if (!(yv.z > 0.f)) g.z *= slope;
+            if (!(yv.w > 0.f)) g.w *= slope;
+        }
+        float4 o;
+        o.x = av.x * g.x + bv.x * (xv.x - m.x) + cv.x;
+        o.y = av.y * g.y + bv.y * (xv.y - m.y) + cv.y;
+        o.z = av.z * g.z + bv.z * (xv.z - m.z) + cv.z;
+        o.w = av.w * g.w + bv.w * (xv.w - m.w) + cv.w;
+        gx[base + i] = o;
     }
 }
 
@@ -183,6 +229,16 @@ int gim_affine_act_fwd(const void* x, const float* mean, const float* a, const f
                        gim_stream_t s) {
     long long total = (long long)n * hw * c;
     if (total <= 0) return GIM_OK;
+    const long long plane4 = (long long)hw * c / 4;
+    if (dtype == GIM_F32 && c % 4 == 0 && n <= 65535 && plane4 < (1LL << 30) && ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)a | (uintptr_t)b) & 15) == 0)) {
+        int gx = (int)((plane4 + 1023) / 1024);                      // four float4 per thread
+        const int cap = (num_sms() * 16 + n - 1) / n;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        affine_act_vec4_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)s>>>((const float4*)x, (const float4*)mean, (const float4*)a, (const float4*)b, (float4*)y,
+                                                                        (int)plane4, c / 4, slope);
+        return check_launch("affine_act_fwd");
+    }
     GIM_DISPATCH_DTYPE(dtype, (affine_act_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, mean, a, b, (T*)y, total, hw, c, slope)));
     return check_launch("affine_act_fwd");
 }
@@ -198,6 +254,17 @@ int gim_norm_bwd_apply(const void* gy, const void* x, const void* y, const float
                        int n, int hw, int c, float slope, int dtype, gim_stream_t s) {
     long long total = (long long)n * hw * c;
     if (total <= 0) return GIM_OK;
+    const long long plane4 = (long long)hw * c / 4;
+    if (dtype == GIM_F32 && c % 4 == 0 && n <= 65535 && plane4 < (1LL << 30) &&
+        ((((uintptr_t)gy | (uintptr_t)x | (uintptr_t)y | (uintptr_t)gx | (uintptr_t)mean | (uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0)) {
+        int g = (int)((plane4 + 1023) / 1024);
+        const int cap = (num_sms() * 16 + n - 1) / n;
+        if (g > cap) g = cap;
+        if (g < 1) g = 1;
+        norm_bwd_apply_vec4_kernel<<<dim3(g, n), 256, 0, (cudaStream_t)s>>>((const float4*)gy, (const float4*)x, (const float4*)y, (const float4*)mean, (const float4*)A,
+                                                                          (const float4*)B, (const float4*)C, (float4*)gx, (int)plane4, c / 4, slope);
+        return check_launch("norm_bwd_apply");
+    }
     GIM_DISPATCH_DTYPE(dtype, (norm_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)gy, (const T*)x, (const T*)y, mean, A, B, C,
                                                                                                        (T*)gx, total, hw, c, slope)));
     return check_launch("norm_bwd_apply");
