@@ -65,6 +65,8 @@ int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y,
 #define GIM_EPI_ADD   4
 #define GIM_EPI_POOL  8
 #define GIM_EPI_ADDUP 16
+#define GIM_EPI_UNIT  32   /* with GIM_EPI_POOL / GIM_EPI_ADDUP: scale 1 instead of 1/4 -- sum pooling (the backward of nn.Upsample(x2), model_blocks.py:740)
+                            * and the addition of a nearest-upsampled half-resolution tensor (the 1x1 residual branch of the up-sampling blocks) */
 int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* y, const void* mask_ref, const float* addend,
                          int n, int h, int wd, int cin, int cout, int ksize, int out_dtype, int epilogue, float slope, gim_stream_t stream);
 /* gw[t][co][ci] (fp32) = sum_{n,h,w} gy[n,h,w,co] * x[n,h+r-p,w+s-p,ci]  (overwrites gw) */
@@ -181,11 +183,18 @@ int gim_norm_stats(const void* x, float* mean, float* m2, int n, int hw, int c, 
 /* y = act(a[n,c]*(x - mean[n,c]) + b[n,c]),  act = LeakyReLU(slope) if slope != 1 */
 int gim_affine_act_fwd(const void* x, const float* mean, const float* a, const float* b, void* y, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
 /* s1[n,c] = sum gyh, s2[n,c] = sum gyh*(x-mean), gyh = gy * act'(y)   (y = forward output, NULL if no act) */
-int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, float* s1, float* s2,
+/* (act_a, act_b: when y is NULL and these are not, the activation mask is recomputed as sign(act_a (x - mean) + act_b) -- the forward
+ *  output was never materialised, see gim_norm_act_operand) */
+int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, const float* act_a, const float* act_b, float* s1, float* s2,
                         int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
 /* gx = A[n,c]*gyh + B[n,c]*(x-mean[n,c]) + C[n,c] */
-int gim_norm_bwd_apply(const void* gy, const void* x, const void* y, const float* mean, const float* A, const float* B, const float* C,
-                       void* gx, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
+int gim_norm_bwd_apply(const void* gy, const void* x, const void* y, const float* mean, const float* act_a, const float* act_b, const float* A, const float* B,
+                       const float* C, void* gx, int n, int hw, int c, float slope, int dtype, gim_stream_t stream);
+/* out[n,(2)h,(2)w,c] = bf16(LeakyReLU_slope(a[n,c] (x - mean[n,c]) + b[n,c])), nearest-upsampled x2 when upsample != 0: the
+ * norm -> activation -> (nn.Upsample) -> conv-operand chain of ResBlockUp / AdaResBlock2 / AdaResBlockUp2 (model_blocks.py:760-768, 805-811,
+ * 851-861) in one pass; x fp32 NHWC, c % 8 == 0 */
+int gim_norm_act_operand(const float* x, const float* mean, const float* a, const float* b, void* out_bf16, int n, int h, int wd, int c, float slope,
+                         int upsample, gim_stream_t stream);
 /* coefficient kernels on [n,c] fp32 arrays.  mode 0 = InstanceNorm(weight[c],bias[c],eps: biased var),
  * mode 1 = ada_in(std_style[n,c], mean_style[n,c], eps added to the unbiased std) */
 int gim_norm_coeffs(int mode, const float* mean, const float* m2, const float* p_scale, const float* p_shift,

@@ -54,8 +54,9 @@ PROTOTYPES = {
     "gim_col2im": "pppiiiiiip",
     "gim_norm_stats": "pppiiiip",
     "gim_affine_act_fwd": "pppppiiifip",
-    "gim_norm_bwd_reduce": "ppppppiiifip",
-    "gim_norm_bwd_apply": "ppppppppiiifip",
+    "gim_norm_bwd_reduce": "ppppppppiiifip",
+    "gim_norm_bwd_apply": "ppppppppppiiifip",
+    "gim_norm_act_operand": "pppppiiiifip",
     "gim_norm_coeffs": "ippppppiiifp",
     "gim_norm_bwd_coeffs": "ippppppppp" + "iiifp",
     "gim_gemm_strided": "pilllpilllpilliiiiffp",

@@ -343,7 +343,7 @@ int gim_conv2d_fwd_fused(const void* x, const void* w, const float* bias, void* 
     GIM_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv2d_fwd_fused: empty shape");
     GIM_REQUIRE(ksize >= 1 && (ksize & 1), "conv2d_fwd_fused: kernel size must be odd ('same' padding)");
     GIM_REQUIRE(out_dtype == GIM_F32 || out_dtype == GIM_BF16, "conv2d_fwd_fused: bad output dtype");
-    GIM_REQUIRE((epilogue & ~31) == 0, "conv2d_fwd_fused: unknown epilogue bits");
+    GIM_REQUIRE((epilogue & ~63) == 0, "conv2d_fwd_fused: unknown epilogue bits");
     if (!conv_tc_supported(n, h, wd, cin, cout, ksize, GIM_BF16)) return fail(GIM_E_UNSUPPORTED, "conv2d_fwd_fused: shape not supported by the tcgen05 path");
     return conv_fwd_tc_ex(x, w, bias, y, n, h, wd, cin, cout, ksize, out_dtype == GIM_F32 ? 1 : 0, epilogue, slope, mask_ref, addend, (cudaStream_t)s);
 }

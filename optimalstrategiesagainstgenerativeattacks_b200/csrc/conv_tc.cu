@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
 //   rotating staging buffers) runs while the MMA warp already accumulates tile i+1; the TMA/MMA smem ring never drains between
 //   tiles.  Fused epilogues: + bias, LeakyReLU, LeakyReLU-backward mask taken from a saved bf16 operand, fp32 or bf16 output.
 // ----------------------------------------------------------------------------------------------------------------
-enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4, kEpiPool = 8, kEpiAddUp = 16 };
+enum { kEpiLrelu = 1, kEpiMask = 2, kEpiAdd = 4, kEpiPool = 8, kEpiAddUp = 16, kEpiUnit = 32 };   // kEpiUnit: scale 1 (not 1/4) in the pool / add-up epilogues
 constexpr int kBoxBytes = kBlockM * 128;                   // one staged output box: 128 rows x 128 B
 
 // A macro tile = m_sub (1 or 2) consecutive 128-pixel tiles x one block_n-wide channel tile.  With m_sub = 2 the two pixel tiles
@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
         int bias_n0 = -1;
         const int lw = m % p.bw, lh = (m / p.bw) % p.bh, ln = m / (p.bw * p.bh);
         const bool store_thread = (et == 0);
+        const float aux_scale = (p.epi & kEpiUnit) ? 1.f : 0.25f;      // nearest-upsample / its backward (sum pooling) vs AvgPool and its backward
         const int cols_per_chunk = p.out_f32 ? 32 : 64;
         uint32_t i = 0;
         int sbuf = 0;                                    // staging box of the current chunk (ring of p.n_staging)
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const float v01 = (sub4 & 1) ? f[8 + e] : f[e], v23 = (sub4 & 1) ? f[24 + e] : f[16 + e];
-                                o[e] = 0.25f * ((sub4 & 2) ? v23 : v01) + bias_sm[cb + 8 * sub4 + e];
+                                o[e] = aux_scale * ((sub4 & 2) ? v23 : v01) + bias_sm[cb + 8 * sub4 + e];
                             }
                             if ((p.epi & kEpiAdd) && valid && n0 + cb < p.cout) {
                                 const long long ppix = ((long long)img * (p.h >> 1) + (hh >> 1)) * (p.w >> 1) + (ww >> 1);
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
 #pragma unroll
                                 for (int v4 = 0; v4 < 8; ++v4) {
                                     const float4 t4 = __ldg(ad + v4);
-                                    f[4 * v4] += 0.25f * t4.x; f[4 * v4 + 1] += 0.25f * t4.y; f[4 * v4 + 2] += 0.25f * t4.z; f[4 * v4 + 3] += 0.25f * t4.w;
+                                    f[4 * v4] += aux_scale * t4.x; f[4 * v4 + 1] += aux_scale * t4.y; f[4 * v4 + 2] += aux_scale * t4.z; f[4 * v4 + 3] += aux_scale * t4.w;
                                 }
                             }
                         }
@@ -848,9 +849,9 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     static const int force_v2 = env_int("GIM_CONV_V2", 0);
     // measured (tools/conv_bench.py): the persistent kernel wins whenever it can use the 256-wide N tile; with 128-wide tiles two
     // co-resident non-persistent CTAs still issue MMAs faster than one persistent CTA
-    const bool tiny = m_tiles * ((cout + 127) / 128) <= num_sms() / 2 && epi == 0;      // e.g. Linear layers: launch latency only
+    const bool tiny = m_tiles * ((cout + 127) / 128) <= num_sms() / 2 && (epi & ~kEpiUnit) == 0;      // e.g. Linear layers: launch latency only
     const bool v2 = !use_v1 && pick_block_n(cout) >= 32 && (!tiny || force_v2);
-    if (!v2 && epi != 0) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: fused epilogues need cout >= 32");
+    if (!v2 && (epi & ~kEpiUnit) != 0) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: fused epilogues need cout >= 32");
     p.block_n = v2 ? pick_block_n2(cout, m_tiles) : pick_block_n(cout);
     static const int force_msub = env_int("GIM_CONV_MSUB", 0), pair_mode = env_int("GIM_CONV_PAIR", 1);
     p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(256) affine_act_vec4_kernel(const float4* __re
 }
 __global__ void __launch_bounds__(256) norm_bwd_apply_vec4_kernel(const float4* __restrict__ gy, const float4* __restrict__ x, const float4* __restrict__ y,
                                                                   const float4* __restrict__ mean, const float4* __restrict__ A, const float4* __restrict__ B,
-                                                                  const float4* __restrict__ C, float4* __restrict__ gx, int plane4, int c4, float slope) {
+                                                                  const float4* __restrict__ C, float4* __restrict__ gx, int plane4, int c4, float slope,
+                                                                  const float4* __restrict__ ca, const float4* __restrict__ cb) {
     const long long base = (long long)blockIdx.y * plane4;
     const long long kb = (long long)blockIdx.y * c4;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane4; i += gridDim.x * blockDim.x) {
@@ -87,6 +88,12 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec4_kernel(const float4* 
             if (!(yv.y > 0.f)) g.y *= slope;
             if (!(yv.z > 0.f)) g.z *= slope;
             if (!(yv.w > 0.f)) g.w *= slope;
+        } else if (ca != nullptr) {                  // the forward output was never materialised: recompute its sign
+            const float4 fa = __ldg(ca + kb + k), fb = __ldg(cb + kb + k);
+            if (!(fa.x * (xv.x - m.x) + fb.x > 0.f)) g.x *= slope;
+            if (!(fa.y * (xv.y - m.y) + fb.y > 0.f)) g.y *= slope;
+            if (!(fa.z * (xv.z - m.z) + fb.z > 0.f)) g.z *= slope;
+            if (!(fa.w * (xv.w - m.w) + fb.w > 0.f)) g.w *= slope;
         }
         float4 o;
         o.x = av.x * g.x + bv.x * (xv.x - m.x) + cv.x;
@@ -97,10 +104,55 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_vec4_kernel(const float4* 
     }
 }
 
+// The norm -> activation -> (nearest x2 upsample) -> bf16 conv operand chain of the attacker's blocks (reference model_blocks.py:760-768,
+// 805-811, 851-861) in ONE pass: out[n, (2)h, (2)w, c] = bf16(LeakyReLU(a (x - mean) + b)).  The fp32 normalised activation never exists.
+// grid (chunks of the plane, n); thread = 8 adjacent channels (two 16-byte loads, one 16-byte store -- four when upsampling).
+__global__ void __launch_bounds__(256) norm_act_operand_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ a,
+                                                               const float* __restrict__ b, bf16* __restrict__ out, int h, int w, int c, float slope, int upsample) {
+    const int c8 = c >> 3, plane8 = h * w * c8;
+    const float* xi = x + (long long)blockIdx.y * h * w * c;
+    const long long kb = (long long)blockIdx.y * c;
+    bf16* oi = out + (long long)blockIdx.y * h * w * c * (upsample ? 4 : 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane8; i += gridDim.x * blockDim.x) {
+        const int k = (i % c8) * 8, pix = i / c8;
+        float v[8];
+        {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(xi + (long long)pix * c + k)), x1 = __ldg(reinterpret_cast<const float4*>(xi + (long long)pix * c + k + 4));
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + kb + k)), m1 = __ldg(reinterpret_cast<const float4*>(mean + kb + k + 4));
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(a + kb + k)), a1 = __ldg(reinterpret_cast<const float4*>(a + kb + k + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + kb + k)), b1 = __ldg(reinterpret_cast<const float4*>(b + kb + k + 4));
+            v[0] = a0.x * (x0.x - m0.x) + b0.x; v[1] = a0.y * (x0.y - m0.y) + b0.y; v[2] = a0.z * (x0.z - m0.z) + b0.z; v[3] = a0.w * (x0.w - m0.w) + b0.w;
+            v[4] = a1.x * (x1.x - m1.x) + b1.x; v[5] = a1.y * (x1.y - m1.y) + b1.y; v[6] = a1.z * (x1.z - m1.z) + b1.z; v[7] = a1.w * (x1.w - m1.w) + b1.w;
+        }
+        uint4 o;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(lrelu_f(v[0], slope), lrelu_f(v[1], slope)), p1 = __floats2bfloat162_rn(lrelu_f(v[2], slope), lrelu_f(v[3], slope));
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(lrelu_f(v[4], slope), lrelu_f(v[5], slope)), p3 = __floats2bfloat162_rn(lrelu_f(v[6], slope), lrelu_f(v[7], slope));
+        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+        if (!upsample) {
+            *reinterpret_cast<uint4*>(oi + (long long)pix * c + k) = o;
+        } else {
+            const int py = pix / w, px = pix - py * w;
+            bf16* q = oi + ((long long)(2 * py) * (2 * w) + 2 * px) * c + k;
+            *reinterpret_cast<uint4*>(q) = o;
+            *reinterpret_cast<uint4*>(q + c) = o;
+            *reinterpret_cast<uint4*>(q + (long long)2 * w * c) = o;
+            *reinterpret_cast<uint4*>(q + (long long)2 * w * c + c) = o;
+        }
+    }
+}
+
+// activation mask of the backward: from the saved forward output y, or -- when y was never materialised (norm_act_operand) --
+// recomputed from the normalisation coefficients: sign(a (x - mean) + b)
+__device__ __forceinline__ bool act_positive(const float* y_or_null, long long i, float xv, float mu, const float* a, const float* b, long long k) {
+    if (y_or_null != nullptr) return y_or_null[i] > 0.f;
+    return a[k] * (xv - mu) + b[k] > 0.f;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ y,
                                                               const float* __restrict__ mean, float* __restrict__ s1, float* __restrict__ s2,
-                                                              int hw, int c, float slope) {
+                                                              int hw, int c, float slope, const float* __restrict__ ca, const float* __restrict__ cb) {
     __shared__ float sh1[8][33], sh2[8][33];
     int ch = blockIdx.x * 32 + threadIdx.x;
     long long img = blockIdx.y;
@@ -111,9 +163,11 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restric
         for (int p = threadIdx.y; p < hw; p += 8) {
             long long i = base + (long long)p * c + ch;
             float g = to_f<T>(gy[i]);
-            if (y != nullptr && !(to_f<T>(y[i]) > 0.f)) g *= slope;
+            const float xv = to_f<T>(x[i]);
+            if (y != nullptr) { if (!(to_f<T>(y[i]) > 0.f)) g *= slope; }
+            else if (ca != nullptr) { if (!(ca[img * c + ch] * (xv - mu) + cb[img * c + ch] > 0.f)) g *= slope; }
             a1 += g;
-            a2 += g * (to_f<T>(x[i]) - mu);
+            a2 += g * (xv - mu);
         }
     }
     sh1[threadIdx.y][threadIdx.x] = a1;
@@ -131,15 +185,18 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ y,
                                                              const float* __restrict__ mean, const float* __restrict__ A, const float* __restrict__ B,
-                                                             const float* __restrict__ C, T* __restrict__ gx, long long total, int hw, int c, float slope) {
+                                                             const float* __restrict__ C, T* __restrict__ gx, long long total, int hw, int c, float slope,
+                                                             const float* __restrict__ ca, const float* __restrict__ cb) {
     long long stride = (long long)gridDim.x * blockDim.x;
     long long plane = (long long)hw * c;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         int ch = (int)(i % c);
         long long k = (i / plane) * c + ch;
         float g = to_f<T>(gy[i]);
-        if (y != nullptr && !(to_f<T>(y[i]) > 0.f)) g *= slope;
-        gx[i] = from_f<T>(A[k] * g + B[k] * (to_f<T>(x[i]) - mean[k]) + C[k]);
+        const float xc = to_f<T>(x[i]) - mean[k];
+        if (y != nullptr) { if (!(to_f<T>(y[i]) > 0.f)) g *= slope; }
+        else if (ca != nullptr) { if (!(ca[k] * xc + cb[k] > 0.f)) g *= slope; }
+        gx[i] = from_f<T>(A[k] * g + B[k] * xc + C[k]);
     }
 }
 
@@ -242,31 +299,45 @@ int gim_affine_act_fwd(const void* x, const float* mean, const float* a, const f
     GIM_DISPATCH_DTYPE(dtype, (affine_act_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)x, mean, a, b, (T*)y, total, hw, c, slope)));
     return check_launch("affine_act_fwd");
 }
-int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, float* s1, float* s2, int n, int hw, int c, float slope,
-                        int dtype, gim_stream_t s) {
+int gim_norm_act_operand(const float* x, const float* mean, const float* a, const float* b, void* out_bf16, int n, int h, int wd, int c, float slope,
+                         int upsample, gim_stream_t s) {
+    if (n <= 0 || h <= 0 || wd <= 0 || c <= 0) return GIM_OK;
+    GIM_REQUIRE(c % 8 == 0 && n <= 65535 && (long long)h * wd * c < (1LL << 31), "norm_act_operand: needs c % 8 == 0");
+    GIM_REQUIRE(((((uintptr_t)x | (uintptr_t)out_bf16 | (uintptr_t)mean | (uintptr_t)a | (uintptr_t)b) & 15) == 0), "norm_act_operand: 16-byte alignment");
+    const int plane8 = h * wd * (c / 8);
+    int gx = (plane8 + 511) / 512;
+    const int cap = (num_sms() * 16 + n - 1) / n;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    norm_act_operand_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)s>>>(x, mean, a, b, (bf16*)out_bf16, h, wd, c, slope, upsample);
+    return check_launch("norm_act_operand");
+}
+int gim_norm_bwd_reduce(const void* gy, const void* x, const void* y, const float* mean, const float* act_a, const float* act_b, float* s1, float* s2,
+                        int n, int hw, int c, float slope, int dtype, gim_stream_t s) {
     if (n <= 0 || c <= 0) return GIM_OK;
     GIM_REQUIRE(hw >= 1 && n <= 65535, "norm_bwd_reduce: bad shape");
     dim3 grid((c + 31) / 32, n), block(32, 8);
-    GIM_DISPATCH_DTYPE(dtype, (norm_bwd_reduce_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)gy, (const T*)x, (const T*)y, mean, s1, s2, hw, c, slope)));
+    GIM_DISPATCH_DTYPE(dtype, (norm_bwd_reduce_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)gy, (const T*)x, (const T*)y, mean, s1, s2, hw, c, slope, act_a, act_b)));
     return check_launch("norm_bwd_reduce");
 }
-int gim_norm_bwd_apply(const void* gy, const void* x, const void* y, const float* mean, const float* A, const float* B, const float* C, void* gx,
-                       int n, int hw, int c, float slope, int dtype, gim_stream_t s) {
+int gim_norm_bwd_apply(const void* gy, const void* x, const void* y, const float* mean, const float* act_a, const float* act_b, const float* A, const float* B,
+                       const float* C, void* gx, int n, int hw, int c, float slope, int dtype, gim_stream_t s) {
     long long total = (long long)n * hw * c;
     if (total <= 0) return GIM_OK;
     const long long plane4 = (long long)hw * c / 4;
     if (dtype == GIM_F32 && c % 4 == 0 && n <= 65535 && plane4 < (1LL << 30) &&
-        ((((uintptr_t)gy | (uintptr_t)x | (uintptr_t)y | (uintptr_t)gx | (uintptr_t)mean | (uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0)) {
+        ((((uintptr_t)gy | (uintptr_t)x | (uintptr_t)y | (uintptr_t)gx | (uintptr_t)mean | (uintptr_t)A | (uintptr_t)B | (uintptr_t)C | (uintptr_t)act_a | (uintptr_t)act_b) & 15) == 0)) {
         int g = (int)((plane4 + 1023) / 1024);
         const int cap = (num_sms() * 16 + n - 1) / n;
         if (g > cap) g = cap;
         if (g < 1) g = 1;
         norm_bwd_apply_vec4_kernel<<<dim3(g, n), 256, 0, (cudaStream_t)s>>>((const float4*)gy, (const float4*)x, (const float4*)y, (const float4*)mean, (const float4*)A,
-                                                                          (const float4*)B, (const float4*)C, (float4*)gx, (int)plane4, c / 4, slope);
+                                                                          (const float4*)B, (const float4*)C, (float4*)gx, (int)plane4, c / 4, slope,
+                                                                          (const float4*)act_a, (const float4*)act_b);
         return check_launch("norm_bwd_apply");
     }
     GIM_DISPATCH_DTYPE(dtype, (norm_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const T*)gy, (const T*)x, (const T*)y, mean, A, B, C,
-                                                                                                       (T*)gx, total, hw, c, slope)));
+                                                                                                       (T*)gx, total, hw, c, slope, act_a, act_b)));
     return check_launch("norm_bwd_apply");
 }
 int gim_norm_coeffs(int mode, const float* mean, const float* m2, const float* p_scale, const float* p_shift, float* a, float* b, int n, int hw, int c,

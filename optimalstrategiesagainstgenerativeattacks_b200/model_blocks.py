@@ -260,9 +260,20 @@ class ResBlockUp(nn.Module):
         self.conv_r2 = SNConv2d(out_channel, out_channel, conv_size, padding=padding_size)
 
     def forward(self, x):
+        w1 = self.conv_r1.effective_weight()
+        if ops.norm_conv_ok(x, w1):
+            # bf16 tensor-core path: norm -> LeakyReLU -> (upsample) -> conv as fused nodes (the normalised fp32 activations never exist);
+            # the half-resolution 1x1 residual branch is added inside the second convolution's epilogue
+            res = self.conv_l1(x)
+            out = ops.norm_conv(x, self.in1.weight, self.in1.bias, w1, self.conv_r1.bias, self.conv_r1.kernel_size, 0, self.in1.eps, 0.2, upsample=True)
+            w2 = self.conv_r2.effective_weight()
+            fuse_add = w2.shape[1] % 32 == 0
+            out = ops.norm_conv(out, self.in2.weight, self.in2.bias, w2, self.conv_r2.bias, self.conv_r2.kernel_size, 0, self.in2.eps, 0.2,
+                                addend=res if fuse_add else None)
+            return out if fuse_add else ops.AddFn.apply(out, ops.upsample2(res))
         out_res = ops.upsample2(self.conv_l1(x))
         out = self.in1(x, 0.2)
-        out = self.conv_r1(out, ops.PRE_UPSAMPLE)     # conv(upsample(.)): the 4x larger tensor only exists as the bf16 operand
+        out = ops.Conv2dFn.apply(out, w1, self.conv_r1.bias, self.conv_r1.kernel_size, ops.PRE_UPSAMPLE, 0.2)     # conv(upsample(.)): the 4x tensor only exists as the operand
         out = self.in2(out, 0.2)
         out = self.conv_r2(out)
         return ops.AddFn.apply(out, out_res)
@@ -290,8 +301,13 @@ class AdaResBlock2(nn.Module):
         """`styles`: the four style projections if the caller already computed them (one batched GEMM for all blocks)."""
         mean_st1, std_st1, mean_st2, std_st2 = styles if styles is not None else [lin(style) for lin in self.style_linears()]
         out = self.conv1(x)
-        out = ops.ada_in(out, mean_st1, std_st1, 1e-5, 0.2)
-        out = self.conv2(out)
+        w2 = self.conv2.effective_weight()
+        n, c = out.shape[0], out.shape[-1]
+        if ops.norm_conv_ok(out, w2):                 # ada_in -> LeakyReLU -> conv2 as one fused node (bf16 tensor-core path)
+            out = ops.norm_conv(out, std_st1.reshape(n, c), mean_st1.reshape(n, c), w2, self.conv2.bias, self.conv2.kernel_size, 1, 1e-5, 0.2)
+        else:
+            out = ops.ada_in(out, mean_st1, std_st1, 1e-5, 0.2)
+            out = ops.Conv2dFn.apply(out, w2, self.conv2.bias, self.conv2.kernel_size, ops.PRE_NONE, 0.2)
         out = ops.ada_in(out, mean_st2, std_st2, 1e-5)
         return ops.AddFn.apply(out, x)
 
@@ -320,9 +336,19 @@ class AdaResBlockUp2(nn.Module):
 
     def forward(self, x, style, styles=None):
         mean_st1, std_st1, mean_st2, std_st2 = styles if styles is not None else [lin(style) for lin in self.style_linears()]
+        w1 = self.conv_r1.effective_weight()
+        n = x.shape[0]
+        if ops.norm_conv_ok(x, w1):                   # same fusion as ResBlockUp with ada_in statistics
+            res = self.conv_l1(x)
+            out = ops.norm_conv(x, std_st1.reshape(n, -1), mean_st1.reshape(n, -1), w1, self.conv_r1.bias, self.conv_r1.kernel_size, 1, 1e-5, 0.2, upsample=True)
+            w2 = self.conv_r2.effective_weight()
+            fuse_add = w2.shape[1] % 32 == 0
+            out = ops.norm_conv(out, std_st2.reshape(n, -1), mean_st2.reshape(n, -1), w2, self.conv_r2.bias, self.conv_r2.kernel_size, 1, 1e-5, 0.2,
+                                addend=res if fuse_add else None)
+            return out if fuse_add else ops.AddFn.apply(out, ops.upsample2(res))
         out_res = ops.upsample2(self.conv_l1(x))
         out = ops.ada_in(x, mean_st1, std_st1, 1e-5, 0.2)
-        out = self.conv_r1(out, ops.PRE_UPSAMPLE)
+        out = ops.Conv2dFn.apply(out, w1, self.conv_r1.bias, self.conv_r1.kernel_size, ops.PRE_UPSAMPLE, 0.2)
         out = ops.ada_in(out, mean_st2, std_st2, 1e-5, 0.2)
         out = self.conv_r2(out)
         return ops.AddFn.apply(out, out_res)

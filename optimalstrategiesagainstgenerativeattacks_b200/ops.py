@@ -438,7 +438,7 @@ class RowBroadcastFn(Function):
 # ------------------------------------------------------------------------------------------------------------
 # block-level fused operators (bf16 tensor-core path, first order)
 # ------------------------------------------------------------------------------------------------------------
-EPI_LRELU, EPI_MASK, EPI_ADD, EPI_POOL, EPI_ADDUP = 1, 2, 4, 8, 16
+EPI_LRELU, EPI_MASK, EPI_ADD, EPI_POOL, EPI_ADDUP, EPI_UNIT = 1, 2, 4, 8, 16, 32
 
 
 class Act:
@@ -1268,7 +1268,7 @@ class _NormFn(Function):
         hw = h * w
         yref = C.ptr(y) if slope != 1.0 else None
         red = _empty((5, n, c), torch.float32, x)         # s1 | s2 | A | B | C
-        C.call("gim_norm_bwd_reduce", C.ptr(gy), C.ptr(x), yref, st[0].data_ptr(), red[0].data_ptr(), red[1].data_ptr(),
+        C.call("gim_norm_bwd_reduce", C.ptr(gy), C.ptr(x), yref, st[0].data_ptr(), None, None, red[0].data_ptr(), red[1].data_ptr(),
                n, hw, c, slope, C.dtype_code(x))
         if mode == 0:
             g_scale = _empty((c,), torch.float32, x)
@@ -1279,9 +1279,96 @@ class _NormFn(Function):
         C.call("gim_norm_bwd_coeffs", mode, st[1].data_ptr(), red[0].data_ptr(), red[1].data_ptr(), C.ptr(p_scale),
                red[2].data_ptr(), red[3].data_ptr(), red[4].data_ptr(), C.ptr(g_scale), C.ptr(g_shift), n, hw, c, eps)
         gx = torch.empty_like(x)
-        C.call("gim_norm_bwd_apply", C.ptr(gy), C.ptr(x), yref, st[0].data_ptr(), red[2].data_ptr(), red[3].data_ptr(),
+        C.call("gim_norm_bwd_apply", C.ptr(gy), C.ptr(x), yref, st[0].data_ptr(), None, None, red[2].data_ptr(), red[3].data_ptr(),
                red[4].data_ptr(), C.ptr(gx), n, hw, c, slope, C.dtype_code(x))
         return gx, g_scale, g_shift, None, None, None
+
+
+class NormConvFn(Function):
+    """conv_k(prologue(norm(x))) as ONE autograd node on the bf16 tensor-core path: InstanceNorm2d (mode 0) or ada_in (mode 1), LeakyReLU,
+    optional nearest x2 upsample and the convolution that consumes them (reference model_blocks.py:760-768 ResBlockUp, :805-811
+    AdaResBlock2, :851-861 AdaResBlockUp2).  Forward: statistics -> coefficients -> ONE pass that writes the (upsampled) bf16 operand --
+    the fp32 normalised activation is never materialised -- -> tcgen05 convolution, optionally with the block's residual branch added
+    in its epilogue (`addend`: the half-resolution 1x1 branch, nearest-upsampled on the fly).  Backward: the upsample's sum-pooling is
+    folded into the input-gradient convolution's epilogue, the activation mask is recomputed from the coefficients.  First order only."""
+
+    @staticmethod
+    def forward(ctx, x, p_scale, p_shift, w32, bias, addend, mode, eps, slope, upsample, ks):
+        x = _c(x)
+        w32 = _c(w32)
+        n, h, w, c = x.shape
+        hw = h * w
+        p_scale, p_shift = _c(p_scale.float()), _c(p_shift.float())
+        st = _empty((4, n, c), torch.float32, x)          # mean | m2 | a | b
+        C.call("gim_norm_stats", C.ptr(x), st[0].data_ptr(), st[1].data_ptr(), n, hw, c, C.F32)
+        C.call("gim_norm_coeffs", mode, st[0].data_ptr(), st[1].data_ptr(), C.ptr(p_scale), C.ptr(p_shift), st[2].data_ptr(), st[3].data_ptr(), n, hw, c, eps)
+        oh, ow = (2 * h, 2 * w) if upsample else (h, w)
+        xop = _empty((n, oh, ow, c), torch.bfloat16, x)
+        C.call("gim_norm_act_operand", C.ptr(x), st[0].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), C.ptr(xop), n, h, w, c, slope, 1 if upsample else 0)
+        w_op = _weight_as(w32, torch.bfloat16, False)
+        co = w32.shape[1]
+        if addend is not None:                            # + nearest-upsampled half-resolution residual branch, inside the epilogue
+            y = _conv_tc_fused(xop, w_op, bias, ks, torch.float32, EPI_ADDUP | EPI_UNIT, addend=_c(addend))
+        elif co % 32 == 0:
+            y = _conv_tc_fused(xop, w_op, bias, ks, torch.float32)
+        else:
+            y = _conv_raw(xop, w_op, bias, ks)
+        ctx.cfg = (mode, eps, slope, upsample, ks, bias is not None, addend is not None)
+        ctx.bias_param = bias
+        ctx.save_for_backward(x, st, p_scale, xop, w32)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, st, p_scale, xop, w32 = ctx.saved_tensors
+        mode, eps, slope, upsample, ks, has_bias, has_add = ctx.cfg
+        n, h, w, c = x.shape
+        hw = h * w
+        gy = _c(gy)
+        gb = None
+        if has_bias and ctx.needs_input_grad[4]:
+            gb = _bias_grad_with_operand(gy, ctx.bias_param)     # bf16 operand copy of gy + bias gradient in one pass
+        gop = _operand(gy)
+        gw = _wgrad_raw(xop, gop, ks) if ctx.needs_input_grad[3] else None
+        g_add = None
+        if has_add and ctx.needs_input_grad[5]:                  # d/d(half-resolution residual) = 2x2 sums of gy
+            g_add = _empty((n, gy.shape[1] // 2, gy.shape[2] // 2, gy.shape[3]), torch.float32, gy)
+            C.call("gim_pool2_sum", C.ptr(gy), None, C.ptr(g_add), n, gy.shape[1], gy.shape[2], gy.shape[3], 1.0, C.F32)
+        gx = g_scale = g_shift = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            w_fl = _weight_as(w32, torch.bfloat16, True)
+            if upsample and c % 32 == 0:
+                g = _conv_tc_fused(gop, w_fl, None, ks, torch.float32, EPI_POOL | EPI_UNIT, out=_empty((n, h, w, c), torch.float32, x))      # input gradient, 2x2-summed in the epilogue
+            else:
+                g = _conv_tc_fused(gop, w_fl, None, ks, torch.float32) if c % 32 == 0 else _conv_raw(gop, w_fl, None, ks)
+                if upsample:
+                    g2 = _empty((n, h, w, c), torch.float32, g)
+                    C.call("gim_pool2_sum", C.ptr(g), None, C.ptr(g2), n, 2 * h, 2 * w, c, 1.0, C.F32)
+                    g = g2
+            red = _empty((5, n, c), torch.float32, x)         # s1 | s2 | A | B | C
+            act_a, act_b = (st[2].data_ptr(), st[3].data_ptr()) if slope != 1.0 else (None, None)
+            C.call("gim_norm_bwd_reduce", C.ptr(g), C.ptr(x), None, st[0].data_ptr(), act_a, act_b, red[0].data_ptr(), red[1].data_ptr(), n, hw, c, slope, C.F32)
+            if mode == 0:
+                g_scale, g_shift = _empty((c,), torch.float32, x), _empty((c,), torch.float32, x)
+            else:
+                g_scale, g_shift = _empty((n, c), torch.float32, x), _empty((n, c), torch.float32, x)
+            C.call("gim_norm_bwd_coeffs", mode, st[1].data_ptr(), red[0].data_ptr(), red[1].data_ptr(), C.ptr(p_scale),
+                   red[2].data_ptr(), red[3].data_ptr(), red[4].data_ptr(), C.ptr(g_scale), C.ptr(g_shift), n, hw, c, eps)
+            gx = torch.empty_like(x)
+            C.call("gim_norm_bwd_apply", C.ptr(g), C.ptr(x), None, st[0].data_ptr(), act_a, act_b, red[2].data_ptr(), red[3].data_ptr(),
+                   red[4].data_ptr(), C.ptr(gx), n, hw, c, slope, C.F32)
+        return gx, g_scale, g_shift, gw, gb, g_add, None, None, None, None, None
+
+
+def norm_conv_ok(x, w32):
+    """The fused node needs the tensor-core path, fp32 NHWC input with c % 8 == 0 and a tensor-core friendly output width."""
+    return fused_blocks_enabled() and x.dtype == torch.float32 and x.shape[-1] % 8 == 0 and w32.shape[1] % 16 == 0 and x.shape[0] <= 65535
+
+
+def norm_conv(x, p_scale, p_shift, w32, bias, ks, mode, eps=1e-5, slope=LRELU_SLOPE, upsample=False, addend=None):
+    """mode 0: InstanceNorm2d(affine) with (weight, bias) = (p_scale, p_shift); mode 1: ada_in with (std_style, mean_style)."""
+    return NormConvFn.apply(x, p_scale, p_shift, w32, bias, addend, mode, eps, slope, upsample, ks)
 
 
 def instance_norm(x, weight, bias, eps=1e-5, slope=1.0):

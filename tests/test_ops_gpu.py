@@ -581,3 +581,73 @@ def test_encoder_merged_attention_projections(precision, tol):
     for name, a_, b_ in zip(names, g_f, g_c):
         assert float(b_.abs().max()) > 0, name
         assert rel_err(a_, b_) < (tol if precision == "fp32" else 2.5 * tol), name
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,ci,co,k,h,w,upsample,with_add", [(3, 64, 64, 3, 8, 8, True, False), (2, 128, 64, 3, 4, 4, False, True), (5, 512, 512, 3, 1, 1, True, False),
+                                                              (2, 64, 32, 9, 8, 8, False, True), (3, 32, 48, 3, 6, 10, False, False), (2, 64, 128, 3, 2, 2, True, False)])
+def test_norm_conv_fused(mode, n, ci, co, k, h, w, upsample, with_add):
+    """The fused norm -> LeakyReLU -> (nearest x2) -> conv (+ upsampled half-resolution residual) node of the attacker's blocks against the float64
+    statement (reference model_blocks.py:760-768, 805-811, 851-861) and against the composition of elementary operators it replaces."""
+    ops = ops_mod()
+    ops.set_precision("bf16")
+    if h * w == 1 and mode == 1:
+        pytest.skip("ada_in needs more than one pixel")
+    x64 = rnd(n, ci, h, w, seed=1).requires_grad_()
+    w64 = (rnd(co, ci, k, k, seed=2) / np.sqrt(ci * k * k)).requires_grad_()
+    b64 = rnd(co, seed=3, scale=0.1).requires_grad_()
+    if mode == 0:
+        sc64, sh64 = (1.0 + 0.1 * rnd(ci, seed=4)).requires_grad_(), rnd(ci, seed=5, scale=0.1).requires_grad_()
+    else:
+        sc64, sh64 = (1.0 + 0.1 * rnd(n, ci, seed=4)).requires_grad_(), rnd(n, ci, seed=5, scale=0.1).requires_grad_()
+    oh, ow = (2 * h, 2 * w) if upsample else (h, w)
+    add64 = rnd(n, co, oh // 2, ow // 2, seed=6).requires_grad_() if with_add else None
+    # float64 statement
+    mu = x64.mean(dim=(2, 3), keepdim=True)
+    if mode == 0:
+        xn = (x64 - mu) / torch.sqrt(((x64 - mu) ** 2).mean(dim=(2, 3), keepdim=True) + 1e-5) * sc64.view(1, -1, 1, 1) + sh64.view(1, -1, 1, 1)
+    else:
+        sd = torch.sqrt(((x64 - mu) ** 2).sum(dim=(2, 3), keepdim=True) / (h * w - 1)) + 1e-5
+        xn = sc64.view(n, ci, 1, 1) * (x64 - mu) / sd + sh64.view(n, ci, 1, 1)
+    t = F.leaky_relu(xn, 0.2)
+    if upsample:
+        t = F.interpolate(t, scale_factor=2, mode="nearest")
+    y64 = F.conv2d(t, w64, b64, padding=(k - 1) // 2)
+    if with_add:
+        y64 = y64 + F.interpolate(add64, scale_factor=2, mode="nearest")
+    probe = rnd(*y64.shape, seed=9)
+    wrt = [x64, sc64, sh64, w64, b64] + ([add64] if with_add else [])
+    ref = torch.autograd.grad((y64 * probe).sum(), wrt)
+    pr = probe.permute(0, 2, 3, 1).contiguous().to("cuda", torch.float32)
+
+    def run(fused):
+        x = to_dev_nhwc(x64.detach(), torch.float32)
+        wp = pack_w(w64.detach())
+        b = b64.detach().to("cuda", torch.float32).requires_grad_()
+        sc, sh = (v.detach().to("cuda", torch.float32).requires_grad_() for v in (sc64, sh64))
+        add = to_dev_nhwc(add64.detach(), torch.float32) if with_add else None
+        if fused:
+            assert ops.norm_conv_ok(x, wp)
+            y = ops.norm_conv(x, sc, sh, wp, b, k, mode, 1e-5, 0.2, upsample=upsample, addend=add)
+        else:
+            y = ops.instance_norm(x, sc, sh, 1e-5, 0.2) if mode == 0 else ops.ada_in(x, sh, sc, 1e-5, 0.2)
+            y = ops.conv2d(y, wp, b, k, ops.PRE_UPSAMPLE if upsample else ops.PRE_NONE, 0.2)
+            if with_add:
+                y = ops.AddFn.apply(y, ops.upsample2(add))
+        g = torch.autograd.grad(ops.DotFn.apply(y, pr).sum(), [x, sc, sh, wp, b] + ([add] if with_add else []))
+        return y, g
+
+    yf, gf = run(True)
+    yc, gc = run(False)
+    assert rel_err(nchw(yf), y64) < BF16_TOL
+    assert rel_err(yf, yc) < 1e-5                      # identical operands, fp32 accumulation in both
+    for i, nm in enumerate(["x", "scale", "shift", "w", "b"] + (["addend"] if with_add else [])):
+        a, c, r = gf[i], gc[i], ref[i]
+        if nm == "w":
+            a, c = unpack_w(a, k), unpack_w(c, k)
+        elif a.dim() == 4:
+            a, c = nchw(a), nchw(c)
+        if float(r.norm()) < 1e-9:                     # (the bias in front of nothing normalising it is fine; degenerate 1x1 cases give zeros)
+            continue
+        assert rel_err(a, c) < 5e-3, (nm, rel_err(a, c))
+        assert rel_err(a, r) < (5e-2 if h * w <= 4 else BF16_TOL), (nm, rel_err(a, r))
