@@ -216,3 +216,15 @@ def test_image_grid_and_png_writer(tmp_path):
     pix = np.frombuffer(rows, dtype=np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
     want = (log.images[("train imgs_0003", "leaked")][1].clamp(0, 1) * 255 + 0.5).to(torch.uint8).permute(1, 2, 0).numpy()
     assert np.array_equal(pix, want) and np.abs(want[2:8, 2:7].astype(float) / 255 - imgs[0].permute(1, 2, 0).numpy()).max() < 3e-3
+
+
+def test_eval_auc_orientation_matches_reference_labels():
+    """authentication_score.py:94-96: y_true = 1 for real, 0 for fake, y_score = the authenticator's logits.  An authenticator that scores
+    real samples higher must get AUC 1, the opposite ordering AUC 0 (what an untrained authenticator shows on an untrained attacker's
+    out-of-distribution images -- tools/bench_extra.py's `auc_random_init: 0.0` -- is this second case, not a label slip)."""
+    ds = D.ResidentGIMDataSet(D.synthetic_classes(4, 16, 1, 4, seed=1), m=2, n=3, k=2, example_cnt_per_class=3, device="cpu", seed=2)
+    au = AE.Authenticator(lambda test_sample, si_sample: test_sample.mean(dim=(1, 2, 3, 4)).unsqueeze(1), th=0.)
+    for shift, want in ((-10.0, 1.0), (10.0, 0.0)):
+        im = AE.Impersonator(lambda leaked_sample, n, s=shift: leaked_sample[:, :1].expand(-1, n, -1, -1, -1) + s)
+        acc, acc_fake, acc_real, auc = AE.eval_authenticator_and_impersonator("cpu", ds, 4, 0, au, im)
+        assert auc == want, (shift, auc)
