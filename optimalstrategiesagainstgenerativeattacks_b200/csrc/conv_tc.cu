@@ -853,10 +853,12 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     const bool v2 = !use_v1 && pick_block_n(cout) >= 32 && (!tiny || force_v2);
     if (!v2 && (epi & ~kEpiUnit) != 0) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: fused epilogues need cout >= 32");
     p.block_n = v2 ? pick_block_n2(cout, m_tiles) : pick_block_n(cout);
-    static const int force_msub = env_int("GIM_CONV_MSUB", 0), pair_mode = env_int("GIM_CONV_PAIR", 1);
+    static const int force_msub = env_int("GIM_CONV_MSUB", 0), pair_mode = env_int("GIM_CONV_PAIR", 2);
     p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;
     if (force_msub == 1 || (force_msub == 2 && v2 && p.block_n <= 128)) p.m_sub = force_msub;
-    // cta_group::2: pairs of CTAs share one 256 x 256 MMA tile, each staging half of the weight tile
+    // cta_group::2: pairs of CTAs share one 256 x 256 MMA tile, each staging half of the weight tile.  pair_mode 2 (default since round 2)
+    // also pairs the 128-column layers (two pixel tiles per CTA, M = 256 per MMA, half of the 128-row weight tile per CTA): measured
+    // +7 % on the 9x9 128->128 layer, +1 % on the 3x3 one, +0.6 % on the O step (tools/conv_bench.py, bench.py A/B)
     p.pair = (v2 && pair_mode && p.block_k == 64 && m_tiles >= 2 &&
               (p.block_n == 256 || (p.block_n == 128 && p.m_sub == 2 && cout % 128 == 0 && pair_mode > 1))) ? 1 : 0;
     const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + (p.pair ? p.block_n / 2 : p.block_n) * p.block_k * 2 + 1023) & ~1023;
