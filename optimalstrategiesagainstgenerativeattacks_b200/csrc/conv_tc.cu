@@ -86,6 +86,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane of a converged warp (the compiler keeps the surrounding warp-uniform values in uniform registers: an `if (lane == 0)`
+// role loop instead makes every descriptor a vector register that has to be moved with R2UR before each UTCHMMA)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
 // arrive on an mbarrier when all previously issued MMAs have completed (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -192,6 +199,16 @@ struct ConvTcParams {
     int n_staging;                               // output staging boxes of the epilogue ring (persistent kernel): 2..4
     int pair;                                    // 1: cta_group::2 kernel variant (two-CTA clusters)
     int debug;                                   // GIM_CONV_DEBUG bits (profiling experiments only): 1 no TMA store, 2 no proxy fence, 4 no smem staging
+    // halo staging (persistent kernel, k > 1): ONE activation box {64 ch, bw+k-1, bn, bh+k-1} per 64-channel block serves all k*k
+    // filter taps -- tap (r, q) is the same smem box read through a descriptor whose start address is advanced by
+    // (r*bn*(bw+k-1) + q) rows of 128 B and whose 8-row groups are (bw+k-1) rows apart (bw == 8; tools/halo_probe.cu shows that
+    // tcgen05.mma un-swizzles by absolute smem address bits, so neither needs 1024-byte alignment).  Pixel rows of the tile are
+    // ordered (h, image, w): with two 8x8 images per tile the sixteen 8-pixel groups are still an arithmetic progression.
+    int halo;                                    // 1: halo staging; tensor maps are then laid out {c, w, n, h}
+    int halo_w;                                  // bw + k - 1: rows of 128 B between consecutive 8-pixel groups
+    int halo_bytes;                              // one halo box, rounded up to 1024 B
+    int halo_tx;                                 // exact bytes of one halo box (mbarrier transaction count)
+    int a_stages, b_stages;                      // depths of the activation (per channel block) and weight (per tap) rings
     float slope;
 };
 
@@ -399,15 +416,21 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
     const int a_bytes = kBlockM * p.block_k * 2;
     const int b_off = p.m_sub * a_bytes;
     const int stage_bytes = (b_off + b_rows * p.block_k * 2 + 1023) & ~1023;
-    uint8_t* staging = smem + p.stages * stage_bytes;
+    // halo mode: two rings -- activation halos (one per 64-channel block, shared by all taps), then weight boxes (one per tap)
+    const int a_stage_bytes = p.m_sub * p.halo_bytes;
+    const int b_bytes = b_rows * p.block_k * 2;
+    uint8_t* ring_b = smem + p.a_stages * a_stage_bytes;
+    uint8_t* staging = p.halo ? ring_b + p.b_stages * b_bytes : smem + p.stages * stage_bytes;
     float* bias_all = (float*)(staging + 2 * p.n_staging * kBoxBytes);        // 256 floats per epilogue group
-    uint64_t* full_bar = (uint64_t*)(bias_all + 512);
-    uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* tmem_full_bar = empty_bar + p.stages;                            // [2]
+    uint64_t* full_bar = (uint64_t*)(bias_all + 512);                          // halo mode: weight ring (b_stages)
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* a_full_bar = empty_bar + 8;                                      // halo mode: activation ring (a_stages <= 4)
+    uint64_t* a_empty_bar = a_full_bar + 4;
+    uint64_t* tmem_full_bar = a_empty_bar + 4;                                 // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;                              // [2]
     uint32_t* tmem_slot = (uint32_t*)(tmem_empty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // shfl: provably warp-uniform role dispatch
     const int pad = (p.ks - 1) / 2;
     const int kc_per_tap = (p.cin + p.block_k - 1) / p.block_k;
     const int num_kb = p.ks * p.ks * kc_per_tap;
@@ -423,7 +446,9 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_y);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }   // two producers: A (warp 0), B (warp 2)
+        // one ring, two producers (A: warp 0, B: warp 2) arm the same barrier; halo mode: one producer per ring
+        for (int s = 0; s < 8; ++s) { mbar_init(&full_bar[s], p.halo ? 1 : 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&a_full_bar[s], 1); mbar_init(&a_empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], kPair ? 16 : 8); }
         fence_barrier_init();
     }
@@ -438,7 +463,58 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
     if (warp == 0 || warp == 2) {
         // two TMA producers share the ring: warp 0 streams the activation boxes (A), warp 2 the weight boxes (B); each arms the
         // full barrier with its own byte count
-        if (lane == 0) {
+        if (lane == 0 && p.halo) {
+            // halo mode.  warp 0: one halo box per (tile, 64-channel block); warp 2: one weight box per (tile, channel block, tap)
+            const bool is_a = warp == 0;
+            int s = 0;
+            uint32_t ph = 1;
+            const uint32_t tx_bytes = (is_a ? (uint32_t)(p.m_sub * p.halo_tx) : (uint32_t)b_bytes) * (kPair ? 2u : 1u);
+            const int taps = p.ks * p.ks;
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                const int mt = tile / n_tiles;
+                const int n0 = (tile - mt * n_tiles) * p.block_n;
+                if (is_a) {
+                    int w0[2], h0[2], img0[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        int t = (kPair ? mt * 2 + (int)rank : mt) * p.m_sub + j;
+                        const int tw = t % p.tiles_w; t /= p.tiles_w;
+                        const int th = t % p.tiles_h; t /= p.tiles_h;
+                        w0[j] = tw * p.bw - pad; h0[j] = th * p.bh - pad; img0[j] = t * p.bn;
+                    }
+                    for (int kc = 0; kc < p.cin; kc += kBlockK) {
+                        mbar_wait(&a_empty_bar[s], ph);
+                        uint8_t* sa = smem + s * a_stage_bytes;
+                        if (kPair) {
+                            if (rank == 0) mbar_expect_tx(&a_full_bar[s], tx_bytes);
+                            tma_load_4d_2sm(sa, &map_x, &a_full_bar[s], kc, w0[0], img0[0], h0[0]);
+                            if (p.m_sub == 2) tma_load_4d_2sm(sa + p.halo_bytes, &map_x, &a_full_bar[s], kc, w0[1], img0[1], h0[1]);
+                        } else {
+                            mbar_expect_tx(&a_full_bar[s], tx_bytes);
+                            tma_load_4d(sa, &map_x, &a_full_bar[s], kc, w0[0], img0[0], h0[0]);
+                            if (p.m_sub == 2) tma_load_4d(sa + p.halo_bytes, &map_x, &a_full_bar[s], kc, w0[1], img0[1], h0[1]);
+                        }
+                        if (++s == p.a_stages) { s = 0; ph ^= 1; }
+                    }
+                } else {
+                    const int row0 = n0 + (int)rank * b_rows;
+                    for (int kc = 0; kc < p.cin; kc += kBlockK) {
+                        for (int tap = 0; tap < taps; ++tap) {
+                            mbar_wait(&empty_bar[s], ph);
+                            uint8_t* sb = ring_b + s * b_bytes;
+                            if (kPair) {
+                                if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
+                                tma_load_2d_2sm(sb, &map_w, &full_bar[s], kc, tap * p.cout + row0);
+                            } else {
+                                mbar_expect_tx(&full_bar[s], tx_bytes);
+                                tma_load_2d(sb, &map_w, &full_bar[s], kc, tap * p.cout + row0);
+                            }
+                            if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             const bool is_a = warp == 0;
             int s = 0;
             uint32_t ph = 1;                                  // parity to wait for on empty[s]: the first pass over the ring is free
@@ -483,7 +559,8 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {                    // pair mode: the leader CTA issues the MMAs of both CTAs
+        if (rank == 0) {                                 // pair mode: the leader CTA issues the MMAs of both CTAs
+            // the WHOLE warp walks the loops (uniform control flow, descriptors in uniform registers); one elected lane issues
             const uint32_t idesc = make_idesc((uint32_t)p.block_n, 0, 0, kPair ? 256u : 128u);
             // descriptors differ between stages only in the 14-bit start-address field: build them once
             const bool k64 = p.block_k == 64;
@@ -492,43 +569,109 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             const uint64_t desc_b0 = k64 ? make_desc_sw128(s0 + b_off, 16, 1024) : make_desc(s0 + b_off, 16, 256, 6);
             const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), a_step = (uint64_t)(a_bytes >> 4);
             const bool two = p.m_sub == 2;
-            int s = 0;
-            uint32_t ph = 0, i = 0;
-            uint64_t da = desc_a0, db = desc_b0;
-            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++i) {
-                const uint32_t buf = i & 1;
-                mbar_wait(&tmem_empty_bar[buf], ((i >> 1) & 1) ^ 1);          // epilogue has drained this accumulator pair
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + buf * buf_cols;
-                const uint32_t tmem_d1 = tmem_d + (uint32_t)p.block_n;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
+            if (p.halo) {
+                // halo mode: per 64-channel block one activation halo (a ring), per tap one weight box (b ring); the tap only moves the
+                // start address of the A descriptor inside the halo: (r * bn * halo_w + q) rows of 128 B; 8-pixel groups halo_w rows apart
+                const uint64_t desc_ha0 = make_desc_sw128(s0, 16, (uint32_t)p.halo_w * 128u);
+                const uint64_t desc_hb0 = make_desc_sw128(smem_u32(ring_b), 16, 1024);
+                const uint64_t a_stage_step = (uint64_t)(a_stage_bytes >> 4), halo_step = (uint64_t)(p.halo_bytes >> 4), b_step = (uint64_t)(b_bytes >> 4);
+                const int row_r = p.bn * p.halo_w;
+                int sa = 0, sb = 0;
+                uint32_t pha = 0, phb = 0, i = 0;
+                for (int tile = tile0; tile < total_tiles; tile += tile_step, ++i) {
+                    const uint32_t buf = i & 1;
+                    mbar_wait(&tmem_empty_bar[buf], ((i >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t acc = kb != 0 ? 1u : 0u;
-                    if (kPair) {
+                    const uint32_t tmem_d = tmem_base + buf * buf_cols;
+                    const uint32_t tmem_d1 = tmem_d + (uint32_t)p.block_n;
+                    uint32_t acc = 0;
+                    for (int kc = 0; kc < p.cin; kc += kBlockK) {
+                        mbar_wait(&a_full_bar[sa], pha);
+                        tc_fence_after();
+                        const uint64_t da_stage = desc_ha0 + (uint64_t)sa * a_stage_step;
+                        for (int r = 0; r < p.ks; ++r) {
+                            for (int q = 0; q < p.ks; ++q) {
+                                mbar_wait(&full_bar[sb], phb);
+                                tc_fence_after();
+                                const uint64_t da = da_stage + (uint64_t)((r * row_r + q) * 8);
+                                const uint64_t db = desc_hb0 + (uint64_t)sb * b_step;
+                                if (elect_one()) {
+                                    if (kPair) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
-                            if (two) umma_bf16_2sm(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
-                        }
-                        umma_commit_2sm(&empty_bar[s]);                        // frees this smem slot in both CTAs
-                    } else {
-                        if (k64) {
+                                        for (int k = 0; k < 4; ++k) {
+                                            umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                            if (two) umma_bf16_2sm(tmem_d1, da + halo_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                        }
+                                        umma_commit_2sm(&empty_bar[sb]);
+                                    } else {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {                      // +32 B along K inside the 128-byte swizzle row
-                                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
-                                if (two) umma_bf16(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                        for (int k = 0; k < 4; ++k) {
+                                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                            if (two) umma_bf16(tmem_d1, da + halo_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                        }
+                                        umma_commit(&empty_bar[sb]);
+                                    }
+                                }
+                                __syncwarp();
+                                acc = 1u;
+                                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                             }
-                        } else {
-                            umma_bf16(tmem_d, da, db, idesc, acc);
-                            if (two) umma_bf16(tmem_d1, da + a_step, db, idesc, acc);
                         }
-                        umma_commit(&empty_bar[s]);
+                        if (elect_one()) {                                    // all taps have read this halo
+                            if (kPair) umma_commit_2sm(&a_empty_bar[sa]); else umma_commit(&a_empty_bar[sa]);
+                        }
+                        __syncwarp();
+                        if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
                     }
-                    da += stage_step; db += stage_step;
-                    if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
+                    if (elect_one()) {
+                        if (kPair) umma_commit_2sm(&tmem_full_bar[buf]); else umma_commit(&tmem_full_bar[buf]);
+                    }
+                    __syncwarp();
                 }
-                if (kPair) umma_commit_2sm(&tmem_full_bar[buf]); else umma_commit(&tmem_full_bar[buf]);
+            } else {
+                int s = 0;
+                uint32_t ph = 0, i = 0;
+                uint64_t da = desc_a0, db = desc_b0;
+                for (int tile = tile0; tile < total_tiles; tile += tile_step, ++i) {
+                    const uint32_t buf = i & 1;
+                    mbar_wait(&tmem_empty_bar[buf], ((i >> 1) & 1) ^ 1);          // epilogue has drained this accumulator pair
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * buf_cols;
+                    const uint32_t tmem_d1 = tmem_d + (uint32_t)p.block_n;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t acc = kb != 0 ? 1u : 0u;
+                        if (!elect_one()) {
+                        } else if (kPair) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                if (two) umma_bf16_2sm(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                            }
+                            umma_commit_2sm(&empty_bar[s]);                        // frees this smem slot in both CTAs
+                        } else {
+                            if (k64) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {                      // +32 B along K inside the 128-byte swizzle row
+                                    umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                    if (two) umma_bf16(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                }
+                            } else {
+                                umma_bf16(tmem_d, da, db, idesc, acc);
+                                if (two) umma_bf16(tmem_d1, da + a_step, db, idesc, acc);
+                            }
+                            umma_commit(&empty_bar[s]);
+                        }
+                        __syncwarp();
+                        da += stage_step; db += stage_step;
+                        if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
+                    }
+                    if (elect_one()) {
+                        if (kPair) umma_commit_2sm(&tmem_full_bar[buf]); else umma_commit(&tmem_full_bar[buf]);
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else if (warp >= 4) {
@@ -544,7 +687,11 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
         const int bar_id = 1 + grp;
         uint32_t chunk_ctr = 0;                          // running chunk index (identical in both groups): parity selects the owner
         int bias_n0 = -1;
-        const int lw = m % p.bw, lh = (m / p.bw) % p.bh, ln = m / (p.bw * p.bh);
+        // pixel of tile row m: (image, h, w) order, or (h, image, w) in halo mode (the tensor maps are then {c, w, n, h})
+        const int lw = m % p.bw;
+        const int lh = p.halo ? m / (p.bw * p.bn) : (m / p.bw) % p.bh;
+        const int ln = p.halo ? (m / p.bw) % p.bn : m / (p.bw * p.bh);
+        const int lane_dh = p.halo ? p.bw * p.bn : p.bw;      // lane distance of the pixel one row below
         const bool store_thread = (et == 0);
         const float aux_scale = (p.epi & kEpiUnit) ? 1.f : 0.25f;      // nearest-upsample / its backward (sum pooling) vs AvgPool and its backward
         const int cols_per_chunk = p.out_f32 ? 32 : 64;
@@ -593,7 +740,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 f[j] += __shfl_xor_sync(0xffffffffu, f[j], 1);
-                                f[j] += __shfl_xor_sync(0xffffffffu, f[j], p.bw);
+                                f[j] += __shfl_xor_sync(0xffffffffu, f[j], lane_dh);
                             }
                             const int sub4 = (lw & 1) | ((lh & 1) << 1);
                             float o[8];
@@ -609,7 +756,8 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                                 o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w;
                                 o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
                             }
-                            const int pm = ((ln * (p.bh >> 1) + (lh >> 1)) * (p.bw >> 1)) + (lw >> 1);       // pooled row inside the box: 0..31
+                            const int pm = p.halo ? (((lh >> 1) * p.bn + ln) * (p.bw >> 1)) + (lw >> 1)
+                                                  : ((ln * (p.bh >> 1) + (lh >> 1)) * (p.bw >> 1)) + (lw >> 1);       // pooled row inside the box: 0..31
                             uint8_t* prow = staging + sbuf * kBoxBytes + pm * 128;
                             *reinterpret_cast<float4*>(prow + (((2 * sub4) ^ (pm & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                             *reinterpret_cast<float4*>(prow + (((2 * sub4 + 1) ^ (pm & 7)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
@@ -690,8 +838,9 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (store_thread && !(p.debug & 1)) {
                         if (n0 + c0 < p.cout) {
-                            if (p.epi & kEpiPool) tma_store_4d(&map_y, staging + sbuf * kBoxBytes, n0 + c0, w0 >> 1, h0 >> 1, img0);
-                            else tma_store_4d(&map_y, staging + sbuf * kBoxBytes, n0 + c0, w0, h0, img0);
+                            const int sh = (p.epi & kEpiPool) ? 1 : 0;
+                            if (p.halo) tma_store_4d(&map_y, staging + sbuf * kBoxBytes, n0 + c0, w0 >> sh, img0, h0 >> sh);
+                            else tma_store_4d(&map_y, staging + sbuf * kBoxBytes, n0 + c0, w0 >> sh, h0 >> sh, img0);
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -750,25 +899,36 @@ static void pixel_box(int h, int w, int& bw, int& bh, int& bn) {
 }
 
 // 4-D map over an NHWC bf16 tensor, box {64 ch, bw, bh, bn}, 128B swizzle, zero OOB fill
-static bool make_act_map(CUtensorMap* map, const void* x, int n, int h, int w, int c, int bw, int bh, int bn, int box_k = kBlockK) {
+// nh_order: dimensions {c, w, n, h} (image index before the row index) -- the halo-mode tile layout
+static bool make_act_map(CUtensorMap* map, const void* x, int n, int h, int w, int c, int bw, int bh, int bn, int box_k = kBlockK, bool nh_order = false) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
     cuuint32_t box[4] = {(cuuint32_t)box_k, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    if (nh_order) {
+        dims[2] = (cuuint64_t)n; dims[3] = (cuuint64_t)h;
+        strides[1] = (cuuint64_t)h * w * c * 2; strides[2] = (cuuint64_t)w * c * 2;
+        box[2] = (cuuint32_t)bn; box[3] = (cuuint32_t)bh;
+    }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                box_k == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // 4-D map over the NHWC output (fp32: box of 32 columns, bf16: 64 columns = 128 B), 128B swizzle; TMA clips at the tensor border
-static bool make_out_map(CUtensorMap* map, void* y, int n, int h, int w, int c, int bw, int bh, int bn, int out_f32) {
+static bool make_out_map(CUtensorMap* map, void* y, int n, int h, int w, int c, int bw, int bh, int bn, int out_f32, bool nh_order = false) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     const cuuint64_t es = out_f32 ? 4 : 2;
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)c * es, (cuuint64_t)w * c * es, (cuuint64_t)h * w * c * es};
     cuuint32_t box[4] = {(cuuint32_t)(out_f32 ? 32 : 64), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    if (nh_order) {
+        dims[2] = (cuuint64_t)n; dims[3] = (cuuint64_t)h;
+        strides[1] = (cuuint64_t)h * w * c * es; strides[2] = (cuuint64_t)w * c * es;
+        box[2] = (cuuint32_t)bn; box[3] = (cuuint32_t)bh;
+    }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(map, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -833,24 +993,36 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
         p.bh = next_pow2(h) < kBlockM / p.bw ? next_pow2(h) : kBlockM / p.bw;
         p.bn = kBlockM / (p.bw * p.bh);
     }
+    p.block_k = cin <= 16 ? 16 : kBlockK;          // skinny inputs (padded images): 32-byte K rows, one MMA per filter tap
+    // halo staging (see ConvTcParams): 3x3 filters on maps of at least 8x8 pixels; tiles are 8 pixels wide so that every 8-row group of
+    // the A operand is one run of 8 consecutive halo rows
+    static const int halo_mode = env_int("GIM_CONV_HALO", 1), force_v2 = env_int("GIM_CONV_V2", 0);
+    // launch-latency-bound problems (e.g. Linear layers) stay on the non-persistent kernel
+    const long long m_tiles0 = (long long)((wd + p.bw - 1) / p.bw) * ((h + p.bh - 1) / p.bh) * ((n + p.bn - 1) / p.bn);
+    const bool tiny = m_tiles0 * ((cout + 127) / 128) <= num_sms() / 2 && (epi & ~kEpiUnit) == 0;
+    const bool v2 = !use_v1 && pick_block_n(cout) >= 32 && (!tiny || force_v2);
+    p.halo = (halo_mode && v2 && ks == 3 && p.block_k == kBlockK && h >= 8 && wd >= 8) ? 1 : 0;
+    if (p.halo) {
+        p.bw = 8;
+        p.bh = next_pow2(h) < 16 ? next_pow2(h) : 16;
+        p.bn = kBlockM / (p.bw * p.bh);
+    }
+    p.halo_w = p.bw + ks - 1;
+    p.halo_tx = 128 * p.halo_w * (p.bh + ks - 1) * p.bn;
+    p.halo_bytes = (p.halo_tx + 1023) & ~1023;
+    p.a_stages = p.b_stages = 0;
     p.tiles_w = (wd + p.bw - 1) / p.bw;
     p.tiles_h = (h + p.bh - 1) / p.bh;
     p.tiles_n = (n + p.bn - 1) / p.bn;
     p.out_f32 = out_f32;
     p.epi = epi;
     p.slope = slope;
-    p.block_k = cin <= 16 ? 16 : kBlockK;          // skinny inputs (padded images): 32-byte K rows, one MMA per filter tap
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     if (m_tiles > 2147483647LL / 64) return fail(GIM_E_ARG, "conv_fwd_tc: too many tiles");
     if ((epi & kEpiMask) && (!mask_ref || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the mask epilogue needs a reference tensor and cout % 32 == 0");
     if ((epi & (kEpiAdd | kEpiAddUp)) && (!addend || cout % 32 != 0)) return fail(GIM_E_ARG, "conv_fwd_tc: the add epilogue needs an addend tensor and cout % 32 == 0");
     if ((epi & kEpiAddUp) && ((epi & (kEpiAdd | kEpiPool)) || (h & 1) || (wd & 1))) return fail(GIM_E_ARG, "conv_fwd_tc: add-upsampled needs even h, w and excludes add / pool");
     CUtensorMap map_x, map_w, map_y;
-    static const int force_v2 = env_int("GIM_CONV_V2", 0);
-    // measured (tools/conv_bench.py): the persistent kernel wins whenever it can use the 256-wide N tile; with 128-wide tiles two
-    // co-resident non-persistent CTAs still issue MMAs faster than one persistent CTA
-    const bool tiny = m_tiles * ((cout + 127) / 128) <= num_sms() / 2 && (epi & ~kEpiUnit) == 0;      // e.g. Linear layers: launch latency only
-    const bool v2 = !use_v1 && pick_block_n(cout) >= 32 && (!tiny || force_v2);
     if (!v2 && (epi & ~kEpiUnit) != 0) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: fused epilogues need cout >= 32");
     p.block_n = v2 ? pick_block_n2(cout, m_tiles) : pick_block_n(cout);
     static const int force_msub = env_int("GIM_CONV_MSUB", 0), pair_mode = env_int("GIM_CONV_PAIR", 2);
@@ -863,9 +1035,11 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
               (p.block_n == 256 || (p.block_n == 128 && p.m_sub == 2 && cout % 128 == 0 && pair_mode > 1))) ? 1 : 0;
     const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + (p.pair ? p.block_n / 2 : p.block_n) * p.block_k * 2 + 1023) & ~1023;
     if (epi & kEpiPool) {
-        if (!make_out_map(&map_y, y, n, h / 2, wd / 2, cout, p.bw / 2, p.bh / 2, p.bn, 1)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(pooled y) failed");
-    } else if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
-    if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn, p.block_k)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
+        if (!make_out_map(&map_y, y, n, h / 2, wd / 2, cout, p.bw / 2, p.bh / 2, p.bn, 1, p.halo)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(pooled y) failed");
+    } else if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32, p.halo)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
+    if (p.halo) {
+        if (!make_act_map(&map_x, x, n, h, wd, cin, p.halo_w, p.bh + ks - 1, p.bn, p.block_k, true)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x halo) failed");
+    } else if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn, p.block_k)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
     if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.pair ? p.block_n / 2 : p.block_n, p.block_k))
         return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
     if (v2) {
@@ -878,7 +1052,19 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
         if (env_stages >= 2 && env_stages < stages) stages = env_stages;
         p.stages = stages;
         p.tma_store = 1;
-        const size_t smem = (size_t)stages * stage_bytes + fixed;
+        size_t smem = (size_t)stages * stage_bytes + fixed;
+        if (p.halo) {
+            // two halos in flight per pixel tile (each lasts 9 taps); the rest of the shared memory is the weight ring
+            static const int env_as = env_int("GIM_CONV_ASTAGES", 0);
+            const int budget = 227 * 1024 - fixed, b_bytes = (p.pair ? p.block_n / 2 : p.block_n) * kBlockK * 2;
+            p.a_stages = env_as >= 1 && env_as <= 4 ? env_as : 2;
+            int bs = (budget - p.a_stages * p.m_sub * p.halo_bytes) / b_bytes;
+            if (bs < 3) { p.a_stages = 1; bs = (budget - p.m_sub * p.halo_bytes) / b_bytes; }
+            if (bs < 2) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: halo staging does not fit in shared memory");
+            p.b_stages = bs > 8 ? 8 : bs;
+            if (env_stages >= 2 && env_stages < p.b_stages) p.b_stages = env_stages;
+            smem = (size_t)p.a_stages * p.m_sub * p.halo_bytes + (size_t)p.b_stages * b_bytes + fixed;
+        }
         static bool attr_set2 = false;
         if (!attr_set2) {
             if (cudaFuncSetAttribute(conv_fwd_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
