@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
     uint64_t* tmem_full_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // tile coordinates
     int t = blockIdx.x;
     const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -267,15 +267,16 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc((uint32_t)p.block_n, 0, 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t round = kb / p.stages;
-                mbar_wait(&full_bar[s], round & 1);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+        // the whole warp walks the loop (uniform control flow keeps the descriptors in uniform registers); one elected lane issues
+        const uint32_t idesc = make_idesc((uint32_t)p.block_n, 0, 0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t round = kb / p.stages;
+            mbar_wait(&full_bar[s], round & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * stage_bytes);
+            const uint32_t sb = sa + a_bytes;
+            if (elect_one()) {
                 if (p.block_k == 64) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -288,8 +289,10 @@ __global__ void __launch_bounds__(192, 2) conv_fwd_tc_kernel(const __grid_consta
                 }
                 umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
             }
-            umma_commit(tmem_full_bar);              // accumulator complete
+            __syncwarp();
         }
+        if (elect_one()) umma_commit(tmem_full_bar);              // accumulator complete
+        __syncwarp();
     } else {
         // ---- epilogue: TMEM -> registers -> (+bias) -> global NHWC ----
         mbar_wait(tmem_full_bar, 0);
@@ -1025,6 +1028,12 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     CUtensorMap map_x, map_w, map_y;
     if (!v2 && (epi & ~kEpiUnit) != 0) return fail(GIM_E_UNSUPPORTED, "conv_fwd_tc: fused epilogues need cout >= 32");
     p.block_n = v2 ? pick_block_n2(cout, m_tiles) : pick_block_n(cout);
+    if (!v2) {
+        // launch-latency-bound problems (Linear layers: a handful of 128-row tiles, long K): narrower N tiles put more CTAs -- and so more
+        // TMA streams -- on the chip; each CTA still walks the whole K range, which is what bounds the launch
+        static const int tiny_split = env_int("GIM_CONV_TINY_BN", 1);
+        while (tiny_split && p.block_n > 32 && cout % (p.block_n / 2) == 0 && m_tiles * ((cout + p.block_n - 1) / p.block_n) < num_sms()) p.block_n /= 2;
+    }
     static const int force_msub = env_int("GIM_CONV_MSUB", 0), pair_mode = env_int("GIM_CONV_PAIR", 2);
     p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;
     if (force_msub == 1 || (force_msub == 2 && v2 && p.block_n <= 128)) p.m_sub = force_msub;
@@ -1154,7 +1163,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
     uint64_t* tmem_full_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     int t = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tap = t % (p.ks * p.ks); t /= (p.ks * p.ks);
     const int co_groups = kPair ? p.co_tiles / 2 : p.co_tiles;
@@ -1214,7 +1223,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {                                 // whole warp, uniform control flow; one elected lane issues
             const uint32_t idesc = make_idesc((uint32_t)p.block_n, 1, 1, kPair ? 256u : 128u);
             const uint32_t s0 = smem_u32(smem);
             const uint64_t desc_a0 = make_desc_sw128(s0, kATileBytes, 1024), desc_b0 = make_desc_sw128(s0 + a_bytes, kATileBytes, 1024);
@@ -1227,16 +1236,22 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t acc = kb != 0 ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kBlockM / 16; ++k) {               // 128 pixels per stage = 8 MMAs of K = 16, 2 KB apart
-                    if (kPair) umma_bf16_2sm((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
-                    else umma_bf16((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
+                    for (int k = 0; k < kBlockM / 16; ++k) {               // 128 pixels per stage = 8 MMAs of K = 16, 2 KB apart
+                        if (kPair) umma_bf16_2sm((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
+                        else umma_bf16((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
+                    }
+                    if (kPair) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
                 }
-                if (kPair) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+                __syncwarp();
                 da += stage_step; db += stage_step;
                 if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
             }
-            if (kPair) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
+            if (elect_one()) {
+                if (kPair) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
         }
     } else {
         mbar_wait(tmem_full_bar, 0);

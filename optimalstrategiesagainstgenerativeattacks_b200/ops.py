@@ -12,6 +12,7 @@ Activations are NHWC tensors of the active precision (`set_precision`): float32 
 bfloat16 (tcgen05 tensor-core path).  Feature vectors, statistics, weights and weight gradients are float32.
 """
 import contextlib
+import os
 import weakref
 
 import torch
@@ -282,10 +283,60 @@ def _conv_raw(x, w_t, bias, ks):
     return y
 
 
-def _wgrad_raw(x, g, ks):
+# ---- weight gradients off the critical path ------------------------------------------------------------------------------------
+# In a backward pass only the input gradients chain from layer to layer; a weight gradient is not read before the batched spectral-norm
+# backward at the END of the pass (deferred_weight_grads).  Launched on a stream of their own (forked after the layer's output gradient
+# exists, joined by the flush), the weight-gradient kernels become parallel branches of the captured graph and fill the tail waves of
+# the persistent forward / input-gradient kernels.  Only when the consumer is known to be the deferred flush (`_wg_async_ok`).
+_wg = {"streams": {}, "used": [], "enabled": os.environ.get("GIM_WGRAD_STREAMS", "1") != "0"}
+_DEFERRED_GRAD_FNS = ("SpectralNormPreparedFnBackward", "SpectralNormFnBackward", "_MergedRowsFnBackward")
+
+
+def set_wgrad_streams(flag):
+    _wg["enabled"] = bool(flag)
+
+
+def _wg_async_ok(w):
+    """Forward-time check: the gradient of this weight tensor flows into a spectral-norm node (whose backward only queues it)."""
+    fn = getattr(w, "grad_fn", None)
+    return fn is not None and type(fn).__name__ in _DEFERRED_GRAD_FNS
+
+
+def _wg_stream():
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    ws = _wg["streams"].get(key)
+    if ws is None:
+        ws = _wg["streams"][key] = torch.cuda.Stream(device=cur.device)
+    return cur, ws
+
+
+def _wg_join():
+    """The current stream waits for every weight-gradient stream that has work in flight."""
+    if _wg["used"]:
+        cur = torch.cuda.current_stream()
+        for ws in _wg["used"]:
+            cur.wait_stream(ws)
+        del _wg["used"][:]
+
+
+def _wgrad_raw(x, g, ks, async_ok=False):
     n, h, w, ci = x.shape
     co = g.shape[3]
     taps = ks * ks
+    if (async_ok and _wg["enabled"] and _side["enabled"] and _state["defer_sn"] and _profile is None and not torch.is_grad_enabled()
+            and _use_tc(x) and ci % 8 == 0 and co % 8 == 0):
+        cur, ws = _wg_stream()
+        ws.wait_stream(cur)                              # x and g exist on the launching stream
+        with torch.cuda.stream(ws):
+            gw = _empty((taps, co, ci), torch.float32, x)
+            C.call("gim_conv2d_wgrad", C.ptr(x), C.ptr(g), C.ptr(gw), n, h, w, ci, co, ks, C.dtype_code(x), _state["conv_algo"])
+        x.record_stream(ws)                              # their memory must outlive the side-stream kernel
+        g.record_stream(ws)
+        gw.record_stream(cur)                            # consumed by the flush on the main stream
+        if ws not in _wg["used"]:
+            _wg["used"].append(ws)
+        return gw
     if _use_tc(x) and ci % 8:                       # gw[t][co][c] = sum_p g[p][co] * xcol[p][t*ci+c]
         kc = _round_up(taps * ci, 8)
         gw2 = _wgrad_raw(_im2col(x, ks, 1, kc), g, 1)
@@ -326,6 +377,7 @@ class Conv2dFn(Function):
         xop = _prepare_operand(x, pre, slope)
         ctx.cfg = (ks, pre, slope, bias is not None)
         ctx.bias_param = bias
+        ctx.wg_async = _wg_async_ok(w32)
         # with a prologue the (half-size) operand is what backward needs: weight-grad input and the LeakyReLU sign mask
         ctx.save_for_backward(x if pre == PRE_NONE else xop, w32)
         return _conv_raw(xop, _weight_as(w32, operand_dtype(), False), bias, ks)
@@ -349,7 +401,10 @@ class Conv2dFn(Function):
                 gx = Pool2Fn.apply(gx, None, 1.0)
         if not _state["input_grads_only"]:
             if ctx.needs_input_grad[1]:
-                gw = WgradFn.apply(xs, gy, ks)
+                if ctx.wg_async and not torch.is_grad_enabled():
+                    gw = _wgrad_raw(_operand(xs), _operand(gy), ks, async_ok=True)
+                else:
+                    gw = WgradFn.apply(xs, gy, ks)
             if want_gb:                                # a graph of the backward is being built: the differentiable operator
                 gb = ColSumFn.apply(gy)
         return gx, gw, gb, None, None, None
@@ -575,6 +630,7 @@ class ResBlockDownFn(Function):
                 C.call("gim_cast", C.ptr(y32), C.F32, C.ptr(yb), C.BF16, y32.numel())
                 C.call("gim_operand_prepare", C.ptr(y32), C.F32, C.ptr(yl), C.BF16, n, h // 2, w // 2, co, PRE_LRELU, slope)
             ctx.cfg = (ks, slope, skinny, even, (n, h, w, ci, co), want_ops)
+            ctx.wg_async = (False, False, _wg_async_ok(w2))
             ctx.lazy = True
             ctx.save_for_backward(x32, None, None, tl, wl, w1, w2)
             ctx.biases = (bl, b1, b2)
@@ -623,6 +679,7 @@ class ResBlockDownFn(Function):
             yl = torch.empty_like(y32, dtype=od) if want_ops else None
             C.call("gim_pool2_multi", C.ptr(res), C.ptr(o), C.ptr(y32), C.ptr(yb), C.ptr(yl), n, h, w, co, 0.25, slope)
         ctx.cfg = (ks, slope, skinny, even, (n, h, w, ci, co), want_ops)
+        ctx.wg_async = (_wg_async_ok(wl), _wg_async_ok(w1), _wg_async_ok(w2))
         ctx.save_for_backward(xa, xr, xl, tl, wl, w1, w2)
         ctx.biases = (bl, b1, b2)
         if want_ops:
@@ -672,13 +729,13 @@ class ResBlockDownFn(Function):
             if not ctx.needs_input_grad[5]:
                 gw1 = None
         if want_w and ctx.needs_input_grad[3] and not fused_wgrad:
-            gwl = _wgrad_raw(xa, gl, 1)
+            gwl = _wgrad_raw(xa, gl, 1, async_ok=ctx.wg_async[0] and not skinny)
             if skinny:
                 gwl = _unskinny_gw(gwl, 1, co, ci)
         if want_w and ctx.needs_input_grad[7]:
-            gw2 = _wgrad_raw(tl, g, ks)
+            gw2 = _wgrad_raw(tl, g, ks, async_ok=ctx.wg_async[2])
         if want_w and ctx.needs_input_grad[5] and not fused_wgrad:
-            gw1 = _wgrad_raw(xr, gt, 1 if skinny else ks)
+            gw1 = _wgrad_raw(xr, gt, 1 if skinny else ks, async_ok=ctx.wg_async[1] and not skinny)
             if skinny:
                 gw1 = _unskinny_gw(gw1, taps, co, ci)
         bl_p, b1_p, b2_p = ctx.biases
@@ -748,6 +805,7 @@ class SpectralNormFn(Function):
         g = _c(g)
         if _defer_sn_backward(ctx, g, w, aux):
             return None, None, None, None
+        _wg_join()
         gw = torch.empty_like(w)
         scratch = _empty((8,), torch.float32, w)
         j = ci * k * k
@@ -793,6 +851,7 @@ def _flush_sn_backward():
     import ctypes
     pending, seen_round = list(_sn_pending), {}
     del _sn_pending[:]
+    _wg_join()                       # weight gradients computed on their own streams
     if not pending:
         return
     rounds = []                      # two gradients of the same parameter (D's encoders run three times per step) go to separate launches
@@ -1315,6 +1374,7 @@ class NormConvFn(Function):
             y = _conv_raw(xop, w_op, bias, ks)
         ctx.cfg = (mode, eps, slope, upsample, ks, bias is not None, addend is not None)
         ctx.bias_param = bias
+        ctx.wg_async = _wg_async_ok(w32)
         ctx.save_for_backward(x, st, p_scale, xop, w32)
         return y
 
@@ -1330,7 +1390,7 @@ class NormConvFn(Function):
         if has_bias and ctx.needs_input_grad[4]:
             gb = _bias_grad_with_operand(gy, ctx.bias_param)     # bf16 operand copy of gy + bias gradient in one pass
         gop = _operand(gy)
-        gw = _wgrad_raw(xop, gop, ks) if ctx.needs_input_grad[3] else None
+        gw = _wgrad_raw(xop, gop, ks, async_ok=ctx.wg_async) if ctx.needs_input_grad[3] else None
         g_add = None
         if has_add and ctx.needs_input_grad[5]:                  # d/d(half-resolution residual) = 2x2 sums of gy
             g_add = _empty((n, gy.shape[1] // 2, gy.shape[2] // 2, gy.shape[3]), torch.float32, gy)

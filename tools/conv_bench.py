@@ -29,6 +29,10 @@ SHAPES = [
     (1, 1, 512, 512, 1),
     (32, 32, 8, 128, 1),
     (8, 8, 256, 256, 1),
+    (1, 1, 1536, 1024, 1),
+    (1, 1, 1024, 1024, 1),
+    (8, 8, 128, 256, 1),
+    (4, 4, 256, 512, 1),
 ]
 
 
