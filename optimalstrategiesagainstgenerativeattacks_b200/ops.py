@@ -209,6 +209,9 @@ def _timed_call(kind, flops, name, *args):
         C.call(name, *args)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # keep the GPU busy (~25 us of spinning BEFORE the start event) while the host enqueues event, kernel, event: otherwise an idle GPU
+    # records the start event at once and the host's launch latency (5-10 us of Python + ctypes) is billed to every small kernel
+    torch.cuda._sleep(50000)
     e0.record()
     C.call(name, *args)
     e1.record()
@@ -287,8 +290,9 @@ def _conv_raw(x, w_t, bias, ks):
 # In a backward pass only the input gradients chain from layer to layer; a weight gradient is not read before the batched spectral-norm
 # backward at the END of the pass (deferred_weight_grads).  Launched on a stream of their own (forked after the layer's output gradient
 # exists, joined by the flush), the weight-gradient kernels become parallel branches of the captured graph and fill the tail waves of
-# the persistent forward / input-gradient kernels.  Only when the consumer is known to be the deferred flush (`_wg_async_ok`).
-_wg = {"streams": {}, "used": [], "enabled": os.environ.get("GIM_WGRAD_STREAMS", "1") != "0"}
+# the persistent forward / input-gradient kernels.  Only when the consumer is known to be the deferred flush (`_wg_async_ok`) and only
+# under graph capture (GIM_WGRAD_STREAMS=2 also in eager mode, =0 never).
+_wg = {"streams": {}, "used": [], "enabled": os.environ.get("GIM_WGRAD_STREAMS", "1") != "0", "eager": os.environ.get("GIM_WGRAD_STREAMS", "1") == "2"}
 _DEFERRED_GRAD_FNS = ("SpectralNormPreparedFnBackward", "SpectralNormFnBackward", "_MergedRowsFnBackward")
 
 
@@ -324,8 +328,11 @@ def _wgrad_raw(x, g, ks, async_ok=False):
     n, h, w, ci = x.shape
     co = g.shape[3]
     taps = ks * ks
+    # only while a CUDA graph is being captured: there the fork/join is a pair of graph edges; in eager mode the extra events, the
+    # cross-stream allocator bookkeeping and the lost memory reuse cost more than the overlap buys (measured: 1069 -> 518 episodes/s on
+    # the eager 105x105 authenticator benchmark)
     if (async_ok and _wg["enabled"] and _side["enabled"] and _state["defer_sn"] and _profile is None and not torch.is_grad_enabled()
-            and _use_tc(x) and ci % 8 == 0 and co % 8 == 0):
+            and _use_tc(x) and ci % 8 == 0 and co % 8 == 0 and (torch.cuda.is_current_stream_capturing() or _wg["eager"])):
         cur, ws = _wg_stream()
         ws.wait_stream(cur)                              # x and g exist on the launching stream
         with torch.cuda.stream(ws):

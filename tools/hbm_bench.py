@@ -54,7 +54,7 @@ def build_cases():
     C.call("gim_norm_stats", C.ptr(x), st[0].data_ptr(), st[1].data_ptr(), N, 1024, 128, C.F32)
     C.call("gim_norm_coeffs", 0, st[0].data_ptr(), st[1].data_ptr(), C.ptr(ones), C.ptr(ones), st[2].data_ptr(), st[3].data_ptr(), N, 1024, 128, 1e-5)
 
-    @case("affine_act (normalise + LeakyReLU) [640,32,32,128] fp32", ["affine_act_kernel"])
+    @case("affine_act (normalise + LeakyReLU) [640,32,32,128] fp32", ["affine_act_kernel", "affine_act_vec4_kernel"])
     def _():
         C.call("gim_affine_act_fwd", C.ptr(x), st[0].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), C.ptr(y), N, 1024, 128, 0.2, C.F32)
         return 2 * nb
@@ -64,7 +64,7 @@ def build_cases():
         C.call("gim_norm_bwd_reduce", C.ptr(gy), C.ptr(x), C.ptr(y), st[0].data_ptr(), None, None, red[0].data_ptr(), red[1].data_ptr(), N, 1024, 128, 0.2, C.F32)
         return 3 * nb
 
-    @case("norm_bwd_apply [640,32,32,128] fp32", ["norm_bwd_apply_kernel"])
+    @case("norm_bwd_apply [640,32,32,128] fp32", ["norm_bwd_apply_kernel", "norm_bwd_apply_vec4_kernel"])
     def _():
         C.call("gim_norm_bwd_apply", C.ptr(gy), C.ptr(x), C.ptr(y), st[0].data_ptr(), None, None, red[2].data_ptr(), red[3].data_ptr(), red[4].data_ptr(), C.ptr(y), N, 1024,
                128, 0.2, C.F32)
@@ -144,7 +144,7 @@ def build_cases():
     n_par = sum(m.weight_orig.numel() for m in convs)
     ops.set_precision("bf16")
 
-    @case("spectral norm forward, 12 x (512->512 3x3): power iteration + sigma + fp32/bf16/flipped-bf16 packs", ["sn_wtu_multi_kernel", "sn_vnorm_multi_kernel", "sn_wv_multi_kernel", "sn_unorm_multi_kernel", "sn_pack_multi_kernel"])
+    @case("spectral norm forward, 12 x (512->512 3x3): power iteration + sigma + fp32/bf16/flipped-bf16 packs", ["sn_wtu_multi_kernel", "sn_vnorm_multi_kernel", "sn_wv_multi_kernel", "sn_unorm_multi_kernel", "sn_pack_multi_kernel", "sn_pack_multi_vec_kernel"])
     def _():
         ops.sn_prepare(convs, True, 1e-12)
         return n_par * (3 * 4 + 4 + 2 + 2)          # W read by W^T u, W v and the pack; W/sigma written in fp32 and twice in bf16
@@ -155,7 +155,7 @@ def build_cases():
     ops.sn_prepare(convs, True, 1e-12)
     preps = [m._prepared for m in convs]
 
-    @case("spectral norm backward, 12 x (512->512 3x3): sum(G.W) then G/sigma - c u v^T accumulated into .grad", ["sn_bwd_dot_multi_kernel", "sn_bwd_apply_multi_kernel"])
+    @case("spectral norm backward, 12 x (512->512 3x3): sum(G.W) then G/sigma - c u v^T accumulated into .grad", ["sn_bwd_dot_multi_kernel", "sn_bwd_apply_multi_kernel", "sn_bwd_dot_multi_vec_kernel", "sn_bwd_apply_multi_vec_kernel"])
     def _():
         table = (C.SnBwdLayer * len(convs))()
         sc = torch.empty(len(convs), device=dev)

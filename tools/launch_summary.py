@@ -32,13 +32,14 @@ def main():
     total = sum(tot.values())
     tc = sum(v for k, v in tot.items() if any(t in k for t in TC_FWD))
     out = ["ncu launch list (gpu__time_duration.sum, --clock-control none, cold-cache serialised): one training iteration, O config (1x32x32, m=n=k=5), B=128, bf16 path",
-           "command: ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/ncu_step.py --batch 128   (round 1, final kernels)",
+           "command: ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/ncu_step.py --batch 128   (round 2, final kernels)",
            "total %.1f ms over %d launches (serialised under ncu; the CUDA-graph step with two-stream overlap is shorter, see bench.py)" % (total, sum(cnt.values())),
            "tcgen05 forward/dgrad kernels (conv_fwd_tc2_kernel<0>, <1>, conv_fwd_tc_kernel): %.1f ms = %.1f %% of the launch list" % (tc, 100 * tc / total), ""]
     for name, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         out.append("%9.3f ms %5.1f%% %6d  %s" % (v, 100 * v / total, cnt[name], name[:110]))
     text = "\n".join(out) + "\n"
-    open(os.path.join(ROOT, "profiles", "launches_r01_summary.txt"), "w").write(text)
+    out_name = sys.argv[2] if len(sys.argv) > 2 else "launches_r02_summary.txt"
+    open(os.path.join(ROOT, "profiles", out_name), "w").write(text)
     print("\n".join(out[:45]))
 
 

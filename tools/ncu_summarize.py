@@ -2,7 +2,8 @@
 
   python tools/ncu_summarize.py gpurun_out/prof_conv_fwd_tc2_shapes_r01.ncu-rep gpurun_out/prof_conv_wgrad_tc_shapes_r01.ncu-rep
 
-Writes profiles/ncu_conv_shapes_r01.txt (table) and profiles/ncu_conv_shapes_r01.json (read by bench.py for `roofline.traffic`).
+Writes profiles/ncu_conv_shapes_<round>.txt (table) and .json (read by bench.py for `roofline.traffic`); also accepts the raw-page CSV
+exported on the GPU box (tools/capture_profiles.sh).
 The captured command is `python tools/conv_bench.py --only fwd|wgrad --shapes 0,1,2 --no-check --reps 1` (640 images = B 128 x 5):
 four launches per shape (three warm-up + one), the last of each shape is reported.
 """
@@ -24,7 +25,10 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1.0, "ms":
 
 
 def load(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):          # already exported on the GPU box (tools/capture_profiles.sh): `ncu -i x.ncu-rep --page raw --csv`
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     res = []
@@ -63,8 +67,9 @@ def main():
                 "tensor_pipe_active_pct": r["tensor"], "tma_load_bytes": r["tma_ld"]}
         out_txt.append("")
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    open(os.path.join(ROOT, "profiles", "ncu_conv_shapes_r01.txt"), "w").write("\n".join(out_txt) + "\n")
-    json.dump(out_json, open(os.path.join(ROOT, "profiles", "ncu_conv_shapes_r01.json"), "w"), indent=1)
+    tag = os.environ.get("GIM_PROFILE_ROUND", "r02")
+    open(os.path.join(ROOT, "profiles", "ncu_conv_shapes_%s.txt" % tag), "w").write("\n".join(out_txt) + "\n")
+    json.dump(out_json, open(os.path.join(ROOT, "profiles", "ncu_conv_shapes_%s.json" % tag), "w"), indent=1)
     print("\n".join(out_txt))
 
 
