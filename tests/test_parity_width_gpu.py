@@ -308,8 +308,9 @@ def test_bf16_attacker_gradients_three_way(schemas, name, B):
 # ----------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("prec,tol", [("fp32", 1e-6), ("bf16", 1e-5)])
 def test_graph_replay_equals_eager_iterations(prec, tol):
-    """Three training iterations at O width: `GraphedIteration` (what bench.py times: one captured graph, two encoder streams, fused
-    Adam with device-side step) vs the eager trainer API on the same batches and noise -- losses per step and ALL parameters afterwards.
+    """Three training iterations at O width: `GraphedIteration` (what bench.py times: one captured graph, two encoder streams, the
+    weight-gradient kernels as parallel graph branches -- ops._wgrad_raw forks them only under capture --, fused Adam with device-side
+    step) vs the eager trainer API on the same batches and noise -- losses per step and ALL parameters afterwards.
     Deterministic reductions, so the only difference allowed is none: tolerance is round-off of the comparison itself."""
     g, C, M, T, S, U = pkg()
     from optimalstrategiesagainstgenerativeattacks_b200.cuda_graph import GraphedIteration
