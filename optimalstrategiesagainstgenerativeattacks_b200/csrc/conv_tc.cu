@@ -979,7 +979,12 @@ static int pick_block_n2(int cout, long long m_tiles) {
     int base = pick_block_n(cout);
     if (base < 128) return base;
     if (forced == 128 || forced == 256) return (forced == 256 && cout % 256 != 0) ? 128 : forced;
-    (void)m_tiles;
+    // Measured with the warp-uniform issue loop (tools/conv_bench.py, 640 images): two interleaved M=256 x N=128 accumulation chains
+    // (pair mode, two pixel tiles per CTA) beat one M=256 x N=256 chain on every layer large enough to give each CTA two pixel tiles --
+    // 256->256 @16x16 1322 -> 1550, 512->512 @8x8 1270 -> 1556, 512->256 @8x8 991 -> 1243 TFLOP/s; a single N=128 chain is the slowest
+    // choice (945-988), so small layers keep the 256-wide tile
+    static const int prefer_two_chains = env_int("GIM_CONV_TWO_CHAINS", 1);
+    if (prefer_two_chains && cout % 128 == 0 && m_tiles >= 2 * (long long)num_sms()) return 128;
     return cout % 256 == 0 ? 256 : 128;
 }
 

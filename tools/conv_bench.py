@@ -33,6 +33,8 @@ SHAPES = [
     (1, 1, 1024, 1024, 1),
     (8, 8, 128, 256, 1),
     (4, 4, 256, 512, 1),
+    (8, 8, 512, 256, 3),
+    (16, 16, 256, 128, 3),
 ]
 
 
