@@ -196,6 +196,7 @@ struct ConvTcParams {
     int block_k;                                 // K elements per stage: 64 (128-byte rows, SWIZZLE_128B) or 16 (32-byte rows, SWIZZLE_32B)
     int epi;                                     // fused epilogue bits (persistent kernel): kEpiLrelu, kEpiMask
     int m_sub;                                   // pixel tiles per macro tile (persistent kernel): 1 or 2
+    int k_chains;                                // 2: one pixel tile, but its K steps alternate between two accumulators (summed by the epilogue)
     int n_staging;                               // output staging boxes of the epilogue ring (persistent kernel): 2..4
     int pair;                                    // 1: cta_group::2 kernel variant (two-CTA clusters)
     int debug;                                   // GIM_CONV_DEBUG bits (profiling experiments only): 1 no TMA store, 2 no proxy fence, 4 no smem staging
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
     const int m_per_tile = (kPair ? 2 : 1) * p.m_sub;              // pixel tiles per (pair-)tile
     const int total_tiles = ((m_tiles + m_per_tile - 1) / m_per_tile) * n_tiles;
     const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const uint32_t buf_cols = (uint32_t)(p.m_sub * p.block_n);
+    const uint32_t buf_cols = (uint32_t)(p.m_sub * p.k_chains * p.block_n);
     const uint32_t tmem_cols = 2u * buf_cols < 32u ? 32u : 2u * buf_cols;    // power of two by construction
 
     if (warp == 0 && lane == 0) {
@@ -572,6 +573,7 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
             const uint64_t desc_b0 = k64 ? make_desc_sw128(s0 + b_off, 16, 1024) : make_desc(s0 + b_off, 16, 256, 6);
             const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), a_step = (uint64_t)(a_bytes >> 4);
             const bool two = p.m_sub == 2;
+            const bool chains = p.k_chains == 2;                 // K steps alternate between two accumulators (m_sub == 1, 64-wide K blocks)
             if (p.halo) {
                 // halo mode: per 64-channel block one activation halo (a ring), per tap one weight box (b ring); the tap only moves the
                 // start address of the A descriptor inside the halo: (r * bn * halo_w + q) rows of 128 B; 8-pixel groups halo_w rows apart
@@ -602,14 +604,16 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                                     if (kPair) {
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) {
-                                            umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                            if (chains) umma_bf16_2sm((k & 1) ? tmem_d1 : tmem_d, da + 2 * k, db + 2 * k, idesc, k > 1 ? 1u : acc);
+                                            else umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                                             if (two) umma_bf16_2sm(tmem_d1, da + halo_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                                         }
                                         umma_commit_2sm(&empty_bar[sb]);
                                     } else {
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) {
-                                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                            if (chains) umma_bf16((k & 1) ? tmem_d1 : tmem_d, da + 2 * k, db + 2 * k, idesc, k > 1 ? 1u : acc);
+                                            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                                             if (two) umma_bf16(tmem_d1, da + halo_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                                         }
                                         umma_commit(&empty_bar[sb]);
@@ -649,7 +653,8 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                         } else if (kPair) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                if (chains) umma_bf16_2sm((k & 1) ? tmem_d1 : tmem_d, da + 2 * k, db + 2 * k, idesc, k > 1 ? 1u : acc);
+                                else umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                                 if (two) umma_bf16_2sm(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                             }
                             umma_commit_2sm(&empty_bar[s]);                        // frees this smem slot in both CTAs
@@ -657,7 +662,8 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                             if (k64) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {                      // +32 B along K inside the 128-byte swizzle row
-                                    umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+                                    if (chains) umma_bf16((k & 1) ? tmem_d1 : tmem_d, da + 2 * k, db + 2 * k, idesc, k > 1 ? 1u : acc);
+                                    else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                                     if (two) umma_bf16(tmem_d1, da + a_step + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
                                 }
                             } else {
@@ -735,6 +741,13 @@ __global__ void __launch_bounds__(384, 1) conv_fwd_tc2_kernel(const __grid_const
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 16; ++j) { f[j] = __uint_as_float(lo[j]); f[16 + j] = __uint_as_float(hi[j]); }
+                            if (p.k_chains == 2) {                   // + the second accumulation chain of the same pixel tile
+                                tmem_ld16(tmem_acc + (uint32_t)(p.block_n + cb), lo);
+                                tmem_ld16(tmem_acc + (uint32_t)(p.block_n + cb + 16), hi);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { f[j] += __uint_as_float(lo[j]); f[16 + j] += __uint_as_float(hi[j]); }
+                            }
                         }
                         if (p.epi & kEpiPool) {
                             // AvgPool2d(2) inside the epilogue: the pixel box is at most 16 wide, so the 2x2 window of a pixel lives in
@@ -1042,11 +1055,19 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     static const int force_msub = env_int("GIM_CONV_MSUB", 0), pair_mode = env_int("GIM_CONV_PAIR", 2);
     p.m_sub = (v2 && p.block_n <= 128 && m_tiles >= 2 * (long long)num_sms()) ? 2 : 1;
     if (force_msub == 1 || (force_msub == 2 && v2 && p.block_n <= 128)) p.m_sub = force_msub;
+    // small layers (one pixel tile per CTA): no second tile to interleave with, so the K steps themselves alternate between two
+    // accumulators that the epilogue adds; needs the 128-wide tile (2 buffers x 2 chains x 128 columns = all of TMEM)
+    static const int k_chains_mode = env_int("GIM_CONV_KCHAINS", 0);      // measured: no gain on the 4x4 / 2x2 layers (they are bound by wave quantisation, not by the chain): opt-in
+    p.k_chains = 1;
+    if (k_chains_mode && v2 && p.m_sub == 1 && p.block_k == kBlockK && cout % 128 == 0 && cout >= 128) {
+        p.block_n = 128;
+        p.k_chains = 2;
+    }
     // cta_group::2: pairs of CTAs share one 256 x 256 MMA tile, each staging half of the weight tile.  pair_mode 2 (default since round 2)
     // also pairs the 128-column layers (two pixel tiles per CTA, M = 256 per MMA, half of the 128-row weight tile per CTA): measured
     // +7 % on the 9x9 128->128 layer, +1 % on the 3x3 one, +0.6 % on the O step (tools/conv_bench.py, bench.py A/B)
     p.pair = (v2 && pair_mode && p.block_k == 64 && m_tiles >= 2 &&
-              (p.block_n == 256 || (p.block_n == 128 && p.m_sub == 2 && cout % 128 == 0 && pair_mode > 1))) ? 1 : 0;
+              (p.block_n == 256 || (p.block_n == 128 && (p.m_sub == 2 || p.k_chains == 2) && cout % 128 == 0 && pair_mode > 1))) ? 1 : 0;
     const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + (p.pair ? p.block_n / 2 : p.block_n) * p.block_k * 2 + 1023) & ~1023;
     if (epi & kEpiPool) {
         if (!make_out_map(&map_y, y, n, h / 2, wd / 2, cout, p.bw / 2, p.bh / 2, p.bn, 1, p.halo)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(pooled y) failed");
@@ -1181,7 +1202,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
     int tile_end = tile_begin + p.tiles_per_split;
     if (tile_end > p.total_tiles) tile_end = p.total_tiles;
     const int num_kb = tile_end - tile_begin;                          // >= 1 by construction of the grid
-    const uint32_t tmem_cols = 2u * (uint32_t)p.block_n;               // two accumulation chains of 64 or 128 columns
+    const int n_chains = 2;                                            // independent accumulation chains, summed in the epilogue (4 measured: no gain, the 128-wide tile is bound by shared-memory operand bandwidth)
+    const uint32_t tmem_cols = (uint32_t)(n_chains * p.block_n);       // 256 or 512 columns
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_gy);
@@ -1233,7 +1255,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
             const uint32_t s0 = smem_u32(smem);
             const uint64_t desc_a0 = make_desc_sw128(s0, kATileBytes, 1024), desc_b0 = make_desc_sw128(s0 + a_bytes, kATileBytes, 1024);
             const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
-            const uint32_t tmem_d1 = tmem_base + (uint32_t)p.block_n;       // second accumulation chain (odd K steps), summed in the epilogue
+            const uint32_t chain_mask = (uint32_t)(n_chains - 1);           // K step k accumulates into chain k & mask
             int s = 0;
             uint32_t ph = 0;
             uint64_t da = desc_a0, db = desc_b0;
@@ -1244,8 +1266,9 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kBlockM / 16; ++k) {               // 128 pixels per stage = 8 MMAs of K = 16, 2 KB apart
-                        if (kPair) umma_bf16_2sm((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
-                        else umma_bf16((k & 1) ? tmem_d1 : tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < 2 ? acc : 1u);
+                        const uint32_t tmem_c = tmem_base + ((uint32_t)k & chain_mask) * (uint32_t)p.block_n;
+                        if (kPair) umma_bf16_2sm(tmem_c, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < n_chains ? acc : 1u);
+                        else umma_bf16(tmem_c, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, k < n_chains ? acc : 1u);
                     }
                     if (kPair) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
                 }
@@ -1266,15 +1289,23 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_cons
         float* dst_row = gw + ((long long)tap * p.cout + co) * p.cin + ci0;
         for (int c0 = 0; c0 < p.block_n; c0 += 16) {
             uint32_t v[16], v1[16];
+            float f[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p.block_n + c0), v1);
             tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + __uint_as_float(v1[j]);
+            if (n_chains == 4) {
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * p.block_n + c0), v);
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(3 * p.block_n + c0), v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(v[j]) + __uint_as_float(v1[j]);
+            }
             if (co < p.cout) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)                      // cin % 8 == 0: whole 4-column groups are in or out
-                    if (ci0 + c0 + j < p.cin)
-                        red_add_v4(dst_row + c0 + j, __uint_as_float(v[j]) + __uint_as_float(v1[j]), __uint_as_float(v[j + 1]) + __uint_as_float(v1[j + 1]),
-                                   __uint_as_float(v[j + 2]) + __uint_as_float(v1[j + 2]), __uint_as_float(v[j + 3]) + __uint_as_float(v1[j + 3]));
+                    if (ci0 + c0 + j < p.cin) red_add_v4(dst_row + c0 + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
             }
         }
     }
