@@ -656,7 +656,7 @@ def main():
     args = parse()
     # a run that stops making progress must fail loudly with the stack of every thread instead of holding the GPU box until its limit
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("GIM_BENCH_WATCHDOG_S", "1500")), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("GIM_BENCH_WATCHDOG_S", "900")), exit=True)
     real_stdout = sys.stdout
     with contextlib.redirect_stdout(sys.stderr):      # trainers print parameter counts etc.: stdout carries the JSON line only
         if args.impl == "reference":

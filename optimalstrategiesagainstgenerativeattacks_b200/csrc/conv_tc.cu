@@ -1349,7 +1349,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc3_kernel(const __grid_con
     uint64_t* tmem_full_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int groups = p.ks * p.groups_per_row;
     int t = blockIdx.x;
     const int g = t % groups; t /= groups;
@@ -1401,7 +1401,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc3_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {                                                // whole warp, uniform control flow; one elected lane issues
             const uint32_t idesc = make_idesc((uint32_t)p.block_n, 1, 1);
             const uint32_t s0 = smem_u32(smem);
             const uint64_t desc_a0 = make_desc_sw128(s0, kWgBox, 1024), desc_b0 = make_desc_sw128(s0 + a_bytes, kWgBox, 1024);
@@ -1413,16 +1413,20 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc3_kernel(const __grid_con
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t acc = kb != 0 ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kWgPix / 16; ++k)                  // 64 pixels per stage = 4 K steps of 16, 2 KB apart
-                    for (int tp = 0; tp < nt; ++tp)
-                        umma_bf16(tmem_base + (uint32_t)(tp * p.block_n), da + (uint64_t)(k * 128), db + tp * tap_step + (uint64_t)(k * 128), idesc,
-                                  k ? 1u : acc);
-                umma_commit(&empty_bar[s]);
+                    for (int k = 0; k < kWgPix / 16; ++k)                  // 64 pixels per stage = 4 K steps of 16, 2 KB apart
+                        for (int tp = 0; tp < nt; ++tp)
+                            umma_bf16(tmem_base + (uint32_t)(tp * p.block_n), da + (uint64_t)(k * 128), db + tp * tap_step + (uint64_t)(k * 128), idesc,
+                                      k ? 1u : acc);
+                    umma_commit(&empty_bar[s]);
+                }
+                __syncwarp();
                 da += stage_step; db += stage_step;
                 if (++s == p.stages) { s = 0; ph ^= 1; da = desc_a0; db = desc_b0; }
             }
-            umma_commit(tmem_full_bar);
+            if (elect_one()) umma_commit(tmem_full_bar);
+            __syncwarp();
         }
     } else {
         mbar_wait(tmem_full_bar, 0);
@@ -1507,12 +1511,12 @@ bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dty
 }
 
 int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
-    // Measured on B200 (tools/conv_bench.py, 640 images, both with vector reductions): sharing the dY tile between three taps only wins
-    // on the 128-channel 3x3 layer (997 vs 921 TFLOP/s) and loses elsewhere (785 vs 943, 821 vs 1197, 9x9: 838 vs 1055) although it moves
-    // a third less data: the weight-gradient kernel is not bound by L2->SM traffic (its epilogue atomics were the limiter: switching
-    // them to red.global.add.v4.f32 gave +10..45 %).  Kept selectable for further experiments.
-    static const int tap_groups = env_int("GIM_WGRAD_TAPGROUP", 0);
-    if (ks > 1 && tap_groups) return conv_wgrad_tc3(x, gy, gw, n, h, wd, cin, cout, ks, st);
+    // Round 1 (tools/conv_bench.py, 640 images, both with vector reductions): sharing the dY tile between three taps only won on the
+    // 128-channel 3x3 layer (997 vs 921 TFLOP/s) and lost elsewhere (785 vs 943, 821 vs 1197, 9x9: 838 vs 1055).
+    // Round 2, with the warp-uniform issue loop: the <= 128-channel 3x3 layers are bound by L2->SM traffic (ncu: 3.0 GB of TMA loads per
+    // launch, 14.4 TB/s), there the shared dY tile wins: 935 -> 1110 TFLOP/s on 128->128 @32x32; the 9x9 layer stays (1059 vs 1018).
+    static const int tap_groups = env_int("GIM_WGRAD_TAPGROUP", 2);      // 0: never, 1: every filter, 2: 3x3 layers with <= 128 channels
+    if (ks > 1 && (tap_groups == 1 || (tap_groups == 2 && ks == 3 && cin <= 128 && cout <= 128))) return conv_wgrad_tc3(x, gy, gw, n, h, wd, cin, cout, ks, st);
     WgradTcParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
     pixel_box(h, wd, p.bw, p.bh, p.bn);

@@ -216,6 +216,31 @@ __global__ void __launch_bounds__(256) unpool2_cast_kernel(const float* __restri
         *reinterpret_cast<uint4*>(out + ((img * h + yy) * (long long)w + x) * c + ch) = r;
     }
 }
+// even h and w: one thread per SOURCE chunk of 8 channels -- read once (32 B), rounded once, stored to the four positions of its 2x2 window
+__global__ void __launch_bounds__(256) unpool2_cast_even_kernel(const float* __restrict__ g, bf16* __restrict__ out, int n, int ho, int wo, int c, float scale) {
+    const int cv = c / 8, w = 2 * wo;
+    long long total = (long long)n * ho * wo * cv;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int ch = (int)(i % cv) * 8;
+        long long p = i / cv;
+        const int x = (int)(p % wo); p /= wo;
+        const int yy = (int)(p % ho);
+        const long long img = p / ho;
+        const float* src = g + i * 8;
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(src)), t1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(scale * t0.x, scale * t0.y), p1 = __floats2bfloat162_rn(scale * t0.z, scale * t0.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(scale * t1.x, scale * t1.y), p3 = __floats2bfloat162_rn(scale * t1.z, scale * t1.w);
+        uint4 r;
+        r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+        r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+        bf16* o = out + ((img * (2 * ho) + 2 * yy) * (long long)w + 2 * x) * c + ch;
+        *reinterpret_cast<uint4*>(o) = r;
+        *reinterpret_cast<uint4*>(o + c) = r;
+        *reinterpret_cast<uint4*>(o + (long long)w * c) = r;
+        *reinterpret_cast<uint4*>(o + (long long)w * c + c) = r;
+    }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
@@ -1122,7 +1147,8 @@ int gim_unpool2_cast(const float* gy, void* gx_bf16, int n, int h, int wd, int c
     long long total = (long long)n * h * wd * c;
     if (total <= 0) return GIM_OK;
     GIM_REQUIRE(c % 8 == 0 && aligned16(gy) && aligned16(gx_bf16), "unpool2_cast: needs c % 8 == 0 and 16-byte aligned tensors");
-    unpool2_cast_kernel<<<ew_grid(total / 8, 256, 1), 256, 0, (cudaStream_t)s>>>(gy, (bf16*)gx_bf16, n, h, wd, c, scale);
+    if (!(h & 1) && !(wd & 1)) unpool2_cast_even_kernel<<<ew_grid(total / 32, 256, 1), 256, 0, (cudaStream_t)s>>>(gy, (bf16*)gx_bf16, n, h / 2, wd / 2, c, scale);
+    else unpool2_cast_kernel<<<ew_grid(total / 8, 256, 1), 256, 0, (cudaStream_t)s>>>(gy, (bf16*)gx_bf16, n, h, wd, c, scale);
     return check_launch("unpool2_cast");
 }
 int gim_first_block_fwd(const float* x, const float* w_r1, const float* b_r1, const float* w_l1, const float* b_l1, void* t_bf16, float* res_pooled,

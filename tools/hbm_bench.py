@@ -81,7 +81,7 @@ def build_cases():
 
     gp = rnd(N, 16, 16, 128)
 
-    @case("unpool2_cast (AvgPool backward -> bf16 operand) [640,32,32,128]", ["unpool2_cast_kernel"])
+    @case("unpool2_cast (AvgPool backward -> bf16 operand) [640,32,32,128]", ["unpool2_cast_kernel", "unpool2_cast_even_kernel"])
     def _():
         C.call("gim_unpool2_cast", C.ptr(gp), C.ptr(op), N, 32, 32, 128, 0.25)
         return gp.numel() * 4 + op.numel() * 2
