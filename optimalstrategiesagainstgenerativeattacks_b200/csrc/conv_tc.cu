@@ -1515,8 +1515,8 @@ int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd
     // 128-channel 3x3 layer (997 vs 921 TFLOP/s) and lost elsewhere (785 vs 943, 821 vs 1197, 9x9: 838 vs 1055).
     // Round 2, with the warp-uniform issue loop: the <= 128-channel 3x3 layers are bound by L2->SM traffic (ncu: 3.0 GB of TMA loads per
     // launch, 14.4 TB/s), there the shared dY tile wins: 935 -> 1110 TFLOP/s on 128->128 @32x32; the 9x9 layer stays (1059 vs 1018).
-    static const int tap_groups = env_int("GIM_WGRAD_TAPGROUP", 2);      // 0: never, 1: every filter, 2: 3x3 layers with <= 128 channels
-    if (ks > 1 && (tap_groups == 1 || (tap_groups == 2 && ks == 3 && cin <= 128 && cout <= 128))) return conv_wgrad_tc3(x, gy, gw, n, h, wd, cin, cout, ks, st);
+    static const int tap_groups = env_int("GIM_WGRAD_TAPGROUP", 2);      // 0: never, 1: every filter, 2: 3x3 layers with <= 128 output channels (also 256->128 @16x16: 874 -> 931; loses with cout >= 256, where the pair kernel runs)
+    if (ks > 1 && (tap_groups == 1 || (tap_groups == 2 && ks == 3 && cout <= 128))) return conv_wgrad_tc3(x, gy, gw, n, h, wd, cin, cout, ks, st);
     WgradTcParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
     pixel_box(h, wd, p.bw, p.bh, p.bn);
