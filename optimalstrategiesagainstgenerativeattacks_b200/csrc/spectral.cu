@@ -227,7 +227,9 @@ __global__ void __launch_bounds__(256) sn_pack_multi_kernel(const __grid_constan
     bf16* wfl = (bf16*)L.w_flip;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
     const int nci = min(32, L.cin - ci0);
-    for (int t0 = 0; t0 < taps; t0 += kPackTaps) {
+    // gridDim.z > 1: one group of <= 9 taps per CTA (a 9x9 filter has only (cout/32)*(cin/32) tiles: too few CTAs to walk 81 taps each)
+    const int t_begin = gridDim.z > 1 ? (int)blockIdx.z * kPackTaps : 0, t_end = gridDim.z > 1 ? min(taps, t_begin + kPackTaps) : taps;
+    for (int t0 = t_begin; t0 < t_end; t0 += kPackTaps) {
         const int nt = min(kPackTaps, taps - t0);
         // read: for each co row, the segment [ci0 .. ci0+nci) x [t0 .. t0+nt) ; consecutive threads walk (ci, t) pairs
         for (int r = ty; r < 32; r += 8) {
@@ -288,7 +290,8 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_multi_kernel(const __grid_cons
     for (int tile = blockIdx.x; tile < ci_tiles * co_tiles; tile += gridDim.x) {
     const int co0 = (tile / ci_tiles) * 32, ci0 = (tile % ci_tiles) * 32;
     const int nci = min(32, L.cin - ci0);
-    for (int t0 = 0; t0 < taps; t0 += kPackTaps) {
+    const int t_begin = gridDim.z > 1 ? (int)blockIdx.z * kPackTaps : 0, t_end = gridDim.z > 1 ? min(taps, t_begin + kPackTaps) : taps;
+    for (int t0 = t_begin; t0 < t_end; t0 += kPackTaps) {
         const int nt = min(kPackTaps, taps - t0);
         for (int tl = 0; tl < nt; ++tl)
             for (int r = ty; r < 32; r += 8) {
@@ -329,7 +332,8 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_multi_kernel(const __grid_co
     const float k = (*L.scratch) * inv * inv;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int nci = min(32, L.cin - ci0);
-    for (int t0 = 0; t0 < taps; t0 += kPackTaps) {
+    const int t_begin = gridDim.z > 1 ? (int)blockIdx.z * kPackTaps : 0, t_end = gridDim.z > 1 ? min(taps, t_begin + kPackTaps) : taps;
+    for (int t0 = t_begin; t0 < t_end; t0 += kPackTaps) {
         const int nt = min(kPackTaps, taps - t0);
         for (int tl = 0; tl < nt; ++tl)
             for (int r = ty; r < 32; r += 8) {
@@ -600,7 +604,10 @@ int gim_sn_forward_multi(const gim_sn_layer* layers, int n_layers, int power_ite
         }
         const unsigned all = c.n >= 32 ? 0xffffffffu : ((1u << c.n) - 1u);
         if (vmask) sn_pack_multi_vec_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c, vmask);
-        if (vmask != all) sn_pack_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c, all & ~vmask);
+        int zmax = 1;                                    // tap groups of the widest scalar-path filter (81 taps -> 9 CTAs per tile)
+        for (int i = 0; i < c.n; ++i)
+            if (!((vmask >> i) & 1u)) zmax = max(zmax, (c.l[i].ksize * c.l[i].ksize + kPackTaps - 1) / kPackTaps);
+        if (vmask != all) sn_pack_multi_kernel<<<dim3(max_tiles, c.n, zmax), 256, 0, st>>>(c, all & ~vmask);
         if ((rc = check_launch("sn_pack_multi")) != GIM_OK) return rc;
     }
     return GIM_OK;
@@ -630,11 +637,14 @@ int gim_sn_backward_multi(const gim_sn_bwd_layer* layers, int n_layers, gim_stre
         const unsigned all = c.n >= 32 ? 0xffffffffu : ((1u << c.n) - 1u);
         const int dot_x = deterministic() ? 1 : max_tiles;
         if (vmask) sn_bwd_dot_multi_vec_kernel<<<dim3(dot_x, c.n), 256, 0, st>>>(c, vmask);
-        if (vmask != all) sn_bwd_dot_multi_kernel<<<dim3(dot_x, c.n), 256, 0, st>>>(c, all & ~vmask);
+        int zmax = 1;
+        for (int i = 0; i < c.n; ++i)
+            if (!((vmask >> i) & 1u)) zmax = max(zmax, (c.l[i].ksize * c.l[i].ksize + kPackTaps - 1) / kPackTaps);
+        if (vmask != all) sn_bwd_dot_multi_kernel<<<dim3(dot_x, c.n, deterministic() ? 1 : zmax), 256, 0, st>>>(c, all & ~vmask);
         int rc = check_launch("sn_bwd_dot_multi");
         if (rc != GIM_OK) return rc;
         if (vmask) sn_bwd_apply_multi_vec_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c, vmask);
-        if (vmask != all) sn_bwd_apply_multi_kernel<<<dim3(max_tiles, c.n), 256, 0, st>>>(c, all & ~vmask);
+        if (vmask != all) sn_bwd_apply_multi_kernel<<<dim3(max_tiles, c.n, zmax), 256, 0, st>>>(c, all & ~vmask);
         if ((rc = check_launch("sn_bwd_apply_multi")) != GIM_OK) return rc;
     }
     return GIM_OK;
