@@ -228,3 +228,19 @@ def test_eval_auc_orientation_matches_reference_labels():
         im = AE.Impersonator(lambda leaked_sample, n, s=shift: leaked_sample[:, :1].expand(-1, n, -1, -1, -1) + s)
         acc, acc_fake, acc_real, auc = AE.eval_authenticator_and_impersonator("cpu", ds, 4, 0, au, im)
         assert auc == want, (shift, auc)
+
+
+def test_weight_gradient_streams_only_for_deferred_consumers():
+    """ops._wg_async_ok: a weight gradient may be computed on the side stream only when its consumer is a spectral-norm node (whose
+    backward just queues the tensor for the batched flush); plain parameters (AccumulateGrad reads the gradient at once) are refused."""
+    import torch
+    from optimalstrategiesagainstgenerativeattacks_b200 import ops
+    w_orig = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+    packed, aux = torch.randn(9, 8, 4), torch.zeros(8 + 36 + 1)
+    w_sn = ops.SpectralNormPreparedFn.apply(w_orig, (packed, aux, None, None))
+    assert ops._wg_async_ok(w_sn)
+    assert not ops._wg_async_ok(w_orig)
+    assert not ops._wg_async_ok(torch.randn(9, 8, 4))
+    merged = ops._MergedRowsFn.apply((torch.randn(64), 0), torch.randn(1, 4, 8, requires_grad=True), torch.randn(1, 4, 8, requires_grad=True))
+    assert ops._wg_async_ok(merged)
+    ops._wg_join()                                   # nothing in flight: a no-op that must not touch CUDA

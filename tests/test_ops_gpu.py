@@ -494,6 +494,57 @@ def test_full_size_conv_kernels():
     assert res.stdout.count("shape n=640") == 5 and "rel" in res.stdout
 
 
+FULL_SHAPES = [  # n, ci, co, k, h, w -- enough tiles that every SM pair of the persistent kernel walks several rounds, ragged last tiles
+    (640, 128, 128, 3, 32, 32),      # halo staging, pair mode, two pixel tiles per CTA (two accumulation chains)
+    (333, 256, 256, 3, 16, 16),      # odd image count: zero-filled tail tiles
+    (321, 512, 512, 3, 8, 8),        # two 8x8 images per tile ((h, image, w) pixel order), odd count
+    (61, 64, 64, 3, 64, 64),         # 64-wide N tile, single-CTA variant
+    (200, 128, 256, 3, 13, 13),      # odd map: ragged 8-pixel-wide tiles
+    (150, 64, 128, 3, 26, 26),
+    (640, 512, 512, 3, 4, 4),        # below 8x8: per-tap boxes (no halo), 256-wide tile
+    (640, 256, 128, 3, 16, 16),      # weight gradient through the shared-dY tap-group kernel (cout <= 128)
+]
+
+
+@pytest.mark.parametrize("shape", FULL_SHAPES)
+def test_conv_tcgen05_full_size_every_image(shape):
+    """Round-2 kernels at full size, EVERY image checked (the benchmark-sized launches walk many tiles per persistent CTA; a wrong tile
+    coordinate, halo offset or ring phase would corrupt only some of them): forward against cuDNN on the same bf16 operands, per image;
+    weight gradient against the CUDA-core kernel."""
+    ops = ops_mod()
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi as C
+    ops.set_precision("bf16")
+    ops.set_conv_algo("tcgen05")
+    n, ci, co, k, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((n, h, w, ci), device="cuda", generator=g).to(torch.bfloat16)
+    wp = (torch.randn((k * k, co, ci), device="cuda", generator=g) / np.sqrt(ci * k * k)).to(torch.bfloat16)
+    b = torch.randn((co,), device="cuda", generator=g)
+    y = torch.empty((n, h, w, co), device="cuda", dtype=torch.float32)
+    C.call("gim_conv2d_fwd", C.ptr(x), C.ptr(wp), C.ptr(b), C.ptr(y), n, h, w, ci, co, k, C.BF16, C.F32, C.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    w_oihw = wp.float().reshape(k, k, co, ci).permute(2, 3, 0, 1).contiguous()
+    worst = 0.0
+    for i0 in range(0, n, 64):                       # fp32 reference in slabs (no TF32)
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            ref = torch.nn.functional.conv2d(x[i0:i0 + 64].float().permute(0, 3, 1, 2), w_oihw, b, padding=(k - 1) // 2).permute(0, 2, 3, 1)
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+        d = (y[i0:i0 + 64] - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)
+        worst = max(worst, float(d.max()))
+    assert worst < 1e-4, worst                       # same operands, fp32 accumulation on both sides: only the summation order differs
+    gy = torch.randn((n, h, w, co), device="cuda", generator=g).to(torch.bfloat16)
+    gw = {}
+    for algo, code in (("tc", C.ALGO_TCGEN05), ("simt", C.ALGO_SIMT)):
+        out = torch.empty((k * k, co, ci), device="cuda", dtype=torch.float32)
+        C.call("gim_conv2d_wgrad", C.ptr(x), C.ptr(gy), C.ptr(out), n, h, w, ci, co, k, C.BF16, code)
+        gw[algo] = out
+    torch.cuda.synchronize()
+    assert rel_err(gw["tc"], gw["simt"]) < 1e-4
+
+
 @pytest.mark.parametrize("channels,n_img", [(128, 3), (256, 5), (256, 160)])
 def test_fused_attention_core(channels, n_img):
     """gim_attention_fwd / _bwd (one CTA per image, 64 positions) against float64 torch and against the composed gemm + softmax route."""
