@@ -53,13 +53,25 @@ def broadcast_module_state(module, src=0, group=None):
             dist.broadcast(t.data, src=src, group=group)
 
 
-_comm = {"stream": None}
+_comm = {"stream": None, "busy": False}
 
 
 def _comm_stream(device):
+    """The communication stream: HIGH priority, so that the collective's few CTAs are placed as soon as any SM frees up -- with the
+    weight-gradient branches filling every tail of the persistent convolution kernels there are no idle SMs left to wait for."""
     if _comm["stream"] is None or _comm["stream"].device != device:
-        _comm["stream"] = torch.cuda.Stream(device=device)
+        _comm["stream"] = torch.cuda.Stream(device=device, priority=-1)
     return _comm["stream"]
+
+
+def _order_after_deferred(device):
+    """Two collectives on one communicator must execute in the same order on every rank.  A deferred all-reduce lives on the
+    communication stream; a later all-reduce issued from the compute stream has no stream dependency on it, so a rank whose deferred
+    collective has not been scheduled yet could start the later one first -- and the ranks would wait for each other forever.  The
+    compute stream therefore waits for the communication stream before it enqueues its own collective."""
+    if _comm["busy"] and _comm["stream"] is not None:
+        torch.cuda.current_stream(device).wait_stream(_comm["stream"])
+        _comm["busy"] = False
 
 
 def attach(optimizer, group=None, defer=False):
@@ -100,6 +112,7 @@ def attach(optimizer, group=None, defer=False):
             return None
         state["pending"] = False
         torch.cuda.current_stream().wait_stream(_comm_stream(state["bucket"].flat.device))
+        _comm["busy"] = False
         return inner_step()
 
     def step(closure=None):
@@ -109,6 +122,8 @@ def attach(optimizer, group=None, defer=False):
         if world <= 1:
             return inner_step()
         if not (defer and state["bucket"] is not None and state["bucket"].flat.is_cuda):
+            if torch.cuda.is_available():
+                _order_after_deferred(torch.cuda.current_device())
             reduce_now()                             # (the first step builds the bucket: gradients move into it)
             return inner_step()
         comm, cur = _comm_stream(state["bucket"].flat.device), torch.cuda.current_stream()
@@ -116,6 +131,7 @@ def attach(optimizer, group=None, defer=False):
         with torch.cuda.stream(comm):
             reduce_now()
         state["pending"] = True
+        _comm["busy"] = True
         return None
 
     def zero_grad(*a, **k):
