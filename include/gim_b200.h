@@ -38,6 +38,13 @@ const char* gim_last_error(void);
 /* 1 if the tcgen05/TMA implicit-GEMM path can take this conv shape/dtype, else 0 */
 int         gim_conv2d_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype);
 int         gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout, int ksize, int dtype);
+/* Dry run of the tensor-core forward / input-gradient launcher (bf16 operands): the configuration gim_conv2d_fwd[_fused] WOULD launch for
+ * this shape, without touching the device (works on a machine with no GPU; 148 SMs assumed there).  plan20 (host, 20 ints):
+ * [0] persistent kernel (1) or non-persistent (0), [1] halo staging, [2] N tile, [3] pixel tiles per CTA, [4] cta_group::2, [5] stages of the
+ * single ring, [6] activation-halo ring depth, [7] weight ring depth, [8] accumulation chains per pixel tile, [9..11] pixel box w, h, images,
+ * [12] grid x, [13] grid y, [14] threads per CTA, [15] dynamic shared memory bytes, [16] TMEM columns, [17] K block, [18] pixel tiles,
+ * [19] bytes of one halo box.  `epilogue`: the bits of gim_conv2d_fwd_fused. */
+int         gim_conv2d_fwd_plan(int n, int h, int w, int cin, int cout, int ksize, int out_dtype, int epilogue, int* plan20);
 /* counts kernel launches issued through this library since the last reset (bench.py `gpu_launches`) */
 long long   gim_launch_count(int reset);
 /* Parity mode: when on, every reduction output (weight gradients, column sums, split-K GEMMs, scalar dots) is owned by ONE CTA, so

@@ -84,7 +84,8 @@ PROTOTYPES = {
     "gim_adam_multi": "pilppfff" + "fp",
     "gim_zero_grads_multi": "pilp",
 }
-OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_launch_count", "gim_set_deterministic")
+OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_conv2d_fwd_plan", "gim_launch_count",
+                 "gim_set_deterministic")
 
 
 
@@ -122,6 +123,8 @@ def lib():
         L.gim_conv2d_tc_supported.restype = _I
         L.gim_conv2d_wgrad_tc_supported.argtypes = [_I] * 7
         L.gim_conv2d_wgrad_tc_supported.restype = _I
+        L.gim_conv2d_fwd_plan.argtypes = [_I] * 8 + [_P]
+        L.gim_conv2d_fwd_plan.restype = _I
         L.gim_launch_count.argtypes = [_I]
         L.gim_launch_count.restype = _L
         L.gim_set_deterministic.argtypes = [_I]
@@ -181,6 +184,19 @@ def set_deterministic(flag):
 
 def conv_tc_supported(n, h, w, cin, cout, k, dtype):
     return bool(lib().gim_conv2d_tc_supported(n, h, w, cin, cout, k, dtype))
+
+
+PLAN_FIELDS = ("persistent", "halo", "block_n", "m_sub", "pair", "stages", "a_stages", "b_stages", "k_chains", "bw", "bh", "bn", "grid_x", "grid_y",
+               "threads", "smem_bytes", "tmem_cols", "block_k", "pixel_tiles", "halo_bytes")
+
+
+def conv_fwd_plan(n, h, w, cin, cout, k, out_dtype=F32, epilogue=0):
+    """The launch configuration the tensor-core forward / input-gradient path would use for this shape (no device needed)."""
+    buf = (ctypes.c_int * 20)()
+    rc = lib().gim_conv2d_fwd_plan(n, h, w, cin, cout, k, out_dtype, epilogue, ctypes.cast(buf, ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError(lib().gim_last_error().decode())
+    return dict(zip(PLAN_FIELDS, list(buf)))
 
 
 def wgrad_tc_supported(n, h, w, cin, cout, k, dtype):

@@ -1001,6 +1001,17 @@ static int pick_block_n2(int cout, long long m_tiles) {
     return cout % 256 == 0 ? 256 : 128;
 }
 
+// Dry run of the launcher (gim_conv2d_fwd_plan): when set, conv_fwd_tc_ex fills this record with the configuration it WOULD launch and
+// returns before it touches the driver (no tensor maps, no attributes, no launch) -- so the tile picker can be swept over shapes on a
+// machine without a GPU (tests/test_host_cpu.py checks shared-memory, TMEM and ring invariants for every layer family).
+static thread_local int* g_plan = nullptr;
+static void fill_plan(const ConvTcParams& p, int v2, long long grid_x, long long grid_y, int threads, size_t smem, int tmem_cols) {
+    int* o = g_plan;
+    o[0] = v2; o[1] = p.halo; o[2] = p.block_n; o[3] = p.m_sub; o[4] = p.pair; o[5] = p.stages; o[6] = p.a_stages; o[7] = p.b_stages;
+    o[8] = p.k_chains; o[9] = p.bw; o[10] = p.bh; o[11] = p.bn; o[12] = (int)grid_x; o[13] = (int)grid_y; o[14] = threads;
+    o[15] = (int)smem; o[16] = tmem_cols; o[17] = p.block_k; o[18] = p.tiles_w * p.tiles_h * p.tiles_n; o[19] = p.halo ? p.halo_bytes : 0;
+}
+
 int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ks, int out_f32,
                    int epi, float slope, const void* mask_ref, const float* addend, cudaStream_t st) {
     static const int use_v1 = env_int("GIM_CONV_V1", 0);
@@ -1069,6 +1080,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     p.pair = (v2 && pair_mode && p.block_k == 64 && m_tiles >= 2 &&
               (p.block_n == 256 || (p.block_n == 128 && (p.m_sub == 2 || p.k_chains == 2) && cout % 128 == 0 && pair_mode > 1))) ? 1 : 0;
     const int stage_bytes = ((v2 ? p.m_sub : 1) * kBlockM * p.block_k * 2 + (p.pair ? p.block_n / 2 : p.block_n) * p.block_k * 2 + 1023) & ~1023;
+    if (!g_plan) {
     if (epi & kEpiPool) {
         if (!make_out_map(&map_y, y, n, h / 2, wd / 2, cout, p.bw / 2, p.bh / 2, p.bn, 1, p.halo)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(pooled y) failed");
     } else if (!make_out_map(&map_y, y, n, h, wd, cout, p.bw, p.bh, p.bn, out_f32, p.halo)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(y) failed");
@@ -1077,6 +1089,7 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     } else if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn, p.block_k)) return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(x) failed");
     if (!make_mat_map(&map_w, w, (long long)ks * ks * cout, cin, p.pair ? p.block_n / 2 : p.block_n, p.block_k))
         return fail(GIM_E_CUDA, "conv_fwd_tc: cuTensorMapEncodeTiled(w) failed");
+    }
     if (v2) {
         static const int env_nb = env_int("GIM_CONV_NSTAGING", 0), env_stages = env_int("GIM_CONV_STAGES", 0);
         p.debug = env_int("GIM_CONV_DEBUG", 0);
@@ -1099,6 +1112,20 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
             p.b_stages = bs > 8 ? 8 : bs;
             if (env_stages >= 2 && env_stages < p.b_stages) p.b_stages = env_stages;
             smem = (size_t)p.a_stages * p.m_sub * p.halo_bytes + (size_t)p.b_stages * b_bytes + fixed;
+        }
+        if (g_plan) {                                // dry run: report the launch and stop
+            const uint32_t buf_cols = (uint32_t)(p.m_sub * p.k_chains * p.block_n);
+            const int tmem_cols = (int)(2u * buf_cols < 32u ? 32u : 2u * buf_cols);
+            long long gx;
+            if (p.pair) {
+                const long long pairs = ((m_tiles + 2 * p.m_sub - 1) / (2 * p.m_sub)) * (cout / p.block_n), max_pairs = num_sms() / 2;
+                gx = 2 * (pairs < max_pairs ? pairs : max_pairs);
+            } else {
+                const long long total = ((m_tiles + p.m_sub - 1) / p.m_sub) * ((cout + p.block_n - 1) / p.block_n);
+                gx = total < num_sms() ? total : num_sms();
+            }
+            fill_plan(p, 1, gx, 1, 384, smem, tmem_cols);
+            return GIM_OK;
         }
         static bool attr_set2 = false;
         if (!attr_set2) {
@@ -1141,6 +1168,10 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     // staged TMA-store epilogue when a whole 32-column group exists and the tile fits in the idle pipeline buffers
     p.tma_store = (p.block_n >= 32 && (size_t)kBlockM * p.block_n * (out_f32 ? 4 : 2) <= (size_t)stages * stage_bytes) ? 1 : 0;
     const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    if (g_plan) {
+        fill_plan(p, 0, m_tiles, (cout + p.block_n - 1) / p.block_n, 192, smem, p.block_n < 32 ? 32 : p.block_n);
+        return GIM_OK;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -1152,6 +1183,17 @@ int conv_fwd_tc_ex(const void* x, const void* w, const float* bias, void* y, int
     return check_launch("conv_fwd_tc");
 }
 
+
+int conv_fwd_tc_plan(int n, int h, int wd, int cin, int cout, int ks, int out_f32, int epi, int* out20) {
+    if (!out20) return fail(GIM_E_ARG, "conv_fwd_plan: null output");
+    if (!conv_tc_supported(n, h, wd, cin, cout, ks, GIM_BF16)) return fail(GIM_E_UNSUPPORTED, "conv_fwd_plan: shape not eligible for the tensor-core kernels");
+    for (int i = 0; i < 20; ++i) out20[i] = 0;
+    g_plan = out20;
+    void* dummy = reinterpret_cast<void*>(static_cast<uintptr_t>(256));      // never dereferenced in a dry run
+    const int rc = conv_fwd_tc_ex(dummy, dummy, nullptr, dummy, n, h, wd, cin, cout, ks, out_f32, epi, 0.2f, dummy, (const float*)dummy, nullptr);
+    g_plan = nullptr;
+    return rc;
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // weight gradient:  dW[tap][co][ci] = sum_pix dY[pix][co] * X[pix + tap][ci]

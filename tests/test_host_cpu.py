@@ -244,3 +244,70 @@ def test_weight_gradient_streams_only_for_deferred_consumers():
     merged = ops._MergedRowsFn.apply((torch.randn(64), 0), torch.randn(1, 4, 8, requires_grad=True), torch.randn(1, 4, 8, requires_grad=True))
     assert ops._wg_async_ok(merged)
     ops._wg_join()                                   # nothing in flight: a no-op that must not touch CUDA
+
+
+def test_conv_launch_plans_respect_the_hardware_limits():
+    """gim_conv2d_fwd_plan (a dry run of the real launcher, no device needed) over every layer family of the O / V / 105x105 networks, small
+    and benchmark-sized batches and every fused epilogue: shared memory <= 227 KB, TMEM <= 512 columns, ring depths, tile geometry, grid
+    sizes -- and the choices DESIGN.md section 4 documents for the profiled shapes."""
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi as C
+    EPI_LRELU, EPI_MASK, EPI_ADD, EPI_POOL, EPI_ADDUP, EPI_UNIT = 1, 2, 4, 8, 16, 32
+    sizes = (1, 2, 4, 6, 8, 13, 16, 26, 32, 52, 64, 105)
+    chans = ((64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 512), (512, 512), (512, 256), (256, 128), (128, 64), (1536, 1024),
+             (16, 128), (128, 16), (88, 16), (320, 256), (32, 64), (72, 1000))
+    checked = 0
+    for hw in sizes:
+        for ci, co in chans:
+            for k in (1, 3, 9):
+                for n in (5, 80, 640):
+                    if n * hw * hw > 640 * 64 * 64:
+                        continue
+                    if not C.conv_tc_supported(n, hw, hw, ci, co, k, C.BF16):
+                        continue
+                    variants = [(C.F32, 0), (C.BF16, 0)]
+                    if co % 32 == 0:
+                        variants += [(C.BF16, EPI_LRELU), (C.F32, EPI_MASK), (C.F32, EPI_MASK | EPI_ADD)]
+                        if hw % 2 == 0:
+                            variants += [(C.F32, EPI_POOL | EPI_ADD), (C.F32, EPI_POOL | EPI_UNIT), (C.F32, EPI_MASK | EPI_ADDUP), (C.F32, EPI_ADDUP | EPI_UNIT)]
+                    for out_dt, epi in variants:
+                        try:
+                            pl = C.conv_fwd_plan(n, hw, hw, ci, co, k, out_dt, epi)
+                        except RuntimeError as e:            # the launcher may refuse (fused epilogues need cout >= 32 ...), never mis-size
+                            assert "conv_fwd_tc" in str(e) or "conv2d" in str(e), str(e)
+                            continue
+                        tag = (n, hw, ci, co, k, out_dt, epi, pl)
+                        assert pl["smem_bytes"] <= 227 * 1024, tag
+                        t = pl["tmem_cols"]
+                        assert 32 <= t <= 512 and (t & (t - 1)) == 0, tag
+                        assert pl["bw"] * pl["bh"] * pl["bn"] == 128, tag
+                        tiles = -(-hw // pl["bw"]) * -(-hw // pl["bh"]) * -(-n // pl["bn"])
+                        assert pl["pixel_tiles"] == tiles, tag
+                        assert pl["block_n"] in (16, 32, 64, 128, 256) and pl["block_k"] in (16, 64), tag
+                        if pl["persistent"]:
+                            assert pl["threads"] == 384 and 1 <= pl["grid_x"] <= 148 and pl["grid_y"] == 1, tag
+                            assert pl["m_sub"] * pl["k_chains"] * pl["block_n"] * 2 <= 512, tag          # two accumulator buffers
+                            if pl["pair"]:
+                                assert pl["grid_x"] % 2 == 0 and pl["block_n"] in (128, 256) and co % pl["block_n"] == 0, tag
+                            if pl["halo"]:
+                                assert k == 3 and hw >= 8 and pl["bw"] == 8 and pl["block_k"] == 64, tag
+                                assert 1 <= pl["a_stages"] <= 4 and 2 <= pl["b_stages"] <= 8 and pl["halo_bytes"] % 1024 == 0, tag
+                                assert pl["halo_bytes"] >= 128 * (pl["bw"] + 2) * (pl["bh"] + 2) * pl["bn"], tag
+                            else:
+                                assert 2 <= pl["stages"] <= 8, tag
+                        else:
+                            assert pl["threads"] == 192 and epi & ~EPI_UNIT == 0 and 2 <= pl["stages"] <= 8, tag
+                            assert pl["grid_x"] == tiles and pl["grid_y"] == -(-co // pl["block_n"]), tag
+                        if epi & EPI_POOL:
+                            assert pl["persistent"] and pl["bw"] <= 16, tag
+                        checked += 1
+    assert checked > 3000
+    # the documented choices for the profiled layers (640 images = 128 episodes x 5 samples)
+    for hw, c in ((32, 128), (16, 256), (8, 512)):
+        pl = C.conv_fwd_plan(640, hw, hw, c, c, 3)
+        assert (pl["persistent"], pl["halo"], pl["pair"], pl["block_n"], pl["m_sub"]) == (1, 1, 1, 128, 2), pl
+    pl = C.conv_fwd_plan(640, 4, 4, 512, 512, 3)
+    assert (pl["halo"], pl["pair"], pl["block_n"], pl["m_sub"]) == (0, 1, 256, 1), pl
+    pl = C.conv_fwd_plan(640, 32, 32, 128, 128, 9)
+    assert (pl["halo"], pl["pair"], pl["block_n"], pl["m_sub"]) == (0, 1, 128, 2), pl
+    pl = C.conv_fwd_plan(640, 1, 1, 1536, 1024, 1)
+    assert pl["persistent"] == 0 and pl["grid_x"] * pl["grid_y"] >= 148, pl
