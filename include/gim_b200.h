@@ -45,6 +45,10 @@ int         gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout
  * [12] grid x, [13] grid y, [14] threads per CTA, [15] dynamic shared memory bytes, [16] TMEM columns, [17] K block, [18] pixel tiles,
  * [19] bytes of one halo box.  `epilogue`: the bits of gim_conv2d_fwd_fused. */
 int         gim_conv2d_fwd_plan(int n, int h, int w, int cin, int cout, int ksize, int out_dtype, int epilogue, int* plan20);
+/* The same for the tensor-core weight gradient.  plan16: [0] kernel (1 plain, 2 cta_group::2, 3 shared-dY tap groups), [1] input-channel
+ * tile, [2] stages, [3] grid x (output tiles), [4] grid y (split-K over pixel tiles), [5] threads, [6] shared memory bytes, [7] TMEM columns,
+ * [8] pixel tiles, [9] pixel tiles per split, [10] taps per CTA, [11..13] pixel box w, h, images. */
+int         gim_conv2d_wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int* plan16);
 /* counts kernel launches issued through this library since the last reset (bench.py `gpu_launches`) */
 long long   gim_launch_count(int reset);
 /* Parity mode: when on, every reduction output (weight gradients, column sums, split-K GEMMs, scalar dots) is owned by ONE CTA, so

@@ -84,7 +84,7 @@ PROTOTYPES = {
     "gim_adam_multi": "pilppfff" + "fp",
     "gim_zero_grads_multi": "pilp",
 }
-OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_conv2d_fwd_plan", "gim_launch_count",
+OTHER_SYMBOLS = ("gim_version", "gim_last_error", "gim_conv2d_tc_supported", "gim_conv2d_wgrad_tc_supported", "gim_conv2d_fwd_plan", "gim_conv2d_wgrad_plan", "gim_launch_count",
                  "gim_set_deterministic")
 
 
@@ -125,6 +125,8 @@ def lib():
         L.gim_conv2d_wgrad_tc_supported.restype = _I
         L.gim_conv2d_fwd_plan.argtypes = [_I] * 8 + [_P]
         L.gim_conv2d_fwd_plan.restype = _I
+        L.gim_conv2d_wgrad_plan.argtypes = [_I] * 6 + [_P]
+        L.gim_conv2d_wgrad_plan.restype = _I
         L.gim_launch_count.argtypes = [_I]
         L.gim_launch_count.restype = _L
         L.gim_set_deterministic.argtypes = [_I]
@@ -197,6 +199,19 @@ def conv_fwd_plan(n, h, w, cin, cout, k, out_dtype=F32, epilogue=0):
     if rc != 0:
         raise RuntimeError(lib().gim_last_error().decode())
     return dict(zip(PLAN_FIELDS, list(buf)))
+
+
+WGRAD_PLAN_FIELDS = ("kernel", "block_n", "stages", "grid_x", "grid_y", "threads", "smem_bytes", "tmem_cols", "pixel_tiles", "tiles_per_split",
+                     "taps_per_cta", "bw", "bh", "bn")
+
+
+def conv_wgrad_plan(n, h, w, cin, cout, k):
+    """The launch configuration of the tensor-core weight gradient for this shape (no device needed)."""
+    buf = (ctypes.c_int * 16)()
+    rc = lib().gim_conv2d_wgrad_plan(n, h, w, cin, cout, k, ctypes.cast(buf, ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError(lib().gim_last_error().decode())
+    return dict(zip(WGRAD_PLAN_FIELDS, list(buf)))
 
 
 def wgrad_tc_supported(n, h, w, cin, cout, k, dtype):

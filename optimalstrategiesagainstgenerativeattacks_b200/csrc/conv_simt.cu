@@ -307,6 +307,7 @@ int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd
 bool conv_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
 bool wgrad_tc_supported(int n, int h, int wd, int cin, int cout, int ks, int dtype);
 int conv_fwd_tc_plan(int n, int h, int wd, int cin, int cout, int ks, int out_f32, int epi, int* out20);
+int conv_wgrad_tc_plan(int n, int h, int wd, int cin, int cout, int ks, int* out16);
 
 }  // namespace gim
 
@@ -325,6 +326,8 @@ int gim_conv2d_wgrad_tc_supported(int n, int h, int w, int cin, int cout, int ks
 int gim_conv2d_fwd_plan(int n, int h, int w, int cin, int cout, int ksize, int out_dtype, int epilogue, int* plan20) {
     return conv_fwd_tc_plan(n, h, w, cin, cout, ksize, out_dtype == GIM_F32 ? 1 : 0, epilogue, plan20);
 }
+
+int gim_conv2d_wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int* plan16) { return conv_wgrad_tc_plan(n, h, w, cin, cout, ksize, plan16); }
 
 int gim_conv2d_fwd(const void* x, const void* w, const float* bias, void* y, int n, int h, int wd, int cin, int cout, int ksize, int dtype,
                    int out_dtype, int algo, gim_stream_t s) {

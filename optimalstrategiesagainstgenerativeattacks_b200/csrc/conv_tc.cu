@@ -1499,6 +1499,41 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_tc3_kernel(const __grid_con
     }
 }
 
+// Split-K factor of the weight-gradient grids.  Every CTA owns an SM (~200 KB of shared memory), so a grid of G CTAs runs in
+// ceil(G / SMs) waves of equal-length CTAs; the old rule "enough splits for ~2 waves, rounded UP" produced 297, 306 and 360 CTAs on the hot
+// layers (gim_conv2d_wgrad_plan) -- a third wave for a handful of CTAs.  Pick the split count (at most two waves) that minimises
+// waves x pixel tiles per CTA instead.  GIM_WGRAD_SPLIT_MODE=0 restores the old rule.
+static long long pick_wgrad_splits(long long out_tiles, long long total, long long max_split) {
+    static const int mode = env_int("GIM_WGRAD_SPLIT_MODE", 1);
+    const long long sms = num_sms();
+    long long want = (sms * 2 + out_tiles - 1) / out_tiles;             // old rule: ~2 waves, rounded up
+    if (mode) {
+        long long cap = (sms * 2) / out_tiles;                          // at most two waves
+        if (cap < 1) cap = 1;
+        if (cap > max_split) cap = max_split;
+        if (cap < 1) cap = 1;
+        auto cost_of = [&](long long s) {
+            const long long per = (total + s - 1) / s, eff = (total + per - 1) / per;
+            return ((out_tiles * eff + sms - 1) / sms) * per;
+        };
+        long long best_cost = cost_of(1);
+        for (long long s = 2; s <= cap; ++s) best_cost = cost_of(s) < best_cost ? cost_of(s) : best_cost;
+        long long best = 1;                                             // the FINEST split within 2 % of the optimum: shorter CTAs interleave
+        for (long long s = 1; s <= cap; ++s)                            // better with the kernels of the other graph branches
+            if (cost_of(s) * 50 <= best_cost * 51) best = s;
+        want = best;
+    }
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    return want;
+}
+
+// Dry run of the weight-gradient launchers (gim_conv2d_wgrad_plan), see g_plan: [0] kernel (1 plain, 2 cta_group::2, 3 tap groups),
+// [1] input-channel tile, [2] stages, [3] grid x, [4] grid y (split-K), [5] threads, [6] shared memory, [7] TMEM columns, [8] pixel tiles,
+// [9] pixel tiles per split, [10] taps per CTA, [11..13] pixel box.
+static thread_local int* g_wplan = nullptr;
+
 static int conv_wgrad_tc3(const void* x, const void* gy, float* gw, int n, int h, int wd, int cin, int cout, int ks, cudaStream_t st) {
     WgradTc3Params p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.ks = ks;
@@ -1520,19 +1555,24 @@ static int conv_wgrad_tc3(const void* x, const void* gy, float* gw, int n, int h
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     const long long out_tiles = (long long)ks * p.groups_per_row * p.co_tiles * p.ci_tiles;
-    long long want = ((long long)num_sms() * 2 + out_tiles - 1) / out_tiles;        // ~2 waves of CTAs over the chip
     long long max_split = (total + 7) / 8;                                         // at least ~8 K blocks per CTA
     if (max_split < 1) max_split = 1;
-    if (want > max_split) want = max_split;
-    if (want < 1) want = 1;
-    if (want > 65535) want = 65535;
+    long long want = pick_wgrad_splits(out_tiles, total, max_split);
     if (deterministic()) want = 1;
     p.tiles_per_split = (int)((total + want - 1) / want);
     const int splits = (int)((total + p.tiles_per_split - 1) / p.tiles_per_split);
     CUtensorMap map_gy, map_x;
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    if (g_wplan) {
+        int* o = g_wplan;
+        uint32_t tc = 32;
+        while (tc < (uint32_t)(p.tgroup * p.block_n)) tc <<= 1;
+        o[0] = 3; o[1] = p.block_n; o[2] = p.stages; o[3] = (int)out_tiles; o[4] = splits; o[5] = 192; o[6] = (int)smem; o[7] = (int)tc;
+        o[8] = p.total_tiles; o[9] = p.tiles_per_split; o[10] = p.tgroup; o[11] = p.bw; o[12] = p.bh; o[13] = p.bn;
+        return GIM_OK;
+    }
     if (!make_act_map(&map_gy, gy, n, h, wd, cout, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(gy) failed");
     if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed");
-    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv_wgrad_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -1579,19 +1619,22 @@ int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd
     const int stage_bytes = 2 * kATileBytes + ((pair ? p.block_n / 2 : p.block_n) / 64) * kATileBytes;
     p.stages = (200 * 1024) / stage_bytes;
     const long long out_tiles = (long long)ks * ks * (pair ? p.co_tiles / 2 : p.co_tiles) * p.ci_tiles * (pair ? 2 : 1);      // CTAs along x
-    long long want = ((long long)num_sms() * 2 + out_tiles - 1) / out_tiles;        // ~2 waves of CTAs over the chip
     long long max_split = (total + 3) / 4;                                         // at least ~4 pixel tiles per CTA
     if (max_split < 1) max_split = 1;
-    if (want > max_split) want = max_split;
-    if (want < 1) want = 1;
-    if (want > 65535) want = 65535;
+    long long want = pick_wgrad_splits(out_tiles, total, max_split);
     if (deterministic()) want = 1;
     p.tiles_per_split = (int)((total + want - 1) / want);
     const int splits = (int)((total + p.tiles_per_split - 1) / p.tiles_per_split);
     CUtensorMap map_gy, map_x;
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    if (g_wplan) {
+        int* o = g_wplan;
+        o[0] = pair ? 2 : 1; o[1] = p.block_n; o[2] = p.stages; o[3] = (int)out_tiles; o[4] = splits; o[5] = 192; o[6] = (int)smem; o[7] = 2 * p.block_n;
+        o[8] = p.total_tiles; o[9] = p.tiles_per_split; o[10] = 1; o[11] = p.bw; o[12] = p.bh; o[13] = p.bn;
+        return GIM_OK;
+    }
     if (!make_act_map(&map_gy, gy, n, h, wd, cout, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(gy) failed");
     if (!make_act_map(&map_x, x, n, h, wd, cin, p.bw, p.bh, p.bn)) return fail(GIM_E_CUDA, "conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed");
-    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -1622,6 +1665,17 @@ int conv_wgrad_tc(const void* x, const void* gy, float* gw, int n, int h, int wd
     }
     conv_wgrad_tc_kernel<0><<<grid, 192, smem, st>>>(map_gy, map_x, gw, p);
     return check_launch("conv_wgrad_tc");
+}
+
+int conv_wgrad_tc_plan(int n, int h, int wd, int cin, int cout, int ks, int* out16) {
+    if (!out16) return fail(GIM_E_ARG, "conv_wgrad_plan: null output");
+    if (!wgrad_tc_supported(n, h, wd, cin, cout, ks, GIM_BF16)) return fail(GIM_E_UNSUPPORTED, "conv_wgrad_plan: shape not eligible for the tensor-core kernels");
+    for (int i = 0; i < 16; ++i) out16[i] = 0;
+    g_wplan = out16;
+    void* dummy = reinterpret_cast<void*>(static_cast<uintptr_t>(256));      // never dereferenced in a dry run
+    const int rc = conv_wgrad_tc(dummy, dummy, (float*)dummy, n, h, wd, cin, cout, ks, nullptr);
+    g_wplan = nullptr;
+    return rc;
 }
 
 }  // namespace gim

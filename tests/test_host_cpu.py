@@ -311,3 +311,37 @@ def test_conv_launch_plans_respect_the_hardware_limits():
     assert (pl["halo"], pl["pair"], pl["block_n"], pl["m_sub"]) == (0, 1, 128, 2), pl
     pl = C.conv_fwd_plan(640, 1, 1, 1536, 1024, 1)
     assert pl["persistent"] == 0 and pl["grid_x"] * pl["grid_y"] >= 148, pl
+
+
+def test_weight_gradient_launch_plans():
+    """gim_conv2d_wgrad_plan (dry run of the real launchers): shared memory, TMEM, split-K coverage, and the wave rule -- a grid never spills
+    a few CTAs into a third wave (every CTA owns an SM: 297 CTAs on 148 SMs cost three waves, 294 cost two)."""
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi as C
+    checked = 0
+    for hw in (1, 2, 4, 8, 13, 16, 26, 32, 64, 105):
+        for ci, co in ((64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 512), (512, 512), (512, 256), (256, 128), (1536, 1024), (16, 128),
+                       (128, 16), (320, 256), (32, 64), (72, 1000)):
+            for k in (1, 3, 9):
+                for n in (5, 80, 640):
+                    if n * hw * hw > 640 * 64 * 64 or not C.wgrad_tc_supported(n, hw, hw, ci, co, k, C.BF16):
+                        continue
+                    pl = C.conv_wgrad_plan(n, hw, hw, ci, co, k)
+                    tag = (n, hw, ci, co, k, pl)
+                    assert pl["smem_bytes"] <= 227 * 1024 and pl["stages"] >= 2 and pl["threads"] == 192, tag
+                    t = pl["tmem_cols"]
+                    assert 32 <= t <= 512 and (t & (t - 1)) == 0, tag
+                    assert pl["grid_y"] >= 1 and pl["tiles_per_split"] * pl["grid_y"] >= pl["pixel_tiles"], tag            # split-K covers every pixel tile
+                    assert pl["tiles_per_split"] * (pl["grid_y"] - 1) < pl["pixel_tiles"], tag                              # and no split is empty
+                    ctas = pl["grid_x"] * pl["grid_y"]
+                    if pl["grid_y"] > 1:
+                        assert ctas <= 2 * 148, tag                                                                         # at most two waves
+                    if pl["kernel"] == 3:
+                        assert k == 3 and co <= 128 and pl["taps_per_cta"] == 3, tag
+                    if pl["kernel"] == 2:
+                        assert co % 256 == 0 and ci % 128 == 0 and pl["grid_x"] % 2 == 0, tag
+                    checked += 1
+    assert checked > 500
+    hot = {(32, 128, 128): 294, (16, 256, 256): 288, (8, 512, 512): 288}
+    for (hw, ci, co), ctas in hot.items():
+        pl = C.conv_wgrad_plan(640, hw, hw, ci, co, 3)
+        assert pl["grid_x"] * pl["grid_y"] == ctas, pl
