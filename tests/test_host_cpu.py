@@ -246,6 +246,16 @@ def test_weight_gradient_streams_only_for_deferred_consumers():
     ops._wg_join()                                   # nothing in flight: a no-op that must not touch CUDA
 
 
+def _built_cabi():
+    """The ctypes stub over a built library (builds it first on a fresh checkout; compiling needs no GPU)."""
+    import os
+    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi as C
+    if not os.path.exists(C.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return C
+
+
 def test_conv_launch_plans_respect_the_hardware_limits():
     """gim_conv2d_fwd_plan (a dry run of the real launcher, no device needed) over every layer family of the O / V / 105x105 networks, small
     and benchmark-sized batches and every fused epilogue: shared memory <= 227 KB, TMEM <= 512 columns, ring depths, tile geometry, grid
@@ -316,7 +326,7 @@ def test_conv_launch_plans_respect_the_hardware_limits():
 def test_weight_gradient_launch_plans():
     """gim_conv2d_wgrad_plan (dry run of the real launchers): shared memory, TMEM, split-K coverage, and the wave rule -- a grid never spills
     a few CTAs into a third wave (every CTA owns an SM: 297 CTAs on 148 SMs cost three waves, 294 cost two)."""
-    from optimalstrategiesagainstgenerativeattacks_b200 import _cabi as C
+    C = _built_cabi()
     checked = 0
     for hw in (1, 2, 4, 8, 13, 16, 26, 32, 64, 105):
         for ci, co in ((64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 512), (512, 512), (512, 256), (256, 128), (1536, 1024), (16, 128),
